@@ -1,0 +1,463 @@
+// C ABI implementation: context, HBM-resident buffers, pass sequencing on one CUDA stream, readbacks.
+// Mirrors the resource ownership of the reference's Renderer (src/Renderer.cpp:100-111 G-buffers x2 ping-pong,
+// :673-761 reservoirs x2 + tmp + storage image, :1587-1691 lights + alias table, :1977-2040 ping-pong wiring)
+// and the call order of src/main.cpp:405-448.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vrs.h"
+#include "vrs_comm.h"
+#include "vrs_device.cuh"
+#include "vrs_grid.h"
+#include "vrs_kernels.h"
+
+using namespace vrs;
+
+struct vrs_ctx {
+  vrs_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint32_t W = 0, H = 0;
+  int band_y0 = 0, band_y1 = 0, store_y0 = 0, store_y1 = 0;
+  size_t npix = 0;                       // stored pixels = (store_y1 - store_y0) * W
+
+  float4* g_planes[2][4] = {{nullptr}};  // worldPos, albedo, normal, matProps
+  float4* r_planes[3][2] = {{nullptr}};  // info, weight
+  float4* accum = nullptr;
+  uint32_t* trace = nullptr;
+  int cur_g = 0;                         // Renderer::m_currentGBufferFrameIdx
+  int last_g = 0;
+  int final_r = 0;                       // reservoirs of the previous frame (temporal input)
+  int src_r = 0;                         // most recently written reservoir buffer inside the frame
+
+  HostGrid host_grid;
+  bool has_grid = false;
+  GridDev grid{};
+  std::vector<void*> grid_allocs;
+  uint64_t grid_bytes = 0;
+  float max_density = 0.f;
+
+  LightsDev lights{};
+  std::vector<vrs_alias_table_cell> alias_host;
+  void* d_lights = nullptr; void* d_alias = nullptr;
+
+  cudaEvent_t ev[8] = {nullptr};
+  vrs_timings timings{};
+  bool timings_valid = false;
+  Comm* comm = nullptr;
+};
+
+static std::string g_create_error;
+
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) {                                                                         \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+      return VRS_ERR_CUDA;                                                                           \
+    }                                                                                                \
+  } while (0)
+
+static vrs_status fail(vrs_ctx* ctx, vrs_status s, const std::string& msg) {
+  if (ctx) ctx->err = msg; else g_create_error = msg;
+  return s;
+}
+
+extern "C" {
+
+const char* vrs_last_error(const vrs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
+  if (!cfg || !out || cfg->width == 0 || cfg->height == 0) return fail(nullptr, VRS_ERR_INVALID, "vrs_create: bad config");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, VRS_ERR_NO_DEVICE, "vrs_create: no CUDA device (libvrs has no CPU fallback)");
+  vrs_ctx* ctx = new vrs_ctx();
+  ctx->cfg = *cfg;
+  auto bail = [&](vrs_status s) { g_create_error = ctx->err; vrs_destroy(ctx); return s; };
+  if (cfg->device >= 0) ctx->device = cfg->device; else if (cudaGetDevice(&ctx->device) != cudaSuccess) ctx->device = 0;
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(VRS_ERR_CUDA); }
+  ctx->W = cfg->width; ctx->H = cfg->height;
+  ctx->band_y0 = (int)cfg->band_y0; ctx->band_y1 = cfg->band_y1 ? (int)cfg->band_y1 : (int)cfg->height;
+  if (ctx->band_y1 > (int)ctx->H || ctx->band_y0 >= ctx->band_y1) { ctx->err = "vrs_create: bad band"; return bail(VRS_ERR_INVALID); }
+  if (cfg->spatial_iterations > VRS_MAX_SPATIAL_ITERATIONS) { ctx->err = "vrs_create: spatial_iterations > 4"; return bail(VRS_ERR_INVALID); }
+  ctx->store_y0 = ctx->band_y0 - (int)cfg->halo_rows; if (ctx->store_y0 < 0) ctx->store_y0 = 0;
+  ctx->store_y1 = ctx->band_y1 + (int)cfg->halo_rows; if (ctx->store_y1 > (int)ctx->H) ctx->store_y1 = (int)ctx->H;
+  ctx->npix = (size_t)(ctx->store_y1 - ctx->store_y0) * ctx->W;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (cudaMalloc(p, bytes) != cudaSuccess) { ctx->err = "cudaMalloc failed (" + std::to_string(bytes) + " bytes)"; return false; }
+    return cudaMemset(*p, 0, bytes) == cudaSuccess;
+  };
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
+  for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) if (!alloc((void**)&ctx->g_planes[i][p], ctx->npix * 16)) return bail(VRS_ERR_CUDA);
+  for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) if (!alloc((void**)&ctx->r_planes[i][p], ctx->npix * 16)) return bail(VRS_ERR_CUDA);
+  if (!alloc((void**)&ctx->accum, ctx->npix * 16)) return bail(VRS_ERR_CUDA);
+  if (cfg->enable_trace && !alloc((void**)&ctx->trace, ctx->npix * 16)) return bail(VRS_ERR_CUDA);
+  for (int i = 0; i < 8; ++i) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
+  cudaDeviceSynchronize();
+  *out = ctx;
+  return VRS_OK;
+}
+
+static void free_grid(vrs_ctx* ctx) {
+  for (void* p : ctx->grid_allocs) cudaFree(p);
+  ctx->grid_allocs.clear(); ctx->has_grid = false; ctx->grid_bytes = 0;
+}
+
+void vrs_destroy(vrs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm) comm_destroy(ctx->comm);
+  free_grid(ctx);
+  for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) cudaFree(ctx->g_planes[i][p]);
+  for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) cudaFree(ctx->r_planes[i][p]);
+  cudaFree(ctx->accum); cudaFree(ctx->trace); cudaFree(ctx->d_lights); cudaFree(ctx->d_alias);
+  for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+// ------------------------------------------------------------------------------------------ grid staging
+static vrs_status upload_grid(vrs_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  free_grid(ctx);
+  const HostGrid& h = ctx->host_grid;
+  if (h.nleaf() == 0 && h.active_voxels == 0) return fail(ctx, VRS_ERR_FORMAT, "grid has no active voxels");
+  GridDev& G = ctx->grid;
+  memset(&G, 0, sizeof(G));
+  for (int a = 0; a < 3; ++a) {
+    G.vmin[a] = (h.bbox_min[a] >> 3) << 3;
+    int vmax = ((h.bbox_max[a] >> 3) + 1) << 3;
+    G.vdim[a] = vmax - G.vmin[a];
+    G.cdim[a] = G.vdim[a] / 8;
+  }
+  G.bg_density = h.density_from_raw(h.background);
+  // world = world_scale * (voxel_size * ijk + translation) + world_translate   (Renderer.cpp:1420-1435)
+  G.A = (float)((double)ctx->cfg.world_scale * h.voxel_size);
+  G.invA = 1.0f / G.A;
+  for (int a = 0; a < 3; ++a) G.B[a] = (float)((double)ctx->cfg.world_scale * h.translation[a] + (double)ctx->cfg.world_translate[a]);
+  G.density_scale = ctx->cfg.density_scale;
+  G.roughness = ctx->cfg.roughness; G.metallic = ctx->cfg.metallic;
+  // densities: atlas + tile table + per-brick majorants
+  std::vector<float> atlas(h.leaf_value.size()), leaf_max(h.nleaf()), tile_density(h.tile_value.size());
+  float gmaxd = 0.f;
+  for (size_t l = 0; l < h.nleaf(); ++l) {
+    float m = 0.f;
+    for (int o = 0; o < 512; ++o) { float d = h.density_from_raw(h.leaf_value[l * 512 + o]); atlas[l * 512 + o] = d; if (d > m) m = d; }
+    leaf_max[l] = m; if (m > gmaxd) gmaxd = m;
+  }
+  for (size_t t = 0; t < h.tile_value.size(); ++t) { tile_density[t] = h.density_from_raw(h.tile_value[t]); if (tile_density[t] > gmaxd) gmaxd = tile_density[t]; }
+  ctx->max_density = gmaxd;
+  auto stage = [&](const void* src, size_t bytes, const void** dst) -> bool {
+    void* p = nullptr;
+    size_t sz = bytes ? bytes : 16;
+    if (cudaMalloc(&p, sz) != cudaSuccess) return false;
+    ctx->grid_allocs.push_back(p); ctx->grid_bytes += sz;
+    if (bytes && cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    *dst = p;
+    return true;
+  };
+  G.nroot = (int)(h.root.size() / 4);
+  bool ok = stage(h.root.data(), h.root.size() * 4, (const void**)&G.root) && stage(h.i5.data(), h.i5.size() * 4, (const void**)&G.i5) &&
+            stage(h.i4.data(), h.i4.size() * 4, (const void**)&G.i4) &&
+            stage(tile_density.data(), tile_density.size() * 4, (const void**)&G.tile_density) &&
+            stage(leaf_max.data(), leaf_max.size() * 4, (const void**)&G.leaf_max) && stage(atlas.data(), atlas.size() * 4, (const void**)&G.atlas);
+  if (!ok) { free_grid(ctx); return fail(ctx, VRS_ERR_CUDA, "grid staging failed"); }
+  ctx->has_grid = true;
+  return VRS_OK;
+}
+
+vrs_status vrs_load_vdb(vrs_ctx* ctx, const char* path, const char* grid_name) {
+  if (!ctx || !path) return VRS_ERR_INVALID;
+  std::string p(path), err;
+  if (p.size() > 5 && p.compare(p.size() - 5, 5, ".vrsg") == 0) return vrs_load_vrsg(ctx, path);
+  if (!read_vdb(p, grid_name, ctx->host_grid, err)) {
+    bool io = err.rfind("cannot open", 0) == 0 || err.rfind("short read", 0) == 0;
+    return fail(ctx, io ? VRS_ERR_IO : VRS_ERR_FORMAT, err);
+  }
+  return upload_grid(ctx);
+}
+vrs_status vrs_load_vrsg(vrs_ctx* ctx, const char* path) {
+  if (!ctx || !path) return VRS_ERR_INVALID;
+  std::string err;
+  if (!read_vrsg(path, ctx->host_grid, err)) return fail(ctx, err.rfind("cannot open", 0) == 0 ? VRS_ERR_IO : VRS_ERR_FORMAT, err);
+  return upload_grid(ctx);
+}
+vrs_status vrs_convert_vdb(const char* vdb_path, const char* grid_name, const char* vrsg_path) {
+  if (!vdb_path || !vrsg_path) return VRS_ERR_INVALID;
+  HostGrid g; std::string err;
+  if (!read_vdb(vdb_path, grid_name, g, err)) return fail(nullptr, err.rfind("cannot open", 0) == 0 ? VRS_ERR_IO : VRS_ERR_FORMAT, err);
+  if (!write_vrsg(vrsg_path, g, err)) return fail(nullptr, VRS_ERR_IO, err);
+  return VRS_OK;
+}
+vrs_status vrs_make_procedural_grid(vrs_ctx* ctx, int kind, uint32_t resolution) {
+  if (!ctx) return VRS_ERR_INVALID;
+  std::string err;
+  if (!make_procedural(kind, resolution, ctx->host_grid, err)) return fail(ctx, VRS_ERR_INVALID, err);
+  return upload_grid(ctx);
+}
+
+vrs_status vrs_get_grid_info(const vrs_ctx* ctx, vrs_grid_info* o) {
+  if (!ctx || !o || !ctx->has_grid) return VRS_ERR_INVALID;
+  const HostGrid& h = ctx->host_grid;
+  memset(o, 0, sizeof(*o));
+  for (int a = 0; a < 3; ++a) { o->bbox_min[a] = h.bbox_min[a]; o->bbox_max[a] = h.bbox_max[a]; o->translation[a] = h.translation[a]; }
+  o->active_voxels = h.active_voxels; o->root_children = h.root_children; o->internal5 = (uint32_t)h.n5(); o->internal4 = (uint32_t)h.n4();
+  o->leaves = (uint32_t)h.nleaf(); o->tiles = (uint32_t)h.tile_value.size(); o->voxel_size = h.voxel_size; o->background = h.background;
+  o->is_level_set = h.level_set ? 1 : 0; o->max_density = ctx->max_density; o->device_bytes = ctx->grid_bytes;
+  const GridDev& G = ctx->grid;
+  for (int a = 0; a < 3; ++a) {
+    o->world_bbox_min[a] = G.A * ((float)G.vmin[a] - 0.5f) + G.B[a];
+    o->world_bbox_max[a] = G.A * ((float)(G.vmin[a] + G.vdim[a]) - 0.5f) + G.B[a];
+  }
+  return VRS_OK;
+}
+vrs_status vrs_grid_get_value(const vrs_ctx* ctx, int32_t i, int32_t j, int32_t k, float* value, int32_t* active) {
+  if (!ctx || !ctx->has_grid || !value) return VRS_ERR_INVALID;
+  bool a = false;
+  *value = ctx->host_grid.get_value(i, j, k, &a);
+  if (active) *active = a ? 1 : 0;
+  return VRS_OK;
+}
+vrs_status vrs_grid_sample_device(vrs_ctx* ctx, const int32_t* ijk, uint32_t n, float* out) {
+  if (!ctx || !ctx->has_grid || !ijk || !out) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  int* d_ijk = nullptr; float* d_out = nullptr;
+  CK(cudaMalloc(&d_ijk, (size_t)n * 12)); CK(cudaMalloc(&d_out, (size_t)n * 4));
+  CK(cudaMemcpyAsync(d_ijk, ijk, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  launch_sample_density(ctx->stream, ctx->grid, d_ijk, n, d_out);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_ijk); cudaFree(d_out);
+  return VRS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ lights
+vrs_status vrs_set_lights(vrs_ctx* ctx, const vrs_point_light* lights, uint32_t n) {
+  if (!ctx || !lights || n == 0) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  std::vector<float> pdf(n);
+  for (uint32_t i = 0; i < n; ++i) pdf[i] = lights[i].emission_luminance[3];      // Renderer.cpp:1653-1657
+  ctx->alias_host.resize(n);
+  vrs_create_alias_table(pdf.data(), n, ctx->alias_host.data());
+  cudaFree(ctx->d_lights); cudaFree(ctx->d_alias); ctx->d_lights = ctx->d_alias = nullptr;
+  CK(cudaMalloc(&ctx->d_lights, (size_t)n * sizeof(vrs_point_light)));
+  CK(cudaMalloc(&ctx->d_alias, (size_t)n * sizeof(vrs_alias_table_cell)));
+  CK(cudaMemcpy(ctx->d_lights, lights, (size_t)n * sizeof(vrs_point_light), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ctx->d_alias, ctx->alias_host.data(), (size_t)n * sizeof(vrs_alias_table_cell), cudaMemcpyHostToDevice));
+  ctx->lights.lights = (const float4*)ctx->d_lights; ctx->lights.alias = (const float4*)ctx->d_alias;
+  ctx->lights.nlights = (int)n; ctx->lights.ntable = (int)n;
+  return VRS_OK;
+}
+vrs_status vrs_set_triangle_lights(vrs_ctx* ctx, const vrs_triangle_light*, uint32_t) {
+  return fail(ctx, VRS_ERR_UNSUPPORTED, "triangle lights belong to the mesh path (SURVEY.md §8f rank 4), not the volume hot path");
+}
+vrs_status vrs_get_alias_table(const vrs_ctx* ctx, vrs_alias_table_cell* out, uint32_t n) {
+  if (!ctx || !out || n != ctx->alias_host.size()) return VRS_ERR_INVALID;
+  memcpy(out, ctx->alias_host.data(), n * sizeof(vrs_alias_table_cell));
+  return VRS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ per-frame
+static Planes planes_of(vrs_ctx* ctx, int i) { Planes p; p.worldPos = ctx->g_planes[i][0]; p.albedo = ctx->g_planes[i][1]; p.normal = ctx->g_planes[i][2]; p.mat = ctx->g_planes[i][3]; return p; }
+static ResPlanes res_of(vrs_ctx* ctx, int i) { ResPlanes r; r.info = ctx->r_planes[i][0]; r.weight = ctx->r_planes[i][1]; return r; }
+
+static vrs_status make_params(vrs_ctx* ctx, const vrs_global_uniforms* gu, const vrs_restir_uniforms* ru, const vrs_push_constant_restir* pc,
+                              uint32_t clock, FrameParams& F) {
+  if (!ctx->has_grid) return fail(ctx, VRS_ERR_INVALID, "no grid loaded");
+  if (!ctx->d_lights) return fail(ctx, VRS_ERR_INVALID, "no lights set");
+  if (ru->screenSize[0] != ctx->W || ru->screenSize[1] != ctx->H) return fail(ctx, VRS_ERR_INVALID, "RestirUniforms.screenSize != context size");
+  if (ru->aliasTableCount != ctx->lights.ntable || ru->pointLightCount != ctx->lights.nlights)
+    return fail(ctx, VRS_ERR_INVALID, "RestirUniforms light counts != uploaded lights");
+  if (ru->triangleLightCount > 1) return fail(ctx, VRS_ERR_UNSUPPORTED, "triangle lights are outside the volume hot path");
+  memset(&F, 0, sizeof(F));
+  if (gu) { memcpy(F.viewInverse, gu->viewInverse, 64); memcpy(F.projInverse, gu->projInverse, 64); }
+  memcpy(F.prevVP, ru->prevFrameProjectionViewMatrix, 64);
+  for (int a = 0; a < 3; ++a) F.camPos[a] = ru->currCamPos[a];
+  F.W = ctx->W; F.H = ctx->H; F.M = ru->initialLightSampleCount; F.temporalMult = ru->temporalSampleCountMultiplier;
+  F.spatialNeighbors = ru->spatialNeighbors; F.spatialRadius = ru->spatialRadius; F.fireflyClamp = ru->fireflyClampThreshold;
+  F.flags = ru->flags; F.clock = clock;
+  if (pc) { F.clear[0] = pc->clearColorRed; F.clear[1] = pc->clearColorGreen; F.clear[2] = pc->clearColorBlue; F.frame = pc->frame; F.initialize = pc->initialize; }
+  return VRS_OK;
+}
+
+static vrs_status exchange(vrs_ctx* ctx, bool gbuf, int g_index, int r_index) {
+  if (!ctx->comm) return VRS_OK;
+  std::vector<float4*> planes;
+  if (gbuf) for (int p = 0; p < 4; ++p) planes.push_back(ctx->g_planes[g_index][p]);
+  if (r_index >= 0) for (int p = 0; p < 2; ++p) planes.push_back(ctx->r_planes[r_index][p]);
+  std::string err;
+  if (!comm_exchange_halo(ctx->comm, ctx->stream, planes, ctx->W, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1, (int)ctx->H, err))
+    return fail(ctx, VRS_ERR_COMM, err);
+  return VRS_OK;
+}
+
+vrs_status vrs_pass_initial(vrs_ctx* ctx, const vrs_global_uniforms* gu, const vrs_restir_uniforms* ru, uint32_t clock) {
+  if (!ctx || !gu || !ru) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  FrameParams F; vrs_status s = make_params(ctx, gu, ru, nullptr, clock, F); if (s) return s;
+  int out = (ctx->final_r + 1) % 3;
+  launch_initial(ctx->stream, ctx->grid, ctx->lights, F, planes_of(ctx, ctx->cur_g), planes_of(ctx, 1 - ctx->cur_g), res_of(ctx, ctx->final_r),
+                 res_of(ctx, out), ctx->trace, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1);
+  CK(cudaGetLastError());
+  ctx->src_r = out; ctx->timings.launches += 1;
+  return VRS_OK;
+}
+vrs_status vrs_pass_spatial(vrs_ctx* ctx, const vrs_restir_uniforms* ru, uint32_t clock, uint32_t iteration) {
+  if (!ctx || !ru || iteration >= VRS_MAX_SPATIAL_ITERATIONS) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  FrameParams F; vrs_status s = make_params(ctx, nullptr, ru, nullptr, clock, F); if (s) return s;
+  int dst = (ctx->src_r + 1) % 3;
+  launch_spatial(ctx->stream, ctx->lights, F, planes_of(ctx, ctx->cur_g), res_of(ctx, ctx->src_r), res_of(ctx, dst), iteration, ctx->band_y0,
+                 ctx->band_y1, ctx->store_y0, ctx->store_y1);
+  CK(cudaGetLastError());
+  ctx->src_r = dst; ctx->timings.launches += 1;
+  return VRS_OK;
+}
+vrs_status vrs_pass_shade(vrs_ctx* ctx, const vrs_restir_uniforms* ru, const vrs_push_constant_restir* pc, uint32_t clock) {
+  if (!ctx || !ru || !pc) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  FrameParams F; vrs_status s = make_params(ctx, nullptr, ru, pc, clock, F); if (s) return s;
+  launch_shade(ctx->stream, ctx->grid, ctx->lights, F, planes_of(ctx, ctx->cur_g), res_of(ctx, ctx->src_r), ctx->accum, ctx->band_y0, ctx->band_y1,
+               ctx->store_y0);
+  CK(cudaGetLastError());
+  ctx->final_r = ctx->src_r; ctx->last_g = ctx->cur_g; ctx->cur_g = 1 - ctx->cur_g;   // updateGBufferFrameIdx, Renderer.cpp:108-111
+  ctx->timings.launches += 1;
+  return VRS_OK;
+}
+
+vrs_status vrs_render_frame(vrs_ctx* ctx, const vrs_global_uniforms* gu, const vrs_restir_uniforms* ru, const vrs_push_constant_restir* pc, uint32_t clock) {
+  if (!ctx || !gu || !ru || !pc) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  ctx->timings.launches = 0;
+  vrs_status s;
+  CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if ((s = vrs_pass_initial(ctx, gu, ru, clock))) return s;                         // main.cpp:405-409
+  CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+  const bool spatial = (ru->flags & VRS_RESTIR_SPATIAL_REUSE_FLAG) != 0 && ctx->cfg.spatial_iterations > 0;
+  if (ctx->comm && spatial && (s = exchange(ctx, true, ctx->cur_g, ctx->src_r))) return s;
+  CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (spatial) {
+    for (uint32_t it = 0; it < ctx->cfg.spatial_iterations; ++it) {                 // main.cpp:410-413
+      if ((s = vrs_pass_spatial(ctx, ru, clock, it))) return s;
+      if (ctx->comm && it + 1 < ctx->cfg.spatial_iterations && (s = exchange(ctx, false, 0, ctx->src_r))) return s;
+    }
+  }
+  CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+  int g_this = ctx->cur_g;
+  if ((s = vrs_pass_shade(ctx, ru, pc, clock))) return s;                           // main.cpp:416-433
+  CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+  // next frame's temporal reuse reads this frame's G-buffer and final reservoirs in the halo rows
+  if (ctx->comm && (ru->flags & VRS_RESTIR_TEMPORAL_REUSE_FLAG) && (s = exchange(ctx, !spatial, g_this, ctx->final_r))) return s;
+  CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+  ctx->timings_valid = true;
+  return VRS_OK;
+}
+
+vrs_status vrs_synchronize(vrs_ctx* ctx) {
+  if (!ctx) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VRS_OK;
+}
+
+vrs_status vrs_get_timings(vrs_ctx* ctx, vrs_timings* out) {
+  if (!ctx || !out || !ctx->timings_valid) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CK(cudaEventSynchronize(ctx->ev[5]));
+  float a, b, c, d, e;
+  CK(cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[1])); CK(cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]));
+  CK(cudaEventElapsedTime(&c, ctx->ev[2], ctx->ev[3])); CK(cudaEventElapsedTime(&d, ctx->ev[3], ctx->ev[4]));
+  CK(cudaEventElapsedTime(&e, ctx->ev[4], ctx->ev[5]));
+  ctx->timings.initial_ms = a; ctx->timings.spatial_ms = c; ctx->timings.shade_ms = d; ctx->timings.exchange_ms = b + e;
+  ctx->timings.frame_ms = a + b + c + d + e;
+  *out = ctx->timings;
+  return VRS_OK;
+}
+void* vrs_stream(vrs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ------------------------------------------------------------------------------------------ readback
+static vrs_status read_plane(vrs_ctx* ctx, const void* dev, void* host, size_t elem) {
+  if (!host) return VRS_OK;
+  size_t off = (size_t)(ctx->band_y0 - ctx->store_y0) * ctx->W * elem;
+  size_t bytes = (size_t)(ctx->band_y1 - ctx->band_y0) * ctx->W * elem;
+  CK(cudaMemcpyAsync(host, (const char*)dev + off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return VRS_OK;
+}
+vrs_status vrs_read_frame(vrs_ctx* ctx, float* rgba) {
+  if (!ctx || !rgba) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  vrs_status s = read_plane(ctx, ctx->accum, rgba, 16); if (s) return s;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VRS_OK;
+}
+vrs_status vrs_read_gbuffer(vrs_ctx* ctx, float* worldPos, float* albedo, float* normal, float* matProps) {
+  if (!ctx) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  float* dst[4] = {worldPos, albedo, normal, matProps};
+  for (int p = 0; p < 4; ++p) { vrs_status s = read_plane(ctx, ctx->g_planes[ctx->last_g][p], dst[p], 16); if (s) return s; }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VRS_OK;
+}
+vrs_status vrs_read_reservoirs(vrs_ctx* ctx, float* info, float* weight) {
+  if (!ctx) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  vrs_status s = read_plane(ctx, ctx->r_planes[ctx->src_r][0], info, 16); if (s) return s;
+  s = read_plane(ctx, ctx->r_planes[ctx->src_r][1], weight, 16); if (s) return s;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VRS_OK;
+}
+vrs_status vrs_read_trace(vrs_ctx* ctx, uint32_t* trace4) {
+  if (!ctx || !trace4 || !ctx->trace) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  vrs_status s = read_plane(ctx, ctx->trace, trace4, 16); if (s) return s;
+  CK(cudaStreamSynchronize(ctx->stream));
+  return VRS_OK;
+}
+
+vrs_status vrs_write_image(vrs_ctx* ctx, const char* path) {
+  if (!ctx || !path) return VRS_ERR_INVALID;
+  size_t rows = (size_t)(ctx->band_y1 - ctx->band_y0), n = rows * ctx->W;
+  std::vector<float> img(n * 4);
+  vrs_status s = vrs_read_frame(ctx, img.data()); if (s) return s;
+  std::string p(path);
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(ctx, VRS_ERR_IO, "cannot write " + p);
+  if (p.size() > 4 && p.compare(p.size() - 4, 4, ".pfm") == 0) {
+    fprintf(f, "PF\n%u %zu\n-1.0\n", ctx->W, rows);
+    for (size_t y = rows; y-- > 0;) for (uint32_t x = 0; x < ctx->W; ++x) fwrite(&img[(y * ctx->W + x) * 4], 4, 3, f);
+  } else {
+    fprintf(f, "P6\n%u %zu\n255\n", ctx->W, rows);
+    for (size_t i = 0; i < n; ++i) for (int c = 0; c < 3; ++c) {
+      float v = powf(img[i * 4 + c] < 0.f ? 0.f : img[i * 4 + c], 1.0f / 0.8f);      // restir_post.frag:104
+      v = v > 1.f ? 1.f : v;
+      fputc((int)(v * 255.f + 0.5f), f);
+    }
+  }
+  fclose(f);
+  return VRS_OK;
+}
+
+// ------------------------------------------------------------------------------------------ multi-GPU
+vrs_status vrs_comm_unique_id(uint8_t id128[128]) {
+  std::string err;
+  if (!comm_unique_id(id128, err)) return fail(nullptr, VRS_ERR_COMM, err);
+  return VRS_OK;
+}
+vrs_status vrs_comm_init(vrs_ctx* ctx, const uint8_t id128[128], int rank, int nranks) {
+  if (!ctx || !id128 || rank < 0 || rank >= nranks) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  std::string err;
+  ctx->comm = comm_create(id128, rank, nranks, err);
+  if (!ctx->comm) return fail(ctx, VRS_ERR_COMM, err);
+  return VRS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,422 @@
+// Device-side math of the volumetric ReSTIR hot path (sm_100a).
+//
+// Everything here is fp32 evaluated in the order written; the translation unit is compiled with
+// -fmad=false (no FMA contraction), IEEE division and square root, no fast-math, so that integer state
+// (RNG streams, voxel / leaf indices, chosen light indices) is bit-exact against the CPU oracle.
+// Citations are relative to the reference root (TheSmokeyGuys/Volume-ReSTIR-Vulkan).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vrs {
+
+// ------------------------------------------------------------------ scene tables staged in HBM
+struct GridDev {
+  int vmin[3], vdim[3], cdim[3];  // leaf-aligned active window (voxels / 8^3 cells)
+  float bg_density;
+  float A, invA, B[3];            // world = A * ijk + B
+  float density_scale;
+  float roughness, metallic;
+  int nroot;
+  const int4* root;               // {origin xyz, child}: child >= 0 internal5 node, < 0 ~tile
+  const int* i5;                  // [n5][32768]  >= 0 internal4 node, < 0 ~tile
+  const int* i4;                  // [n4][4096]   >= 0 leaf, < 0 ~tile
+  const float* tile_density;      // [ntile], tile 0 = background
+  const float* leaf_max;          // [nleaf] majorant density of the brick
+  const float* atlas;             // [nleaf][512] densities, offset (x<<6)|(y<<3)|z
+};
+
+struct LightsDev {
+  const float4* lights;           // 2 x float4 per PointLight (host_device.h:184-187)
+  const float4* alias;            // AliasTableCell as 16 bytes {alias, prob, pdf, aliasPdf} (:197-202)
+  int nlights, ntable;
+};
+
+struct FrameParams {
+  float viewInverse[16], projInverse[16];
+  float prevVP[16];
+  float camPos[3];
+  uint32_t W, H;
+  uint32_t M;                     // initialLightSampleCount
+  int temporalMult;
+  uint32_t spatialNeighbors;
+  float spatialRadius;
+  float fireflyClamp;
+  int flags;
+  uint32_t clock;
+  float clear[3];
+  int frame, initialize;
+};
+
+struct Planes {                   // band-local RGBA32F planes (reference layouts)
+  float4* worldPos; float4* albedo; float4* normal; float4* mat;
+};
+struct ResPlanes { float4* info; float4* weight; };
+
+// ------------------------------------------------------------------ small vector helpers
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 add(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 sub(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 mul(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ V3 muls(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 divs(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 normalize(V3 a) { return divs(a, sqrtf(dot(a, a))); }
+__device__ __forceinline__ float gmax(float a, float b) { return a < b ? b : a; }   // GLSL max
+__device__ __forceinline__ float gmin(float a, float b) { return b < a ? b : a; }   // GLSL min
+__device__ __forceinline__ float gclamp(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
+__device__ __forceinline__ float gmix(float x, float y, float a) { return x * (1.0f - a) + y * a; }
+
+#define VRS_PI 3.1415926535897932384626433832795f   /* headers/math.glsl:1 */
+
+// ------------------------------------------------------------------ RNG: headers/random.glsl
+__device__ __forceinline__ uint32_t lcg(uint32_t& prev) {          // :58-63
+  prev = 1664525u * prev + 1013904223u;
+  return prev & 0x00FFFFFFu;
+}
+__device__ __forceinline__ float rnd(uint32_t& seed) {             // :90-99, RAND_LCG
+  return float(lcg(seed)) / 16777216.0f;
+}
+__device__ __forceinline__ uint32_t pixel_seed(uint32_t px, uint32_t py, uint32_t clock, uint32_t pass) {
+  // pcg2d (:73-87) of pixel * K, K = clock*8 + pass + 1 replacing int(clockARB()) (restir.rgen:139)
+  uint32_t K = clock * 8u + pass + 1u;
+  uint32_t x = px * K, y = py * K;
+  x = x * 1664525u + 1013904223u;
+  y = y * 1664525u + 1013904223u;
+  x += y * 1664525u;
+  y += x * 1664525u;
+  x = x ^ (x >> 16u);
+  y = y ^ (y >> 16u);
+  x += y * 1664525u;
+  y += x * 1664525u;
+  x = x ^ (x >> 16u);
+  y = y ^ (y >> 16u);
+  return x + y;
+}
+
+__device__ __forceinline__ float luminance_common(float r, float g, float b) {   // headers/common.glsl:5-7
+  return 0.2126f * r + 0.7152f * g + 0.0722f * b;
+}
+__device__ __forceinline__ float luminance_utils(V3 v) {                          // headers/restirUtils.glsl:6-8
+  return dot(v, v3(0.212671f, 0.715160f, 0.072169f));
+}
+
+// ------------------------------------------------------------------ Disney BRDF: headers/disneyBRDF.glsl
+__device__ __forceinline__ float schlickFresnel(float c) {                       // :6-10
+  float m = gclamp(1.0f - c, 0.0f, 1.0f);
+  float sm = m * m;
+  return sm * sm * m;
+}
+__device__ __forceinline__ float GTR2(float NdotH, float a) {                    // :13-17
+  float a2 = a * a;
+  float t = 1.0f + (a2 - 1.0f) * NdotH * NdotH;
+  return a2 / (VRS_PI * t * t);
+}
+__device__ __forceinline__ float smithG_GGX(float NdotV, float alphaG) {         // :19-23
+  float a = alphaG * alphaG;
+  float b = NdotV * NdotV;
+  return 1.0f / (fabsf(NdotV) + gmax(sqrtf(a + b - a * b), 0.0001f));
+}
+__device__ __forceinline__ float diffuseFactor(float cosIn, float cosOut, float cosInHalf, float roughness, float metallic) {  // :25-33
+  float fresnelIn = schlickFresnel(cosIn);
+  float fresnelOut = schlickFresnel(cosOut);
+  float fd90 = 0.5f + 2.0f * cosInHalf * cosInHalf * roughness;
+  float fd = gmix(1.0f, fd90, fresnelIn) * gmix(1.0f, fd90, fresnelOut);
+  return fd * (1.0f - metallic) / VRS_PI;
+}
+__device__ __forceinline__ void specularFactors(float cosIn, float cosOut, float cosHalf, float cosInHalf, float roughness,
+                                                float& fresnelInHalf, float& GsDs) {                                          // :47-62
+  fresnelInHalf = schlickFresnel(cosInHalf);
+  float a = gmax(0.001f, roughness * roughness);
+  float Ds = GTR2(cosHalf, a);
+  float Gs = smithG_GGX(cosIn, a);
+  Gs *= smithG_GGX(cosOut, a);
+  GsDs = Gs * Ds;
+}
+__device__ __forceinline__ float disneyBrdfLuminance(float cosIn, float cosOut, float cosHalf, float cosInHalf, float lum,
+                                                     float roughness, float metallic) {                                       // :98-110
+  if (cosIn < 0.0f) return 0.0f;
+  float diffuse = lum * diffuseFactor(cosIn, cosOut, cosInHalf, roughness, metallic);
+  float fih, gsds;
+  specularFactors(cosIn, cosOut, cosHalf, cosInHalf, roughness, fih, gsds);
+  float specLum = gmix(0.04f, lum, metallic);
+  float Fs = gmix(specLum, 1.0f, fih);
+  float specular = Fs * gsds;
+  return diffuse + specular;
+}
+__device__ __forceinline__ V3 disneyBrdfColor(float cosIn, float cosOut, float cosHalf, float cosInHalf, V3 albedo,
+                                              float roughness, float metallic) {                                              // :86-97
+  if (cosIn < 0.0f) return v3(0.0f, 0.0f, 0.0f);
+  V3 diffuse = muls(albedo, diffuseFactor(cosIn, cosOut, cosInHalf, roughness, metallic));
+  float fih, gsds;
+  specularFactors(cosIn, cosOut, cosHalf, cosInHalf, roughness, fih, gsds);
+  V3 specColor = v3(gmix(0.04f, albedo.x, metallic), gmix(0.04f, albedo.y, metallic), gmix(0.04f, albedo.z, metallic));
+  V3 Fs = v3(gmix(specColor.x, 1.0f, fih), gmix(specColor.y, 1.0f, fih), gmix(specColor.z, 1.0f, fih));
+  V3 specular = muls(Fs, gsds);
+  return add(diffuse, specular);
+}
+
+// ------------------------------------------------------------------ GeometryInfo / Reservoir: structs/restirStructs.glsl
+struct GInfo {
+  V3 camPos, worldPos, normal;
+  float albedo[4];
+  float albedoLum, roughness, metallic;
+  uint32_t sampleSeed;
+};
+struct Res {
+  uint32_t M, lightIndex; int32_t lightKind; uint32_t sampleSeed;
+  float pHat, sumWeights, w;
+};
+__device__ __forceinline__ Res newReservoir() {                                  // reservoir.glsl:92-100
+  Res r; r.M = 0; r.lightIndex = 0; r.lightKind = 0; r.sampleSeed = 0; r.pHat = 0.0f; r.sumWeights = 0.0f; r.w = 0.0f;
+  return r;
+}
+__device__ __forceinline__ Res unpackReservoir(float4 info, float4 weight) {     // reservoir.glsl:4-16
+  Res r;
+  r.M = __float_as_uint(info.x); r.lightIndex = __float_as_uint(info.y);
+  r.lightKind = __float_as_int(info.z); r.sampleSeed = __float_as_uint(info.w);
+  r.pHat = weight.x; r.sumWeights = weight.y; r.w = weight.z;
+  return r;
+}
+__device__ __forceinline__ void packReservoir(const Res& r, float4& info, float4& weight) {   // reservoir.glsl:18-28
+  info = make_float4(__uint_as_float(r.M), __uint_as_float(r.lightIndex), __int_as_float(r.lightKind), __uint_as_float(r.sampleSeed));
+  weight = make_float4(r.pHat, r.sumWeights, r.w, 0.0f);
+}
+
+// ------------------------------------------------------------------ p-hat: headers/restirUtils.glsl (point lights)
+struct PHatGeom { V3 wi; float cosIn, cosOut, cosHalf, cosInHalf, geometry; bool back; };
+__device__ __forceinline__ PHatGeom phat_geometry(V3 lightPos, const GInfo& g) {  // :39-71
+  PHatGeom o;
+  V3 wi = sub(lightPos, g.worldPos);
+  o.back = dot(wi, g.normal) < 0.0f;
+  float sqrDist = dot(wi, wi);
+  wi = divs(wi, sqrtf(sqrDist));
+  V3 wo = normalize(sub(g.camPos, g.worldPos));
+  o.cosIn = dot(g.normal, wi);
+  o.cosOut = dot(g.normal, wo);
+  V3 halfVec = normalize(add(wi, wo));
+  o.cosHalf = dot(g.normal, halfVec);
+  o.cosInHalf = dot(wi, halfVec);
+  o.geometry = 1.0f * o.cosIn / sqrDist;
+  o.wi = wi;
+  return o;
+}
+__device__ __forceinline__ float evaluatePHat(const LightsDev& L, uint32_t lightIdx, const GInfo& g) {   // :36-78
+  float4 lp = __ldg(&L.lights[2 * lightIdx]);
+  float4 le = __ldg(&L.lights[2 * lightIdx + 1]);
+  PHatGeom q = phat_geometry(v3(lp.x, lp.y, lp.z), g);
+  if (q.back) return 0.0f;
+  return le.w * disneyBrdfLuminance(q.cosIn, q.cosOut, q.cosHalf, q.cosInHalf, g.albedoLum, g.roughness, g.metallic) * q.geometry;
+}
+__device__ __forceinline__ V3 evaluatePHatFull(const LightsDev& L, uint32_t lightIdx, const GInfo& g) {  // :80-122
+  float4 lp = __ldg(&L.lights[2 * lightIdx]);
+  float4 le = __ldg(&L.lights[2 * lightIdx + 1]);
+  PHatGeom q = phat_geometry(v3(lp.x, lp.y, lp.z), g);
+  if (q.back) return v3(0.0f, 0.0f, 0.0f);
+  V3 brdf = disneyBrdfColor(q.cosIn, q.cosOut, q.cosHalf, q.cosInHalf, v3(g.albedo[0], g.albedo[1], g.albedo[2]), g.roughness, g.metallic);
+  return muls(mul(v3(le.x, le.y, le.z), brdf), q.geometry);
+}
+
+// ------------------------------------------------------------------ reservoir ops: headers/reservoir.glsl
+__device__ __forceinline__ void updateReservoir(Res& res, uint32_t lightIdx, int32_t lightKind, float weight, float pHat, float w,
+                                                uint32_t& seed, uint32_t sampleSeed) {            // :30-43
+  res.sumWeights += weight;
+  float replacePossibility = weight / res.sumWeights;
+  if (rnd(seed) < replacePossibility) {
+    res.lightIndex = lightIdx; res.lightKind = lightKind; res.pHat = pHat; res.w = w; res.sampleSeed = sampleSeed;
+  }
+}
+__device__ __forceinline__ void addSampleToReservoir(const LightsDev& L, Res& res, uint32_t lightIdx, int32_t lightKind,
+                                                     float lightPdf, const GInfo& g, uint32_t& seed) {   // :45-54
+  float pHat = evaluatePHat(L, lightIdx, g);
+  float weight = pHat / lightPdf;
+  res.M += 1;
+  float w = (res.sumWeights + weight) / (float(res.M) * pHat);
+  updateReservoir(res, lightIdx, lightKind, weight, pHat, w, seed, g.sampleSeed);
+}
+__device__ __forceinline__ void combineReservoirsGeom(const LightsDev& L, Res& self, const Res& other, const GInfo& g,
+                                                      const GInfo& og, uint32_t& seed) {          // :56-76
+  uint32_t Z = self.M;
+  self.M += other.M;
+  float pHat = evaluatePHat(L, other.lightIndex, g);
+  float weight = pHat * other.w * float(other.M);
+  if (weight > 0.0f) updateReservoir(self, other.lightIndex, other.lightKind, weight, pHat, other.w, seed, other.sampleSeed);
+  pHat = evaluatePHat(L, self.lightIndex, og);
+  if (pHat > 0.0f) Z += other.M;
+  if (self.w > 0.0f) self.w = self.sumWeights / (float(Z) * self.pHat);
+}
+
+__device__ __forceinline__ void aliasTableSample(const LightsDev& L, float r1, float r2, uint32_t& index, float& prob) {   // restir.rgen:97-110
+  uint32_t col = uint32_t(float(L.ntable) * r1);
+  uint32_t last = uint32_t(L.ntable - 1);
+  if (last < col) col = last;
+  float4 c = __ldg(&L.alias[col]);
+  if (c.y > r2) { index = col; prob = c.z; } else { index = (uint32_t)__float_as_int(c.x); prob = c.w; }
+}
+
+// ------------------------------------------------------------------ sparse grid lookups (flattened Tree_float_5_4_3)
+// Returns leaf index (>= 0) or ~tile (< 0) for the 8^3 cell containing absolute voxel (x,y,z).
+__device__ __forceinline__ int cell_lookup(const GridDev& G, int x, int y, int z) {
+  int kx = x & ~4095, ky = y & ~4095, kz = z & ~4095;
+  int n5 = -1;
+  for (int r = 0; r < G.nroot; ++r) {
+    int4 e = __ldg(&G.root[r]);
+    if (e.x == kx && e.y == ky && e.z == kz) { n5 = e.w; break; }
+  }
+  if (n5 < 0) return n5;                                      // ~tile (missing root key = ~0 = background)
+  int s5 = (((x & 4095) >> 7) << 10) | (((y & 4095) >> 7) << 5) | ((z & 4095) >> 7);
+  int n4 = __ldg(&G.i5[(size_t)n5 * 32768 + s5]);
+  if (n4 < 0) return n4;
+  int s4 = (((x & 127) >> 3) << 8) | (((y & 127) >> 3) << 4) | ((z & 127) >> 3);
+  return __ldg(&G.i4[(size_t)n4 * 4096 + s4]);
+}
+__device__ __forceinline__ float density_at(const GridDev& G, int i, int j, int k) {
+  int x = i - G.vmin[0], y = j - G.vmin[1], z = k - G.vmin[2];
+  if (x < 0 || y < 0 || z < 0 || x >= G.vdim[0] || y >= G.vdim[1] || z >= G.vdim[2]) return G.bg_density;
+  int c = cell_lookup(G, i, j, k);
+  if (c < 0) return __ldg(&G.tile_density[~c]);
+  return __ldg(&G.atlas[(size_t)c * 512 + (((i & 7) << 6) | ((j & 7) << 3) | (k & 7))]);
+}
+
+__device__ __forceinline__ float neglog1m(float u) {   // -ln(1-u) with + - * / only
+  float x = 1.0f - u;
+  uint32_t bits = __float_as_uint(x);
+  int e = int(bits >> 23) - 127;
+  float m = __uint_as_float((bits & 0x007FFFFFu) | 0x3F800000u);
+  if (m > 1.41421356f) { m = m * 0.5f; e = e + 1; }
+  float f = m - 1.0f;
+  float s = f / (2.0f + f);
+  float z = s * s;
+  float p = 0.18181818f;
+  p = p * z + 0.22222222f;
+  p = p * z + 0.28571429f;
+  p = p * z + 0.4f;
+  p = p * z + 0.66666667f;
+  float lnm = 2.0f * s + s * z * p;
+  return -(float(e) * 0.69314718f + lnm);
+}
+
+struct TrackResult { bool hit; float t; int vox[3]; float T; uint32_t ntent, ncells; };
+
+// DDA over 8^3-voxel cells with per-cell majorants. MODE 0: delta tracking, MODE 1: ratio tracking. DESIGN.md §3.4
+template <int MODE>
+__device__ __forceinline__ TrackResult track(const GridDev& G, V3 org, V3 dir, float tmin, float tmax, uint32_t& seed) {
+  TrackResult R; R.hit = false; R.t = 0.0f; R.vox[0] = R.vox[1] = R.vox[2] = 0; R.T = 1.0f; R.ntent = 0; R.ncells = 0;
+  float o[3] = { (org.x - G.B[0]) * G.invA + 0.5f, (org.y - G.B[1]) * G.invA + 0.5f, (org.z - G.B[2]) * G.invA + 0.5f };
+  float d[3] = { dir.x * G.invA, dir.y * G.invA, dir.z * G.invA };
+  float t0 = tmin, t1 = tmax;
+  float inv[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float lo = float(G.vmin[a]), hi = float(G.vmin[a] + G.vdim[a]);
+    if (d[a] == 0.0f) {
+      inv[a] = 0.0f;
+      if (o[a] < lo || !(o[a] < hi)) return R;
+    } else {
+      inv[a] = 1.0f / d[a];
+      float ta = (lo - o[a]) * inv[a], tb = (hi - o[a]) * inv[a];
+      float tn = gmin(ta, tb), tf = gmax(ta, tb);
+      t0 = gmax(t0, tn); t1 = gmin(t1, tf);
+    }
+  }
+  if (!(t0 < t1)) return R;
+  int c[3], step[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float q = o[a] + d[a] * t0;
+    int v = int(floorf(q)) - G.vmin[a];
+    int ci = v >> 3;
+    if (ci < 0) ci = 0;
+    if (ci > G.cdim[a] - 1) ci = G.cdim[a] - 1;
+    c[a] = ci;
+    step[a] = d[a] > 0.0f ? 1 : -1;
+  }
+  float t = t0;
+  for (;;) {
+    R.ncells += 1;
+    float tn[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      if (d[a] == 0.0f) tn[a] = __int_as_float(0x7f800000);
+      else {
+        float bound = float(G.vmin[a] + (c[a] + (step[a] > 0 ? 1 : 0)) * 8);
+        tn[a] = (bound - o[a]) * inv[a];
+      }
+    }
+    int axis = 0; float tcell = tn[0];
+    if (tn[1] < tcell) { tcell = tn[1]; axis = 1; }
+    if (tn[2] < tcell) { tcell = tn[2]; axis = 2; }
+    bool last = false;
+    if (!(tcell < t1)) { tcell = t1; last = true; }
+    int vlo0 = G.vmin[0] + c[0] * 8, vlo1 = G.vmin[1] + c[1] * 8, vlo2 = G.vmin[2] + c[2] * 8;
+    int cell = cell_lookup(G, vlo0, vlo1, vlo2);
+    float mu_d = cell < 0 ? __ldg(&G.tile_density[~cell]) : __ldg(&G.leaf_max[cell]);
+    if (mu_d > 0.0f) {
+      float inv_mu = 1.0f / (mu_d * G.density_scale);
+      const float* brick = cell < 0 ? nullptr : G.atlas + (size_t)cell * 512;
+      for (;;) {
+        float u = rnd(seed);
+        t = t + neglog1m(u) * inv_mu;
+        if (!(t < tcell)) break;
+        R.ntent += 1;
+        int vx = int(floorf(o[0] + d[0] * t)), vy = int(floorf(o[1] + d[1] * t)), vz = int(floorf(o[2] + d[2] * t));
+        vx = vx < vlo0 ? vlo0 : (vx > vlo0 + 7 ? vlo0 + 7 : vx);
+        vy = vy < vlo1 ? vlo1 : (vy > vlo1 + 7 ? vlo1 + 7 : vy);
+        vz = vz < vlo2 ? vlo2 : (vz > vlo2 + 7 ? vlo2 + 7 : vz);
+        float dens = brick ? __ldg(&brick[((vx & 7) << 6) | ((vy & 7) << 3) | (vz & 7)]) : mu_d;
+        if (MODE == 0) {
+          float u2 = rnd(seed);
+          if (u2 * mu_d < dens) { R.hit = true; R.t = t; R.vox[0] = vx; R.vox[1] = vy; R.vox[2] = vz; return R; }
+        } else {
+          R.T = R.T * (1.0f - dens / mu_d);
+          if (!(R.T > 0.0f)) { R.T = 0.0f; return R; }
+        }
+      }
+    }
+    t = tcell;
+    if (last) return R;
+    if (axis == 0) { c[0] += step[0]; if (c[0] < 0 || c[0] >= G.cdim[0]) return R; }
+    else if (axis == 1) { c[1] += step[1]; if (c[1] < 0 || c[1] >= G.cdim[1]) return R; }
+    else { c[2] += step[2]; if (c[2] < 0 || c[2] >= G.cdim[2]) return R; }
+  }
+}
+
+__device__ __forceinline__ float ratio_track(const GridDev& G, V3 P, V3 L, uint32_t& seed) {
+  V3 dir = sub(L, P);
+  float dist = sqrtf(dot(dir, dir));
+  if (!(dist > 0.0f)) return 1.0f;
+  dir = divs(dir, dist);
+  TrackResult r = track<1>(G, P, dir, 0.0f, dist, seed);
+  return r.T;
+}
+
+// voxel material: vdb/vdb.cpp:814-821 + Renderer.cpp:1494-1500 (nvmath::normalize = multiply by reciprocal norm)
+__device__ __forceinline__ float4 voxel_albedo(float v) {
+  float n3 = sqrtf(100.0f * 100.0f + 100.0f * 100.0f + 100.0f * 100.0f);
+  float s = 100.0f * (1.0f / n3);
+  float c = s * v * 1000.0f;
+  float n4 = sqrtf(c * c + c * c + c * c + 1.0f * 1.0f);
+  float inv = n4 > 10e-6f ? 1.0f / n4 : 0.0f;
+  return make_float4(c * inv, c * inv, c * inv, 1.0f * inv);
+}
+
+__device__ __forceinline__ void mat_vec(const float* m, float x, float y, float z, float w, float* o) {   // nvmath.inl:483-492
+#pragma unroll
+  for (int r = 0; r < 4; ++r) o[r] = m[0 + r] * x + m[4 + r] * y + m[8 + r] * z + m[12 + r] * w;
+}
+
+__device__ __forceinline__ GInfo ginfo_from_planes(const Planes& gb, size_t idx, const float* camPos) {
+  float4 p = gb.worldPos[idx], a = gb.albedo[idx], n = gb.normal[idx], m = gb.mat[idx];
+  GInfo g;
+  g.albedo[0] = a.x; g.albedo[1] = a.y; g.albedo[2] = a.z; g.albedo[3] = a.w;
+  g.normal = v3(n.x, n.y, n.z);
+  g.worldPos = v3(p.x, p.y, p.z);
+  g.roughness = m.x; g.metallic = m.y;
+  g.albedoLum = luminance_common(a.x, a.y, a.z);
+  g.camPos = v3(camPos[0], camPos[1], camPos[2]);
+  g.sampleSeed = 0;
+  return g;
+}
+
+}  // namespace vrs

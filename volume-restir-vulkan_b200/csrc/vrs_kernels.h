@@ -1,0 +1,20 @@
+// Launch interface between the host runtime (vrs_api.cu) and the kernels (vrs_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vrs {
+struct GridDev;
+struct LightsDev;
+struct FrameParams;
+struct Planes;
+struct ResPlanes;
+
+void launch_initial(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, Planes cur, Planes prev, ResPlanes prevR,
+                    ResPlanes outR, uint32_t* trace, int y0, int y1, int store_y0, int store_y1);
+void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams& F, Planes cur, ResPlanes inR, ResPlanes outR, uint32_t iteration,
+                    int y0, int y1, int store_y0, int store_y1);
+void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, Planes cur, ResPlanes rs, float4* accum,
+                  int y0, int y1, int store_y0);
+void launch_sample_density(cudaStream_t s, const GridDev& G, const int* ijk, uint32_t n, float* out);
+}  // namespace vrs
