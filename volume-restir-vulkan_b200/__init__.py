@@ -366,6 +366,7 @@ class Renderer:
         self.updateUniformBuffer()
         self.updateRestirUniformBuffer()
         self.updateFrame()
+        self._last_initialize = self.m_pcRestirPost.initialize
         self.submit(clock)
         if self.m_pcRestirPost.frame > 10:
             self.m_pcRestirPost.initialize = 0
