@@ -1,0 +1,326 @@
+#!/usr/bin/env python3
+"""bench.py — volumetric ReSTIR hot-path benchmark (contract: see the task brief / DESIGN.md §6).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path through the C ABI (libvrs.so)
+  python bench.py --impl reference ...                     # the reference math on the box's host cores (oracle port)
+
+A "step" is one frame of BASELINE.json configs[1]: smoke.vdb, 1920x1080, 64 point lights, RIS M=32 + temporal
+reuse, camera on a 6 deg/frame orbit.  N > 1 (torchrun) splits the screen into horizontal bands, grid replicated,
+halo rows exchanged over NCCL (strong scaling: total work fixed).
+"""
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (asset, W, H, lights, M, flags, spatial k, iterations)
+    "smoke_1080p_temporal": dict(asset="smoke", W=1920, H=1080, lights=64, M=32, flags=1 | 2, k=5, iters=0,
+                                 desc="configs[1]: smoke.vdb 1920x1080, 64 point lights, RIS M=32 + temporal reuse, 6deg/frame orbit"),
+    "smoke_1080p_full": dict(asset="smoke", W=1920, H=1080, lights=64, M=32, flags=1 | 2 | 4, k=5, iters=2,
+                             desc="smoke.vdb 1920x1080, 64 lights, full spatiotemporal (k=5, 2 iterations)"),
+    "smoke_4k_full": dict(asset="smoke", W=3840, H=2160, lights=10000, M=32, flags=1 | 2 | 4, k=5, iters=2,
+                          desc="configs[3] shape on smoke.vdb: 3840x2160, 10k lights, full spatiotemporal"),
+}
+BYTES_PER_PX = {"initial": 96, "temporal": 96, "spatial_iter": 128, "shade": 128}   # SURVEY.md §8d / BASELINE.md §4
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def orbit_eye(center, radius, height, angle_deg):
+    a = math.radians(angle_deg)
+    return (center[0] + radius * math.cos(a), center[1] + height, center[2] + radius * math.sin(a))
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def build_scene_inputs(V, wl, R):
+    gi = R.gridInfo()
+    lo, hi = list(gi.world_bbox_min), list(gi.world_bbox_max)
+    ctr = [(a + b) * 0.5 for a, b in zip(lo, hi)]
+    ext = [(b - a) * 0.5 for a, b in zip(lo, hi)]
+    lights = V.generate_point_lights([c - e for c, e in zip(ctr, ext)], [c + e for c, e in zip(ctr, ext)], False, wl["lights"])
+    diag = math.sqrt(sum(e * e for e in ext))
+    return lights, ctr, diag
+
+
+def run_ours(args):
+    import torch
+    import vrs_pkg
+    V = vrs_pkg.load()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("bench.py: --gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, H = wl["W"], wl["H"]
+    band = V.band_for_rank(H, rank, world) if world > 1 else None
+    R = V.Renderer(W, H, spatial_iterations=wl["iters"], band=band, halo_rows=32, device=local)
+    R.loadVDB(os.path.join(ROOT, "assets", wl["asset"] + ".vrsg"))
+    lights, ctr, diag = build_scene_inputs(V, wl, R)
+    R.createRestirLights(lights)
+    if world > 1:
+        uid = [V.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        R.commInit(uid[0], rank, world)
+    u = R.m_restirUniforms
+    u.initialLightSampleCount, u.spatialNeighbors, u.flags = wl["M"], wl["k"], wl["flags"]
+    radius = 1.25 * diag
+    R.CameraManip.setLookat(orbit_eye(ctr, radius, 0.0, 0.0), ctr)
+    R.createRestirUniformBuffer()
+
+    stream = torch.cuda.ExternalStream(R.stream())
+    frame_no = [0]
+
+    def step():
+        R.CameraManip.setLookat(orbit_eye(ctr, radius, 0.0, 6.0 * frame_no[0]), ctr)
+        R.renderFrame(clock=frame_no[0])
+        frame_no[0] += 1
+
+    def barrier():
+        R.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: K frames, CUDA events on the launching stream
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pass_ms = {"initial": 0.0, "spatial": 0.0, "shade": 0.0, "exchange": 0.0}
+    launches = 0
+    t_wall0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    # per-pass event times of a few more frames (the events are recorded inside vrs_render_frame)
+    probe = min(args.steps, 20)
+    for _ in range(probe):
+        step()
+        t = R.timings()
+        pass_ms["initial"] += t.initial_ms; pass_ms["spatial"] += t.spatial_ms; pass_ms["shade"] += t.shade_ms; pass_ms["exchange"] += t.exchange_ms
+        launches = t.launches
+    for k_ in pass_ms:
+        pass_ms[k_] /= probe
+    barrier()
+
+    # ---- end to end through the public API: host uniforms in, host frame buffer out, every step
+    pinned = torch.empty((R.rows, W, 4), dtype=torch.float32, pin_memory=True)
+    host_frame = pinned.numpy()
+    for _ in range(2):
+        step(); R.readFrame(host_frame)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 30))
+    for _ in range(e2e_steps):
+        step()
+        R.readFrame(host_frame)          # synchronous D2H of the accumulated frame
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    ms_step = ms_total / args.steps
+    e2e_ms = 1000.0 * e2e_s / e2e_steps
+    if dist is not None:
+        tt = torch.tensor([ms_step, e2e_ms, pass_ms["initial"], pass_ms["spatial"], pass_ms["shade"], pass_ms["exchange"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms = float(tt[0]), float(tt[1])
+        pass_ms = {"initial": float(tt[2]), "spatial": float(tt[3]), "shade": float(tt[4]), "exchange": float(tt[5])}
+    if rank == 0:
+        fps = 1000.0 / ms_step
+        px = W * H
+        peak, peak_src = measured_peak()
+        rows_frac = (R.rows / H)
+        temporal = bool(wl["flags"] & 2)
+        init_bytes = px * rows_frac * (BYTES_PER_PX["initial"] + (BYTES_PER_PX["temporal"] if temporal else 0))
+        ach = init_bytes / (pass_ms["initial"] * 1e-3) / 1e9 if pass_ms["initial"] > 0 else 0.0
+        frame_bytes = px * (BYTES_PER_PX["initial"] + (BYTES_PER_PX["temporal"] if temporal else 0) + BYTES_PER_PX["shade"] +
+                            (BYTES_PER_PX["spatial_iter"] * wl["iters"] if wl["flags"] & 4 else 0))
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("k_initial_dram_bytes_per_launch")
+        line = {
+            "metric": "ReSTIR frames/s", "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic camera orbit + generated lights over the reference's smoke.vdb grid (assets/smoke.vrsg)",
+            "config": {"workload": wl["desc"], "name": args.workload, "resolution": [W, H], "M": wl["M"], "lights": wl["lights"], "flags": wl["flags"],
+                       "spatial_iterations": wl["iters"], "partition": "bands x%d, halo 32 rows" % world if world > 1 else "single GPU",
+                       "l2": "per-frame working set %.0f MB > 126 MB L2 (inputs larger than L2, no flush)" % (px * 240 / 1e6)},
+            "mpixels_per_s": round(px * fps / 1e6, 1), "mpixel_samples_per_s": round(px * wl["M"] * fps / 1e6, 1),
+            "frame_hbm_gbs": round(frame_bytes * fps / 1e9, 1), "frame_hbm_frac": round(frame_bytes * fps / 1e9 / peak, 4),
+            "pass_ms": {k_: round(v, 5) for k_, v in pass_ms.items()},
+            "roofline": {"kernel": "k_initial (primary delta tracking + RIS M=%d + shadow transmittance + temporal)" % wl["M"], "bound": "hbm",
+                         "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(init_bytes)},
+            "e2e": {"value": round(1000.0 / e2e_ms, 3), "unit": "frames/s", "h2d_bytes_per_step": 192 + 320 + 20,
+                    "d2h_bytes_per_step": int(R.rows * W * 16), "ms_per_step": round(e2e_ms, 4)},
+            "gpu_launches": int(launches * args.steps), "clocks": clocks, "wall_s": round(t_wall, 3),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args.workload, frames=args.cpu_frames)
+        print(json.dumps(line), flush=True)
+    R.destroy()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def oracle_setup(workload):
+    """The oracle's own scene for a workload (reads assets/*.vrsg with its own numpy reader)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import grid_py
+    import oracle as O
+    import vdb_py
+    O.build()
+    import vrs_pkg
+    V = vrs_pkg.load()     # host-only helper (light generation) — no device use
+    wl = WORKLOADS[workload]
+    g = grid_py.read_vrsg(os.path.join(ROOT, "assets", wl["asset"] + ".vrsg"))
+    raw, vmin, _ = grid_py.dense_raw(g)
+    dens = vdb_py.density_from_raw(raw, g.level_set, g.background)
+    probe = O.OracleScene(dens, vmin, g.voxel_size, g.translation, np.ones((1, 8), np.float32))
+    lo, hi = probe.world_bbox()
+    ctr = [(a + b) * 0.5 for a, b in zip(lo, hi)]
+    ext = [(b - a) * 0.5 for a, b in zip(lo, hi)]
+    lights = V.generate_point_lights([c - e for c, e in zip(ctr, ext)], [c + e for c, e in zip(ctr, ext)], False, wl["lights"])
+    scene = O.OracleScene(dens, vmin, g.voxel_size, g.translation, lights)
+    diag = math.sqrt(sum(e * e for e in ext))
+    return O, wl, scene, ctr, diag
+
+
+def oracle_frames(O, wl, scene, ctr, diag, frames, first=0, renderer=None):
+    W, H = wl["W"], wl["H"]
+    OR = renderer or O.OracleRenderer(scene, W, H, spatial_iterations=wl["iters"])
+    radius = 1.25 * diag
+    prev = None
+    times = []
+    for f in range(first, first + frames):
+        cam = O.Camera(orbit_eye(ctr, radius, 0.0, 6.0 * f), ctr)
+        gu = O.global_uniforms(cam, W, H)
+        ru = O.restir_uniforms(cam, prev, W, H, wl["lights"], M=wl["M"], flags=wl["flags"], k=wl["k"])
+        pc = O.PushConstant(0, 0, 0, 0, 1)
+        t0 = time.perf_counter()
+        OR.render(gu, ru, pc, f)
+        times.append(time.perf_counter() - t0)
+        prev = cam
+    return OR, times
+
+
+def cpu_baseline(workload, frames=20):
+    O, wl, scene, ctr, diag = oracle_setup(workload)
+    OR, _ = oracle_frames(O, wl, scene, ctr, diag, 1)
+    _, times = oracle_frames(O, wl, scene, ctr, diag, frames, first=1, renderer=OR)
+    fps = len(times) / sum(times)
+    return {"value": round(fps, 4), "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
+            "sample": "%d full %dx%d frames of the same workload through oracle/liboracle.so (OpenMP over rows, -O2 -ffp-contract=off)" % (frames, wl["W"], wl["H"])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    O, wl, scene, ctr, diag = oracle_setup(args.workload)
+    OR, _ = oracle_frames(O, wl, scene, ctr, diag, max(1, args.warmup))
+    _, times = oracle_frames(O, wl, scene, ctr, diag, args.steps, first=args.warmup, renderer=OR)
+    ms = 1000.0 * sum(times) / len(times)
+    fps = 1000.0 / ms
+    W, H = wl["W"], wl["H"]
+    line = {
+        "impl": "reference", "metric": "ReSTIR frames/s", "value": round(fps, 4), "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic camera orbit + generated lights over the reference's smoke.vdb grid (assets/smoke.vrsg)",
+        "config": {"workload": wl["desc"], "name": args.workload, "resolution": [W, H], "M": wl["M"], "lights": wl["lights"], "flags": wl["flags"],
+                   "spatial_iterations": wl["iters"]},
+        "cpu_baseline": {"value": round(fps, 4), "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
+                         "sample": "each step = one full %dx%d frame of the workload on the host cores (oracle/liboracle.so: the reference shader math "
+                                   "restated in C++, OpenMP over rows; the reference's own Vulkan-RT binary cannot run here)" % (W, H)},
+        "e2e": {"value": round(fps, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mpixel_samples_per_s": round(W * H * wl["M"] * fps / 1e6, 2),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="smoke_1080p_temporal", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=20)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
