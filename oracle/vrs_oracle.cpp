@@ -273,7 +273,11 @@ inline Grid make_grid(const orc_scene* s) {
   Grid g; g.s = s; g.cdim[0] = s->vdim[0] / 8; g.cdim[1] = s->vdim[1] / 8; g.cdim[2] = s->vdim[2] / 8; return g;
 }
 
-// Shared DDA over 8^3-voxel cells.  MODE 0: delta tracking (first real collision), MODE 1: ratio tracking.
+// Shared DDA over 8^3-voxel cells with per-cell majorants.
+// MODE 0: delta tracking (first real collision), MODE 1: ratio tracking (transmittance estimate).
+// One exponential optical-depth sample tau is carried across cells ("residual" tracking): a cell with majorant mu
+// consumes (tcell - t) * mu of it; only when tau runs out inside a cell does a tentative collision happen there,
+// after which a fresh tau is drawn.  Exit times advance incrementally (tn[axis] += dt[axis]).
 struct TrackResult { bool hit; float t; int vox[3]; float T; uint32_t ntent, ncells; };
 
 template <int MODE>
@@ -299,6 +303,7 @@ inline TrackResult track(const Grid& g, V3 org, V3 dir, float tmin, float tmax, 
   }
   if (!(t0 < t1)) return R;
   int c[3], step[3];
+  float tn[3], dt[3];
   for (int a = 0; a < 3; ++a) {
     float q = o[a] + d[a] * t0;
     int v = int(floorf(q)) - s->vmin[a];
@@ -307,19 +312,17 @@ inline TrackResult track(const Grid& g, V3 org, V3 dir, float tmin, float tmax, 
     if (ci > g.cdim[a] - 1) ci = g.cdim[a] - 1;
     c[a] = ci;
     step[a] = d[a] > 0.0f ? 1 : -1;
+    if (d[a] == 0.0f) { tn[a] = INFINITY; dt[a] = 0.0f; }
+    else {
+      float bound = float(s->vmin[a] + (c[a] + (step[a] > 0 ? 1 : 0)) * 8);
+      tn[a] = (bound - o[a]) * inv[a];
+      dt[a] = fabsf(inv[a]) * 8.0f;
+    }
   }
   float t = t0;
+  float tau = neglog1m(rnd(seed));
   for (;;) {
     R.ncells += 1;
-    // exit time of this cell
-    float tn[3];
-    for (int a = 0; a < 3; ++a) {
-      if (d[a] == 0.0f) { tn[a] = INFINITY; }
-      else {
-        float bound = float(s->vmin[a] + (c[a] + (step[a] > 0 ? 1 : 0)) * 8);
-        tn[a] = (bound - o[a]) * inv[a];
-      }
-    }
     int axis = 0; float tcell = tn[0];
     if (tn[1] < tcell) { tcell = tn[1]; axis = 1; }
     if (tn[2] < tcell) { tcell = tn[2]; axis = 2; }
@@ -327,12 +330,12 @@ inline TrackResult track(const Grid& g, V3 org, V3 dir, float tmin, float tmax, 
     if (!(tcell < t1)) { tcell = t1; last = true; }
     float mu_d = g.cellmax(c[0], c[1], c[2]);
     if (mu_d > 0.0f) {
-      float inv_mu = 1.0f / (mu_d * s->density_scale);
+      float mu = mu_d * s->density_scale;
       int vlo[3] = { s->vmin[0] + c[0] * 8, s->vmin[1] + c[1] * 8, s->vmin[2] + c[2] * 8 };
       for (;;) {
-        float u = rnd(seed);
-        t = t + neglog1m(u) * inv_mu;
-        if (!(t < tcell)) break;
+        float seg = (tcell - t) * mu;
+        if (!(tau < seg)) { tau = tau - seg; break; }
+        t = t + tau / mu;
         R.ntent += 1;
         int vx[3];
         for (int a = 0; a < 3; ++a) {
@@ -349,12 +352,14 @@ inline TrackResult track(const Grid& g, V3 org, V3 dir, float tmin, float tmax, 
           R.T = R.T * (1.0f - dens / mu_d);
           if (!(R.T > 0.0f)) { R.T = 0.0f; return R; }
         }
+        tau = neglog1m(rnd(seed));
       }
     }
     t = tcell;
     if (last) return R;
     c[axis] += step[axis];
     if (c[axis] < 0 || c[axis] >= g.cdim[axis]) return R;
+    tn[axis] = tn[axis] + dt[axis];
   }
 }
 

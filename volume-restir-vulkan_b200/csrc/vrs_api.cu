@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -45,6 +46,9 @@ struct vrs_ctx {
   LightsDev lights{};
   std::vector<vrs_alias_table_cell> alias_host;
   void* d_lights = nullptr; void* d_alias = nullptr;
+
+  Queues queues{};
+  int persistent_blocks = 148 * 12;
 
   cudaEvent_t ev[8] = {nullptr};
   vrs_timings timings{};
@@ -98,6 +102,16 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
   for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) if (!alloc((void**)&ctx->r_planes[i][p], ctx->npix * 16)) return bail(VRS_ERR_CUDA);
   if (!alloc((void**)&ctx->accum, ctx->npix * 16)) return bail(VRS_ERR_CUDA);
   if (cfg->enable_trace && !alloc((void**)&ctx->trace, ctx->npix * 16)) return bail(VRS_ERR_CUDA);
+  {
+    Queues& Q = ctx->queues;
+    if (!alloc((void**)&Q.counters, 64) || !alloc((void**)&Q.cand, ctx->npix * 4) || !alloc((void**)&Q.hit_pix, ctx->npix * 4) ||
+        !alloc((void**)&Q.hit_t, ctx->npix * 4) || !alloc((void**)&Q.hit_vcode, ctx->npix * 4) || !alloc((void**)&Q.hit_seed, ctx->npix * 4) ||
+        !alloc((void**)&Q.hit_T, ctx->npix * 4) || !alloc((void**)&Q.shadow, ctx->npix * 4) ||
+        !alloc((void**)&Q.cand_ray, ctx->npix * 32) || !alloc((void**)&Q.shadow_ray, ctx->npix * 32))
+      return bail(VRS_ERR_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) ctx->persistent_blocks = prop.multiProcessorCount * (getenv("VRS_BLOCKS_PER_SM") ? atoi(getenv("VRS_BLOCKS_PER_SM")) : 12);
+  }
   for (int i = 0; i < 8; ++i) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
   cudaDeviceSynchronize();
   *out = ctx;
@@ -118,6 +132,11 @@ void vrs_destroy(vrs_ctx* ctx) {
   for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) cudaFree(ctx->g_planes[i][p]);
   for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) cudaFree(ctx->r_planes[i][p]);
   cudaFree(ctx->accum); cudaFree(ctx->trace); cudaFree(ctx->d_lights); cudaFree(ctx->d_alias);
+  {
+    Queues& Q = ctx->queues;
+    cudaFree(Q.counters); cudaFree(Q.cand); cudaFree(Q.hit_pix); cudaFree(Q.hit_t); cudaFree(Q.hit_vcode); cudaFree(Q.hit_seed);
+    cudaFree(Q.hit_T); cudaFree(Q.shadow); cudaFree(Q.cand_ray); cudaFree(Q.shadow_ray);
+  }
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -163,11 +182,32 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
     *dst = p;
     return true;
   };
+  // dense directory over the window's cells
+  const size_t ncell = (size_t)G.cdim[0] * G.cdim[1] * G.cdim[2];
+  if (ncell > ((size_t)1 << 30)) { free_grid(ctx); return fail(ctx, VRS_ERR_UNSUPPORTED, "grid window exceeds 2^30 cells"); }
+  std::vector<float> dir_max(ncell); std::vector<int32_t> dir_leaf(ncell);
+  for (int cz = 0; cz < G.cdim[2]; ++cz)
+    for (int cy = 0; cy < G.cdim[1]; ++cy)
+      for (int cx = 0; cx < G.cdim[0]; ++cx) {
+        const int32_t x = G.vmin[0] + cx * 8, y = G.vmin[1] + cy * 8, z = G.vmin[2] + cz * 8;
+        int32_t c = ~0;
+        const int32_t kx = x & ~4095, ky = y & ~4095, kz = z & ~4095;
+        for (size_t r = 0; r < h.root.size() / 4; ++r)
+          if (h.root[4 * r] == kx && h.root[4 * r + 1] == ky && h.root[4 * r + 2] == kz) { c = h.root[4 * r + 3]; break; }
+        if (c >= 0) {
+          c = h.i5[(size_t)c * 32768 + ((((x & 4095) >> 7) << 10) | (((y & 4095) >> 7) << 5) | ((z & 4095) >> 7))];
+          if (c >= 0) c = h.i4[(size_t)c * 4096 + ((((x & 127) >> 3) << 8) | (((y & 127) >> 3) << 4) | ((z & 127) >> 3))];
+        }
+        const size_t ci = ((size_t)cz * G.cdim[1] + cy) * G.cdim[0] + cx;
+        dir_leaf[ci] = c;
+        dir_max[ci] = c < 0 ? tile_density[~c] : leaf_max[c];
+      }
   G.nroot = (int)(h.root.size() / 4);
   bool ok = stage(h.root.data(), h.root.size() * 4, (const void**)&G.root) && stage(h.i5.data(), h.i5.size() * 4, (const void**)&G.i5) &&
             stage(h.i4.data(), h.i4.size() * 4, (const void**)&G.i4) &&
             stage(tile_density.data(), tile_density.size() * 4, (const void**)&G.tile_density) &&
-            stage(leaf_max.data(), leaf_max.size() * 4, (const void**)&G.leaf_max) && stage(atlas.data(), atlas.size() * 4, (const void**)&G.atlas);
+            stage(leaf_max.data(), leaf_max.size() * 4, (const void**)&G.leaf_max) && stage(atlas.data(), atlas.size() * 4, (const void**)&G.atlas) &&
+            stage(dir_max.data(), dir_max.size() * 4, (const void**)&G.dir_max) && stage(dir_leaf.data(), dir_leaf.size() * 4, (const void**)&G.dir_leaf);
   if (!ok) { free_grid(ctx); return fail(ctx, VRS_ERR_CUDA, "grid staging failed"); }
   ctx->has_grid = true;
   return VRS_OK;
@@ -305,9 +345,9 @@ vrs_status vrs_pass_initial(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
   FrameParams F; vrs_status s = make_params(ctx, gu, ru, nullptr, clock, F); if (s) return s;
   int out = (ctx->final_r + 1) % 3;
   launch_initial(ctx->stream, ctx->grid, ctx->lights, F, planes_of(ctx, ctx->cur_g), planes_of(ctx, 1 - ctx->cur_g), res_of(ctx, ctx->final_r),
-                 res_of(ctx, out), ctx->trace, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1);
+                 res_of(ctx, out), ctx->queues, ctx->trace, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks);
   CK(cudaGetLastError());
-  ctx->src_r = out; ctx->timings.launches += 1;
+  ctx->src_r = out; ctx->timings.launches += (uint32_t)initial_pass_launches(ru->flags);
   return VRS_OK;
 }
 vrs_status vrs_pass_spatial(vrs_ctx* ctx, const vrs_restir_uniforms* ru, uint32_t clock, uint32_t iteration) {

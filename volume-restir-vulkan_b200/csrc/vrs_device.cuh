@@ -24,6 +24,10 @@ struct GridDev {
   const float* tile_density;      // [ntile], tile 0 = background
   const float* leaf_max;          // [nleaf] majorant density of the brick
   const float* atlas;             // [nleaf][512] densities, offset (x<<6)|(y<<3)|z
+  // Dense directory over the window's 8^3 cells (the top tree levels flattened once more): the raymarch reads one
+  // L1/L2-resident entry per cell instead of walking root -> internal5 -> internal4.
+  const float* dir_max;           // [cdim z][cdim y][cdim x] majorant density of the cell (0 = empty)
+  const int* dir_leaf;            // same shape: leaf index (>= 0) or ~tile (< 0)
 };
 
 struct LightsDev {
@@ -52,6 +56,20 @@ struct Planes {                   // band-local RGBA32F planes (reference layout
   float4* worldPos; float4* albedo; float4* normal; float4* mat;
 };
 struct ResPlanes { float4* info; float4* weight; };
+
+// Work queues of the initial pass (all indices are band-local pixel indices or hit slots)
+struct Queues {
+  uint32_t* counters;   // [0] candidates [1] hits [2] shadow rays [3] primary queue head [4] shadow queue head
+  uint32_t* cand;       // pixels whose primary ray enters the grid window
+  uint32_t* hit_pix;    // pixel of hit slot s
+  float* hit_t;         // free-flight distance of the primary collision
+  uint32_t* hit_vcode;  // collided voxel, linear code inside the window
+  uint32_t* hit_seed;   // RNG state carried between the kernels of the pass
+  float* hit_T;         // shadow transmittance estimate (1 when no shadow ray was needed)
+  uint32_t* shadow;     // hit slots that need a shadow ray
+  float4* cand_ray;     // 2 x float4 per candidate: clipped primary ray {o.xyz, t0}, {d.xyz, t1}
+  float4* shadow_ray;   // 2 x float4 per shadow-queue entry
+};
 
 // ------------------------------------------------------------------ small vector helpers
 struct V3 { float x, y, z; };
@@ -299,86 +317,194 @@ __device__ __forceinline__ float neglog1m(float u) {   // -ln(1
 
 struct TrackResult { bool hit; float t; int vox[3]; float T; uint32_t ntent, ncells; };
 
-// DDA over 8^3-voxel cells with per-cell majorants. MODE 0: delta tracking, MODE 1: ratio tracking. DESIGN.md §3.4
-template <int MODE>
-__device__ __forceinline__ TrackResult track(const GridDev& G, V3 org, V3 dir, float tmin, float tmax, uint32_t& seed) {
-  TrackResult R; R.hit = false; R.t = 0.0f; R.vox[0] = R.vox[1] = R.vox[2] = 0; R.T = 1.0f; R.ntent = 0; R.ncells = 0;
-  float o[3] = { (org.x - G.B[0]) * G.invA + 0.5f, (org.y - G.B[1]) * G.invA + 0.5f, (org.z - G.B[2]) * G.invA + 0.5f };
-  float d[3] = { dir.x * G.invA, dir.y * G.invA, dir.z * G.invA };
+// A ray clipped to the grid window, in voxel space (o + d t), ready to march: what k_classify / k_ris hand to the
+// persistent raymarch kernels through the work queues (2 x float4 per ray).
+struct RaySeg { float o[3], d[3], t0, t1; };
+
+// Voxel-space ray + slab test against the window.  false = nothing to march.
+__device__ __forceinline__ bool clip_ray(const GridDev& G, V3 org, V3 dir, float tmin, float tmax, RaySeg& r) {
+  r.o[0] = (org.x - G.B[0]) * G.invA + 0.5f; r.o[1] = (org.y - G.B[1]) * G.invA + 0.5f; r.o[2] = (org.z - G.B[2]) * G.invA + 0.5f;
+  r.d[0] = dir.x * G.invA; r.d[1] = dir.y * G.invA; r.d[2] = dir.z * G.invA;
   float t0 = tmin, t1 = tmax;
-  float inv[3];
 #pragma unroll
   for (int a = 0; a < 3; ++a) {
     float lo = float(G.vmin[a]), hi = float(G.vmin[a] + G.vdim[a]);
-    if (d[a] == 0.0f) {
-      inv[a] = 0.0f;
-      if (o[a] < lo || !(o[a] < hi)) return R;
+    if (r.d[a] == 0.0f) {
+      if (r.o[a] < lo || !(r.o[a] < hi)) return false;
     } else {
-      inv[a] = 1.0f / d[a];
-      float ta = (lo - o[a]) * inv[a], tb = (hi - o[a]) * inv[a];
-      float tn = gmin(ta, tb), tf = gmax(ta, tb);
-      t0 = gmax(t0, tn); t1 = gmin(t1, tf);
+      float inv = 1.0f / r.d[a];
+      float ta = (lo - r.o[a]) * inv, tb = (hi - r.o[a]) * inv;
+      float tnr = gmin(ta, tb), tf = gmax(ta, tb);
+      t0 = gmax(t0, tnr); t1 = gmin(t1, tf);
     }
   }
-  if (!(t0 < t1)) return R;
-  int c[3], step[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    float q = o[a] + d[a] * t0;
-    int v = int(floorf(q)) - G.vmin[a];
-    int ci = v >> 3;
-    if (ci < 0) ci = 0;
-    if (ci > G.cdim[a] - 1) ci = G.cdim[a] - 1;
-    c[a] = ci;
-    step[a] = d[a] > 0.0f ? 1 : -1;
-  }
-  float t = t0;
-  for (;;) {
-    R.ncells += 1;
-    float tn[3];
+  r.t0 = t0; r.t1 = t1;
+  return t0 < t1;
+}
+
+enum { RAY_DONE = 0, RAY_SKIP = 1, RAY_COLLIDE = 2 };
+
+// Residual-optical-depth tracking over the dense cell directory, as two kinds of unit step so that a warp can batch
+// them (march_loop below) — the same arithmetic and RNG draws, in the same order, as the oracle's nested loops:
+//   cell_step()    visit one 8^3 cell: one directory load; the carried sample tau either crosses the cell
+//                  (tau -= (tcell - t) * mu) or runs out inside it                       (cheap, no RNG)
+//   collide_step() the tentative collision where tau ran out: brick load, accept test / T update, fresh tau
+template <int MODE>
+struct Ray {
+  float o[3], d[3], tn[3], dt[3];
+  float t, t1, tcell, mu_d, mu, tau, T;
+  int c[3];
+  int cell, axis;
+  uint32_t ntent, ncells;
+  bool last, hit;
+  int vox[3];
+
+  __device__ __forceinline__ void start(const GridDev& G, const RaySeg& r, uint32_t& seed) {
+    hit = false; T = 1.0f; ntent = 0; ncells = 0; vox[0] = vox[1] = vox[2] = 0;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-      if (d[a] == 0.0f) tn[a] = __int_as_float(0x7f800000);
+      o[a] = r.o[a]; d[a] = r.d[a];
+      float q = o[a] + d[a] * r.t0;
+      int v = int(floorf(q)) - G.vmin[a];
+      int ci = v >> 3;
+      if (ci < 0) ci = 0;
+      if (ci > G.cdim[a] - 1) ci = G.cdim[a] - 1;
+      c[a] = ci;
+      if (d[a] == 0.0f) { tn[a] = __int_as_float(0x7f800000); dt[a] = 0.0f; }
       else {
-        float bound = float(G.vmin[a] + (c[a] + (step[a] > 0 ? 1 : 0)) * 8);
-        tn[a] = (bound - o[a]) * inv[a];
+        float inv = 1.0f / d[a];
+        float bound = float(G.vmin[a] + (c[a] + (d[a] > 0.0f ? 1 : 0)) * 8);
+        tn[a] = (bound - o[a]) * inv;
+        dt[a] = fabsf(inv) * 8.0f;
       }
     }
-    int axis = 0; float tcell = tn[0];
+    t = r.t0; t1 = r.t1;
+    tau = neglog1m(rnd(seed));
+  }
+
+  // leave the current cell along `axis` (branch-free over the axis); returns false when the ray is finished
+  __device__ __forceinline__ bool advance(const GridDev& G) {
+    t = tcell;
+    if (last) return false;
+    c[0] += axis == 0 ? (d[0] > 0.0f ? 1 : -1) : 0;
+    c[1] += axis == 1 ? (d[1] > 0.0f ? 1 : -1) : 0;
+    c[2] += axis == 2 ? (d[2] > 0.0f ? 1 : -1) : 0;
+    if ((unsigned)c[0] >= (unsigned)G.cdim[0] || (unsigned)c[1] >= (unsigned)G.cdim[1] || (unsigned)c[2] >= (unsigned)G.cdim[2]) return false;
+    tn[0] = axis == 0 ? tn[0] + dt[0] : tn[0];
+    tn[1] = axis == 1 ? tn[1] + dt[1] : tn[1];
+    tn[2] = axis == 2 ? tn[2] + dt[2] : tn[2];
+    return true;
+  }
+
+  // does the carried sample run out inside the current cell?  (else it is consumed and the cell is left)
+  __device__ __forceinline__ int consume(const GridDev& G) {
+    float seg = (tcell - t) * mu;
+    if (tau < seg) return RAY_COLLIDE;
+    tau = tau - seg;
+    return advance(G) ? RAY_SKIP : RAY_DONE;
+  }
+
+  __device__ __forceinline__ int cell_step(const GridDev& G) {
+    ncells += 1;
+    axis = 0; tcell = tn[0];
     if (tn[1] < tcell) { tcell = tn[1]; axis = 1; }
     if (tn[2] < tcell) { tcell = tn[2]; axis = 2; }
-    bool last = false;
+    last = false;
     if (!(tcell < t1)) { tcell = t1; last = true; }
+    const int ci = (c[2] * G.cdim[1] + c[1]) * G.cdim[0] + c[0];
+    mu_d = __ldg(&G.dir_max[ci]);
+    if (mu_d > 0.0f) { cell = ci; mu = mu_d * G.density_scale; return consume(G); }
+    return advance(G) ? RAY_SKIP : RAY_DONE;
+  }
+
+  __device__ __forceinline__ int collide_step(const GridDev& G, uint32_t& seed) {
+    t = t + tau / mu;
+    ntent += 1;
     int vlo0 = G.vmin[0] + c[0] * 8, vlo1 = G.vmin[1] + c[1] * 8, vlo2 = G.vmin[2] + c[2] * 8;
-    int cell = cell_lookup(G, vlo0, vlo1, vlo2);
-    float mu_d = cell < 0 ? __ldg(&G.tile_density[~cell]) : __ldg(&G.leaf_max[cell]);
-    if (mu_d > 0.0f) {
-      float inv_mu = 1.0f / (mu_d * G.density_scale);
-      const float* brick = cell < 0 ? nullptr : G.atlas + (size_t)cell * 512;
-      for (;;) {
-        float u = rnd(seed);
-        t = t + neglog1m(u) * inv_mu;
-        if (!(t < tcell)) break;
-        R.ntent += 1;
-        int vx = int(floorf(o[0] + d[0] * t)), vy = int(floorf(o[1] + d[1] * t)), vz = int(floorf(o[2] + d[2] * t));
-        vx = vx < vlo0 ? vlo0 : (vx > vlo0 + 7 ? vlo0 + 7 : vx);
-        vy = vy < vlo1 ? vlo1 : (vy > vlo1 + 7 ? vlo1 + 7 : vy);
-        vz = vz < vlo2 ? vlo2 : (vz > vlo2 + 7 ? vlo2 + 7 : vz);
-        float dens = brick ? __ldg(&brick[((vx & 7) << 6) | ((vy & 7) << 3) | (vz & 7)]) : mu_d;
-        if (MODE == 0) {
-          float u2 = rnd(seed);
-          if (u2 * mu_d < dens) { R.hit = true; R.t = t; R.vox[0] = vx; R.vox[1] = vy; R.vox[2] = vz; return R; }
-        } else {
-          R.T = R.T * (1.0f - dens / mu_d);
-          if (!(R.T > 0.0f)) { R.T = 0.0f; return R; }
-        }
-      }
+    int vx = int(floorf(o[0] + d[0] * t)), vy = int(floorf(o[1] + d[1] * t)), vz = int(floorf(o[2] + d[2] * t));
+    vx = vx < vlo0 ? vlo0 : (vx > vlo0 + 7 ? vlo0 + 7 : vx);
+    vy = vy < vlo1 ? vlo1 : (vy > vlo1 + 7 ? vlo1 + 7 : vy);
+    vz = vz < vlo2 ? vlo2 : (vz > vlo2 + 7 ? vlo2 + 7 : vz);
+    const int leaf = __ldg(&G.dir_leaf[cell]);
+    float dens = leaf < 0 ? mu_d : __ldg(&G.atlas[(size_t)leaf * 512 + (((vx & 7) << 6) | ((vy & 7) << 3) | (vz & 7))]);
+    if (MODE == 0) {
+      float u2 = rnd(seed);
+      if (u2 * mu_d < dens) { hit = true; vox[0] = vx; vox[1] = vy; vox[2] = vz; return RAY_DONE; }
+    } else {
+      T = T * (1.0f - dens / mu_d);
+      if (!(T > 0.0f)) { T = 0.0f; return RAY_DONE; }
     }
-    t = tcell;
-    if (last) return R;
-    if (axis == 0) { c[0] += step[0]; if (c[0] < 0 || c[0] >= G.cdim[0]) return R; }
-    else if (axis == 1) { c[1] += step[1]; if (c[1] < 0 || c[1] >= G.cdim[1]) return R; }
-    else { c[2] += step[2]; if (c[2] < 0 || c[2] >= G.cdim[2]) return R; }
+    tau = neglog1m(rnd(seed));
+    return consume(G);
+  }
+};
+
+// Nested-loop form for one-ray-per-thread callers (k_shade's optional final visibility): runs a Ray to completion.
+template <int MODE>
+__device__ __forceinline__ TrackResult track(const GridDev& G, V3 org, V3 dir, float tmin, float tmax, uint32_t& seed) {
+  TrackResult R; R.hit = false; R.t = 0.0f; R.vox[0] = R.vox[1] = R.vox[2] = 0; R.T = 1.0f; R.ntent = 0; R.ncells = 0;
+  RaySeg seg;
+  if (!clip_ray(G, org, dir, tmin, tmax, seg)) return R;
+  Ray<MODE> ray;
+  ray.start(G, seg, seed);
+  int st = RAY_SKIP;
+  while (st != RAY_DONE) st = st == RAY_SKIP ? ray.cell_step(G) : ray.collide_step(G, seed);
+  R.hit = ray.hit; R.t = ray.t; R.vox[0] = ray.vox[0]; R.vox[1] = ray.vox[1]; R.vox[2] = ray.vox[2]; R.T = ray.T;
+  R.ntent = ray.ntent; R.ncells = ray.ncells;
+  return R;
+}
+
+// warp-cooperative work fetch: lanes with `want` take consecutive indices from *head (one atomic per warp)
+__device__ __forceinline__ uint32_t warp_fetch(uint32_t* head, bool want) {
+  const unsigned full = 0xffffffffu;
+  unsigned b = __ballot_sync(full, want);
+  if (b == 0) return 0xFFFFFFFFu;
+  int lane = threadIdx.x & 31;
+  int leader = __ffs(b) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(head, (uint32_t)__popc(b));
+  base = __shfl_sync(full, base, leader);
+  return want ? base + (uint32_t)__popc(b & ((1u << lane) - 1u)) : 0xFFFFFFFFu;
+}
+// warp-aggregated append from divergent code: returns this lane's slot
+__device__ __forceinline__ uint32_t warp_append(uint32_t* counter) {
+  unsigned m = __activemask();
+  int lane = threadIdx.x & 31;
+  int leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+}
+
+// Warp-level scheduler of the persistent raymarch kernels.  Each lane owns one ray (Job supplies fetch / retire).
+// Per iteration the warp executes ONE kind of unit step, the kind more lanes are waiting for, so divergent lanes are
+// batched instead of serialised; lanes whose ray retired are refilled from the job queue once enough are idle.
+template <int MODE, class Job>
+__device__ __forceinline__ void march_loop(const GridDev& G, Job& job, uint32_t* head, uint32_t njobs, int refill_min_idle) {
+  const unsigned full = 0xffffffffu;
+  Ray<MODE> ray;
+  int st = RAY_DONE;
+  uint32_t seed = 0;
+  bool queue_empty = false;
+  for (;;) {
+    const unsigned bs = __ballot_sync(full, st == RAY_SKIP), bc = __ballot_sync(full, st == RAY_COLLIDE);
+    const unsigned busy = bs | bc;
+    if (!queue_empty && (__popc(~busy) >= refill_min_idle || busy == 0)) {
+      const bool want = st == RAY_DONE;
+      const uint32_t j = warp_fetch(head, want);
+      if (want && j < njobs) st = job.fetch(G, j, ray, seed) ? RAY_SKIP : RAY_DONE;
+      queue_empty = __any_sync(full, want && j >= njobs);
+      continue;
+    }
+    if (busy == 0) break;
+    if (bc == 0 || __popc(bs) >= __popc(bc)) {
+#pragma unroll 1
+      for (int r = 0; r < 2; ++r)           // two cell visits per scheduling decision (they are cheap)
+        if (st == RAY_SKIP) { st = ray.cell_step(G); if (st == RAY_DONE) job.retire(G, ray, seed); }
+    } else {
+      if (st == RAY_COLLIDE) { st = ray.collide_step(G, seed); if (st == RAY_DONE) job.retire(G, ray, seed); }
+    }
   }
 }
 

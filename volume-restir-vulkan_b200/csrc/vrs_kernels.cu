@@ -4,6 +4,8 @@
 #include "vrs_device.cuh"
 #include "vrs_kernels.h"
 
+#include <cstdlib>
+
 namespace vrs {
 
 static constexpr uint32_t PASS_INITIAL = 0, PASS_SPATIAL0 = 1, PASS_SHADE = 5;
@@ -12,158 +14,219 @@ static constexpr int FLAG_FINAL_VISIBILITY = 1 << 4, FLAG_FINALIZE_W = 1 << 5;
 static constexpr int MAX_NEIGHBORS = 16;
 
 // -------------------------------------------------------------------------------------------------
-// Kernel A — restir.rgen main (:136-290) on a volume.
-// Phase 1: one thread per pixel of a 16x16 tile: primary ray (:142-148), delta-tracking raymarch through the
-//          sparse grid, G-buffer stores (:193-197).  Miss pixels store an empty reservoir and retire.
-// Phase 2: the surviving (hit) pixels are compacted with warp ballots + a block scan into shared memory, so
-//          that the M-candidate RIS loop, the shadow transmittance raymarch and the temporal merge run on
-//          densely packed warps instead of on scattered lanes.
+// Initial pass — restir.rgen main (:136-290) on a volume, as five kernels over device-side work queues.
+// The pass is instruction-issue bound (ncu, profiles/r01_v1_*): what matters is how many of the 32 lanes do
+// useful work, so each stage runs on the smallest, densest set of lanes it can:
+//   A0 k_classify  every pixel: primary ray (:142-148) vs. the grid window; rays that miss it store the
+//                  empty G-buffer / reservoir at once (coalesced, HBM-bound), the rest go to a queue.
+//   A1 k_primary   persistent warps: delta-tracking raymarch of queued rays as a flattened state machine with
+//                  lane refill (a finished lane takes the next ray instead of idling until the warp drains).
+//   A2 k_ris       one thread per real collision, compact: G-buffer stores (:193-197), M-candidate RIS
+//                  (:203-227) — uniform trip count, no divergence.
+//   A3 k_shadow    persistent warps + refill: ratio-tracking transmittance toward the selected light (:229-235).
+//   A4 k_finish    one thread per collision: apply the transmittance, temporal merge (:237-284), pack (:286-289).
 // -------------------------------------------------------------------------------------------------
-struct HitRec {
-  float P[3]; float n[3]; float albedo[4];
-  uint32_t seed; uint32_t pix;      // pix = ly * 16 + lx inside the tile
+enum { Q_CAND = 0, Q_HIT = 1, Q_SHADOW = 2, Q_PRIMARY_HEAD = 3, Q_SHADOW_HEAD = 4 };
+static constexpr int REFILL_MIN_IDLE = 16;
+
+__device__ __forceinline__ void primary_ray(const FrameParams& F, int x, int y, V3& org, V3& dir) {   // :142-148
+  float ux = float(x) / float(F.W), uy = float(y) / float(F.H);
+  float dx = ux * 2.0f - 1.0f, dy = uy * 2.0f - 1.0f;
+  float o4[4], t4[4], d4[4];
+  mat_vec(F.viewInverse, 0.0f, 0.0f, 0.0f, 1.0f, o4);
+  mat_vec(F.projInverse, dx, dy, 1.0f, 1.0f, t4);
+  V3 tn = normalize(v3(t4[0], t4[1], t4[2]));
+  mat_vec(F.viewInverse, tn.x, tn.y, tn.z, 0.0f, d4);
+  org = v3(o4[0], o4[1], o4[2]); dir = v3(d4[0], d4[1], d4[2]);
+}
+
+__device__ __forceinline__ void store_miss(const Planes& cur, const ResPlanes& outR, uint32_t* trace, size_t idx, uint32_t ntent,
+                                           uint32_t ncells, uint32_t seed) {
+  cur.worldPos[idx] = make_float4(0.f, 0.f, 0.f, 0.f); cur.albedo[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  cur.normal[idx] = make_float4(0.f, 0.f, 0.f, 1.f); cur.mat[idx] = make_float4(0.f, 0.f, 1.f, 1.f);   // :193-197 on a miss
+  float4 a, b; packReservoir(newReservoir(), a, b);
+  outR.info[idx] = a; outR.weight[idx] = b;
+  if (trace) { trace[idx * 4 + 0] = 0xFFFFFFFFu; trace[idx * 4 + 1] = ntent; trace[idx * 4 + 2] = ncells; trace[idx * 4 + 3] = seed; }
+}
+
+__global__ void __launch_bounds__(256) k_classify(const GridDev G, const FrameParams F, Planes cur, ResPlanes outR, Queues Q,
+                                                  uint32_t* __restrict__ trace, int y0, int y1, int store_y0) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = y0 + blockIdx.y * 8 + threadIdx.y;
+  bool enters = false;
+  size_t idx = 0;
+  RaySeg seg;
+  if (x < (int)F.W && y < y1) {
+    idx = (size_t)(y - store_y0) * F.W + x;
+    V3 org, dir; primary_ray(F, x, y, org, dir);
+    enters = clip_ray(G, org, dir, 0.0001f, 100000.0f, seg);                       // :164-166 ray range
+    // every pixel starts as a miss (coalesced stores); k_ris overwrites the pixels that get a real collision
+    store_miss(cur, outR, trace, idx, 0u, 0u, pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_INITIAL));
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, enters);
+  if (b) {
+    const int lane = (threadIdx.y * 32 + threadIdx.x) & 31;
+    uint32_t base = 0;
+    if (lane == __ffs(b) - 1) base = atomicAdd(&Q.counters[Q_CAND], (uint32_t)__popc(b));
+    base = __shfl_sync(0xffffffffu, base, __ffs(b) - 1);
+    if (enters) {
+      const uint32_t j = base + __popc(b & ((1u << lane) - 1u));
+      Q.cand[j] = (uint32_t)idx;
+      Q.cand_ray[2 * j] = make_float4(seg.o[0], seg.o[1], seg.o[2], seg.t0);
+      Q.cand_ray[2 * j + 1] = make_float4(seg.d[0], seg.d[1], seg.d[2], seg.t1);
+    }
+  }
+}
+
+struct PrimaryJob {
+  const FrameParams& F; Queues Q; uint32_t* trace; int store_y0;
+  uint32_t idx;
+  __device__ __forceinline__ bool fetch(const GridDev& G, uint32_t j, Ray<0>& ray, uint32_t& seed) {
+    idx = Q.cand[j];
+    const float4 a = Q.cand_ray[2 * j], b = Q.cand_ray[2 * j + 1];
+    RaySeg seg; seg.o[0] = a.x; seg.o[1] = a.y; seg.o[2] = a.z; seg.t0 = a.w; seg.d[0] = b.x; seg.d[1] = b.y; seg.d[2] = b.z; seg.t1 = b.w;
+    seed = pixel_seed(idx % F.W, idx / F.W + (uint32_t)store_y0, F.clock, PASS_INITIAL);   // :139-140
+    ray.start(G, seg, seed);
+    return true;
+  }
+  __device__ __forceinline__ void retire(const GridDev& G, const Ray<0>& ray, uint32_t seed) {
+    if (ray.hit) {
+      const uint32_t s = warp_append(&Q.counters[Q_HIT]);
+      Q.hit_pix[s] = idx; Q.hit_t[s] = ray.t; Q.hit_seed[s] = seed;
+      Q.hit_vcode[s] = uint32_t(ray.vox[0] - G.vmin[0]) + uint32_t(G.vdim[0]) * (uint32_t(ray.vox[1] - G.vmin[1]) + uint32_t(G.vdim[1]) * uint32_t(ray.vox[2] - G.vmin[2]));
+    }
+    if (trace) { trace[(size_t)idx * 4 + 1] = ray.ntent; trace[(size_t)idx * 4 + 2] = ray.ncells; trace[(size_t)idx * 4 + 3] = seed; }
+  }
 };
 
-template <bool TRACE>
-__global__ void __launch_bounds__(256) k_initial(const GridDev G, const LightsDev L, const FrameParams F, Planes cur, Planes prev,
-                                                 ResPlanes prevR, ResPlanes outR, uint32_t* __restrict__ trace, int y0, int y1,
-                                                 int store_y0, int store_y1) {
-  __shared__ HitRec s_hits[256];
-  __shared__ int s_warp_count[8];
-  __shared__ int s_total;
+__global__ void __launch_bounds__(128) k_primary(const GridDev G, const FrameParams F, Queues Q, uint32_t* __restrict__ trace, int store_y0, int refill) {
+  PrimaryJob job{F, Q, trace, store_y0, 0u};
+  march_loop<0>(G, job, &Q.counters[Q_PRIMARY_HEAD], Q.counters[Q_CAND], refill);
+}
 
-  const int tid = threadIdx.y * 16 + threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int x = blockIdx.x * 16 + threadIdx.x;
-  const int y = y0 + blockIdx.y * 16 + threadIdx.y;
-  const bool inside = x < (int)F.W && y < y1;
-
-  bool hit = false;
-  HitRec rec;
-  uint32_t seed = 0;
-  if (inside) {
-    const size_t idx = (size_t)(y - store_y0) * F.W + x;
-    seed = pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_INITIAL);          // :139-140
-    // primary ray, :142-148
-    float ux = float(x) / float(F.W), uy = float(y) / float(F.H);
-    float dx = ux * 2.0f - 1.0f, dy = uy * 2.0f - 1.0f;
-    float o4[4], t4[4], d4[4];
-    mat_vec(F.viewInverse, 0.0f, 0.0f, 0.0f, 1.0f, o4);
-    mat_vec(F.projInverse, dx, dy, 1.0f, 1.0f, t4);
-    V3 tn = normalize(v3(t4[0], t4[1], t4[2]));
-    mat_vec(F.viewInverse, tn.x, tn.y, tn.z, 0.0f, d4);
-    V3 org = v3(o4[0], o4[1], o4[2]), dir = v3(d4[0], d4[1], d4[2]);
-
-    TrackResult r = track<0>(G, org, dir, 0.0001f, 100000.0f, seed);            // :164-166 ray range
-    float4 wp = make_float4(0.f, 0.f, 0.f, 0.f), al = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 nr = make_float4(0.f, 0.f, 0.f, 1.f), mt = make_float4(0.f, 0.f, 1.f, 1.f);
-    uint32_t vcode = 0xFFFFFFFFu;
-    if (r.hit) {
-      hit = true;
-      V3 P = add(org, muls(dir, r.t));
-      int i = r.vox[0], j = r.vox[1], k = r.vox[2];
-      vcode = uint32_t(i - G.vmin[0]) + uint32_t(G.vdim[0]) * (uint32_t(j - G.vmin[1]) + uint32_t(G.vdim[1]) * uint32_t(k - G.vmin[2]));
-      float dens = density_at(G, i, j, k);
-      V3 grad = v3(density_at(G, i + 1, j, k) - density_at(G, i - 1, j, k), density_at(G, i, j + 1, k) - density_at(G, i, j - 1, k),
-                   density_at(G, i, j, k + 1) - density_at(G, i, j, k - 1));
-      float gg = dot(grad, grad);
-      V3 n;
-      if (gg > 0.0f) { float l = sqrtf(gg); n = v3(-grad.x / l, -grad.y / l, -grad.z / l); }
-      else n = v3(-dir.x, -dir.y, -dir.z);
-      wp = make_float4(P.x, P.y, P.z, 1.0f);
-      al = voxel_albedo(dens);
-      nr = make_float4(n.x, n.y, n.z, 1.0f);
-      mt = make_float4(G.roughness, G.metallic, 1.0f, 1.0f);
-      rec.P[0] = P.x; rec.P[1] = P.y; rec.P[2] = P.z;
-      rec.n[0] = n.x; rec.n[1] = n.y; rec.n[2] = n.z;
-      rec.albedo[0] = al.x; rec.albedo[1] = al.y; rec.albedo[2] = al.z; rec.albedo[3] = al.w;
-      rec.seed = seed; rec.pix = (uint32_t)tid;
+__global__ void __launch_bounds__(128) k_ris(const GridDev G, const LightsDev L, const FrameParams F, Planes cur, ResPlanes outR, Queues Q,
+                                             uint32_t* __restrict__ trace, int store_y0, int needs_finish) {
+  const uint32_t nhit = Q.counters[Q_HIT];
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
+    const uint32_t idx = Q.hit_pix[s];
+    const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
+    uint32_t seed = Q.hit_seed[s];
+    V3 org, dir; primary_ray(F, x, y, org, dir);
+    const V3 P = add(org, muls(dir, Q.hit_t[s]));
+    const uint32_t vcode = Q.hit_vcode[s];
+    const int i = (int)(vcode % (uint32_t)G.vdim[0]) + G.vmin[0];
+    const int j = (int)((vcode / (uint32_t)G.vdim[0]) % (uint32_t)G.vdim[1]) + G.vmin[1];
+    const int k = (int)(vcode / ((uint32_t)G.vdim[0] * (uint32_t)G.vdim[1])) + G.vmin[2];
+    const float dens = density_at(G, i, j, k);
+    V3 grad = v3(density_at(G, i + 1, j, k) - density_at(G, i - 1, j, k), density_at(G, i, j + 1, k) - density_at(G, i, j - 1, k),
+                 density_at(G, i, j, k + 1) - density_at(G, i, j, k - 1));
+    const float gg = dot(grad, grad);
+    V3 n;
+    if (gg > 0.0f) { float l = sqrtf(gg); n = v3(-grad.x / l, -grad.y / l, -grad.z / l); }
+    else n = v3(-dir.x, -dir.y, -dir.z);
+    const float4 al = voxel_albedo(dens);
+    cur.worldPos[idx] = make_float4(P.x, P.y, P.z, 1.0f); cur.albedo[idx] = al;                        // :193-197
+    cur.normal[idx] = make_float4(n.x, n.y, n.z, 1.0f); cur.mat[idx] = make_float4(G.roughness, G.metallic, 1.0f, 1.0f);
+    GInfo gi;
+    gi.albedo[0] = al.x; gi.albedo[1] = al.y; gi.albedo[2] = al.z; gi.albedo[3] = al.w;
+    gi.normal = n; gi.worldPos = P; gi.metallic = G.metallic; gi.roughness = G.roughness;
+    gi.albedoLum = luminance_common(al.x, al.y, al.z);                                                 // :182
+    gi.camPos = v3(F.camPos[0], F.camPos[1], F.camPos[2]);                                             // :183
+    gi.sampleSeed = 0;
+    Res res = newReservoir();
+    if (dot(gi.normal, gi.normal) != 0.0f) {                                                           // :205
+      for (uint32_t c = 0; c < F.M; ++c) {                                                             // :206-226
+        gi.sampleSeed = seed;                                                                          // :213
+        float r1 = rnd(seed), r2 = rnd(seed);                                                          // :116, GLSL left-to-right
+        uint32_t sel; float pdf;
+        aliasTableSample(L, r1, r2, sel, pdf);
+        addSampleToReservoir(L, res, sel, 0, pdf, gi, seed);                                           // :224-225
+      }
     }
-    cur.worldPos[idx] = wp; cur.albedo[idx] = al; cur.normal[idx] = nr; cur.mat[idx] = mt;   // :193-197
-    if (TRACE) { trace[idx * 4 + 0] = vcode; trace[idx * 4 + 1] = r.ntent; trace[idx * 4 + 2] = r.ncells; }
-    if (!hit) {                                                                   // miss: empty reservoir
-      float4 a, b; packReservoir(newReservoir(), a, b);
-      outR.info[idx] = a; outR.weight[idx] = b;
-      if (TRACE) trace[idx * 4 + 3] = seed;
-    }
-  }
-
-  // ---- block compaction of hit pixels (warp ballot + popc prefix, block scan over 8 warps)
-  const unsigned ballot = __ballot_sync(0xffffffffu, hit);
-  const int warp_prefix = __popc(ballot & ((1u << lane) - 1u));
-  if (lane == 0) s_warp_count[warp] = __popc(ballot);
-  __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) { int c = s_warp_count[w]; s_warp_count[w] = acc; acc += c; }
-    s_total = acc;
-  }
-  __syncthreads();
-  if (hit) s_hits[s_warp_count[warp] + warp_prefix] = rec;
-  __syncthreads();
-  const int nhit = s_total;
-  if (tid >= nhit) return;
-
-  // ---- phase 2: RIS + visibility + temporal on packed lanes
-  const HitRec h = s_hits[tid];
-  const int px = blockIdx.x * 16 + (h.pix & 15), py = y0 + blockIdx.y * 16 + (h.pix >> 4);
-  const size_t idx = (size_t)(py - store_y0) * F.W + px;
-  seed = h.seed;
-  GInfo gi;
-  gi.albedo[0] = h.albedo[0]; gi.albedo[1] = h.albedo[1]; gi.albedo[2] = h.albedo[2]; gi.albedo[3] = h.albedo[3];
-  gi.normal = v3(h.n[0], h.n[1], h.n[2]);
-  gi.worldPos = v3(h.P[0], h.P[1], h.P[2]);
-  gi.metallic = G.metallic; gi.roughness = G.roughness;
-  gi.albedoLum = luminance_common(gi.albedo[0], gi.albedo[1], gi.albedo[2]);     // :182
-  gi.camPos = v3(F.camPos[0], F.camPos[1], F.camPos[2]);                         // :183
-  gi.sampleSeed = 0;
-  Res res = newReservoir();
-  if (dot(gi.normal, gi.normal) != 0.0f) {                                       // :205
-    for (uint32_t i = 0; i < F.M; ++i) {                                         // :206-226
-      gi.sampleSeed = seed;                                                      // :213
-      float r1 = rnd(seed), r2 = rnd(seed);                                      // :116, GLSL left-to-right
-      uint32_t sel; float pdf;
-      aliasTableSample(L, r1, r2, sel, pdf);
-      addSampleToReservoir(L, res, sel, 0, pdf, gi, seed);                       // :224-225
+    if ((F.flags & FLAG_FINALIZE_W) != 0 && res.w > 0.0f) res.w = res.sumWeights / (float(res.M) * res.pHat);
+    float4 a, b; packReservoir(res, a, b);
+    outR.info[idx] = a; outR.weight[idx] = b;
+    Q.hit_seed[s] = seed; Q.hit_T[s] = 1.0f;
+    if (trace) { trace[(size_t)idx * 4 + 0] = vcode; if (!needs_finish) trace[(size_t)idx * 4 + 3] = seed; }
+    if ((F.flags & FLAG_VISIBILITY) != 0 && res.w > 0.0f) {                                              // shadow ray of ratio_track()
+      const float4 lp = __ldg(&L.lights[2 * res.lightIndex]);
+      V3 sd = sub(v3(lp.x, lp.y, lp.z), P);
+      const float dist = sqrtf(dot(sd, sd));
+      RaySeg seg;
+      bool march = dist > 0.0f;
+      if (march) { sd = divs(sd, dist); march = clip_ray(G, P, sd, 0.0f, dist, seg); }
+      if (march) {                        // otherwise T = 1 and the RNG state is untouched
+        const uint32_t q = warp_append(&Q.counters[Q_SHADOW]);
+        Q.shadow[q] = s;
+        Q.shadow_ray[2 * q] = make_float4(seg.o[0], seg.o[1], seg.o[2], seg.t0);
+        Q.shadow_ray[2 * q + 1] = make_float4(seg.d[0], seg.d[1], seg.d[2], seg.t1);
+      }
     }
   }
-  if ((F.flags & FLAG_FINALIZE_W) != 0 && res.w > 0.0f) res.w = res.sumWeights / (float(res.M) * res.pHat);
-  if ((F.flags & FLAG_VISIBILITY) != 0 && res.w > 0.0f) {                        // :229-235 -> transmittance
-    float4 lp = __ldg(&L.lights[2 * res.lightIndex]);
-    float T = ratio_track(G, gi.worldPos, v3(lp.x, lp.y, lp.z), seed);
-    res.w = res.w * T;
-    res.sumWeights = res.sumWeights * T;
+}
+
+struct ShadowJob {
+  Queues Q;
+  uint32_t s;
+  __device__ __forceinline__ bool fetch(const GridDev& G, uint32_t j, Ray<1>& ray, uint32_t& seed) {
+    s = Q.shadow[j];
+    seed = Q.hit_seed[s];
+    const float4 a = Q.shadow_ray[2 * j], b = Q.shadow_ray[2 * j + 1];
+    RaySeg seg; seg.o[0] = a.x; seg.o[1] = a.y; seg.o[2] = a.z; seg.t0 = a.w; seg.d[0] = b.x; seg.d[1] = b.y; seg.d[2] = b.z; seg.t1 = b.w;
+    ray.start(G, seg, seed);
+    return true;
   }
-  if ((F.flags & FLAG_TEMPORAL) != 0) {                                          // :237-284 (dormant block, intent)
-    float q[4];
-    mat_vec(F.prevVP, gi.worldPos.x, gi.worldPos.y, gi.worldPos.z, 1.0f, q);
-    q[0] = q[0] / q[3]; q[1] = q[1] / q[3]; q[2] = q[2] / q[3];
-    q[0] = (q[0] + 1.0f) * 0.5f * float(F.W);
-    q[1] = (q[1] + 1.0f) * 0.5f * float(F.H);
-    if (q[0] > 0.0f && q[1] > 0.0f && q[0] < float(F.W) && q[1] < float(F.H)) {
-      int fx = int(q[0]), fy = int(q[1]);
-      if (fy >= store_y0 && fy < store_y1) {                                     // rows held by this context
-        size_t pidx = (size_t)(fy - store_y0) * F.W + (size_t)fx;
-        GInfo pg = ginfo_from_planes(prev, pidx, F.camPos);                      // prevGInfo.camPos = gInfo.camPos (:259)
-        V3 pd = sub(gi.worldPos, pg.worldPos);
-        if (dot(pd, pd) < 0.01f) {
-          V3 ad = v3(gi.albedo[0] - pg.albedo[0], gi.albedo[1] - pg.albedo[1], gi.albedo[2] - pg.albedo[2]);
-          if (dot(ad, ad) < 0.01f) {
-            if (dot(gi.normal, pg.normal) > 0.5f) {
-              Res pr = unpackReservoir(prevR.info[pidx], prevR.weight[pidx]);    // at prevFrag
-              uint32_t cap = uint32_t(F.temporalMult) * res.M;
-              if (cap < pr.M) pr.M = cap;
-              combineReservoirsGeom(L, res, pr, gi, pg, seed);
+  __device__ __forceinline__ void retire(const GridDev&, const Ray<1>& ray, uint32_t seed) { Q.hit_T[s] = ray.T; Q.hit_seed[s] = seed; }
+};
+
+__global__ void __launch_bounds__(128) k_shadow(const GridDev G, Queues Q, int refill) {
+  ShadowJob job{Q, 0u};
+  march_loop<1>(G, job, &Q.counters[Q_SHADOW_HEAD], Q.counters[Q_SHADOW], refill);
+}
+
+__global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FrameParams F, Planes cur, Planes prev, ResPlanes prevR,
+                                                ResPlanes outR, Queues Q, uint32_t* __restrict__ trace, int store_y0, int store_y1) {
+  const uint32_t nhit = Q.counters[Q_HIT];
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
+    const uint32_t idx = Q.hit_pix[s];
+    uint32_t seed = Q.hit_seed[s];
+    Res res = unpackReservoir(outR.info[idx], outR.weight[idx]);
+    GInfo gi = ginfo_from_planes(cur, idx, F.camPos);
+    if ((F.flags & FLAG_VISIBILITY) != 0 && res.w > 0.0f) {                                            // :229-235 -> transmittance
+      const float T = Q.hit_T[s];
+      res.w = res.w * T;
+      res.sumWeights = res.sumWeights * T;
+    }
+    if ((F.flags & FLAG_TEMPORAL) != 0) {                                                              // :237-284 (dormant block, intent)
+      float q[4];
+      mat_vec(F.prevVP, gi.worldPos.x, gi.worldPos.y, gi.worldPos.z, 1.0f, q);
+      q[0] = q[0] / q[3]; q[1] = q[1] / q[3]; q[2] = q[2] / q[3];
+      q[0] = (q[0] + 1.0f) * 0.5f * float(F.W);
+      q[1] = (q[1] + 1.0f) * 0.5f * float(F.H);
+      if (q[0] > 0.0f && q[1] > 0.0f && q[0] < float(F.W) && q[1] < float(F.H)) {
+        int fx = int(q[0]), fy = int(q[1]);
+        if (fy >= store_y0 && fy < store_y1) {                                                         // rows held by this context
+          size_t pidx = (size_t)(fy - store_y0) * F.W + (size_t)fx;
+          GInfo pg = ginfo_from_planes(prev, pidx, F.camPos);                                          // prevGInfo.camPos = gInfo.camPos (:259)
+          V3 pd = sub(gi.worldPos, pg.worldPos);
+          if (dot(pd, pd) < 0.01f) {
+            V3 ad = v3(gi.albedo[0] - pg.albedo[0], gi.albedo[1] - pg.albedo[1], gi.albedo[2] - pg.albedo[2]);
+            if (dot(ad, ad) < 0.01f) {
+              if (dot(gi.normal, pg.normal) > 0.5f) {
+                Res pr = unpackReservoir(prevR.info[pidx], prevR.weight[pidx]);                        // at prevFrag
+                uint32_t cap = uint32_t(F.temporalMult) * res.M;
+                if (cap < pr.M) pr.M = cap;
+                combineReservoirsGeom(L, res, pr, gi, pg, seed);
+              }
             }
           }
         }
       }
     }
+    float4 a, b; packReservoir(res, a, b);                                                             // :286-289
+    outR.info[idx] = a; outR.weight[idx] = b;
+    if (trace) trace[(size_t)idx * 4 + 3] = seed;
   }
-  float4 a, b; packReservoir(res, a, b);                                         // :286-289
-  outR.info[idx] = a; outR.weight[idx] = b;
-  if (TRACE) trace[idx * 4 + 3] = seed;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -270,11 +333,22 @@ __global__ void k_sample_density(const GridDev G, const int* __restrict__ ijk, u
 }
 
 // ------------------------------------------------------------------------------------------------- launchers
-void launch_initial(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, Planes cur, Planes prev, ResPlanes prevR,
-                    ResPlanes outR, uint32_t* trace, int y0, int y1, int store_y0, int store_y1) {
-  dim3 block(16, 16), grid((F.W + 15) / 16, (y1 - y0 + 15) / 16);
-  if (trace) k_initial<true><<<grid, block, 0, s>>>(G, L, F, cur, prev, prevR, outR, trace, y0, y1, store_y0, store_y1);
-  else k_initial<false><<<grid, block, 0, s>>>(G, L, F, cur, prev, prevR, outR, nullptr, y0, y1, store_y0, store_y1);
+void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, Planes cur, Planes prev, ResPlanes prevR,
+                    ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1, int persistent_blocks) {
+  static const int refill = getenv("VRS_REFILL") ? atoi(getenv("VRS_REFILL")) : REFILL_MIN_IDLE;
+  cudaMemsetAsync(Q.counters, 0, 8 * sizeof(uint32_t), st);
+  dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
+  k_classify<<<grid, block, 0, st>>>(G, F, cur, outR, Q, trace, y0, y1, store_y0);
+  k_primary<<<persistent_blocks, 128, 0, st>>>(G, F, Q, trace, store_y0, refill);
+  const bool vis = (F.flags & FLAG_VISIBILITY) != 0, temporal = (F.flags & FLAG_TEMPORAL) != 0;
+  const int needs_finish = (vis || temporal) ? 1 : 0;
+  k_ris<<<persistent_blocks, 128, 0, st>>>(G, L, F, cur, outR, Q, trace, store_y0, needs_finish);
+  if (vis) k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill);
+  if (needs_finish) k_finish<<<persistent_blocks, 128, 0, st>>>(L, F, cur, prev, prevR, outR, Q, trace, store_y0, store_y1);
+}
+int initial_pass_launches(int flags) {
+  const bool vis = (flags & FLAG_VISIBILITY) != 0, temporal = (flags & FLAG_TEMPORAL) != 0;
+  return 3 + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
 }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams& F, Planes cur, ResPlanes inR, ResPlanes outR, uint32_t iteration,
                     int y0, int y1, int store_y0, int store_y1) {

@@ -9,9 +9,11 @@ struct LightsDev;
 struct FrameParams;
 struct Planes;
 struct ResPlanes;
+struct Queues;
 
 void launch_initial(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, Planes cur, Planes prev, ResPlanes prevR,
-                    ResPlanes outR, uint32_t* trace, int y0, int y1, int store_y0, int store_y1);
+                    ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1, int persistent_blocks);
+int initial_pass_launches(int flags);
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams& F, Planes cur, ResPlanes inR, ResPlanes outR, uint32_t iteration,
                     int y0, int y1, int store_y0, int store_y1);
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, Planes cur, ResPlanes rs, float4* accum,
