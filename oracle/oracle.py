@@ -296,24 +296,34 @@ class OracleRenderer:
         self.iters = spatial_iterations
         self.final_res = 0   # index into f.res of the last frame's final reservoirs
 
-    def render(self, gu, ru, pc, clock, y0=0, y1=None):
+    def render(self, gu, ru, pc, clock, y0=0, y1=None, exchange=None):
+        """`exchange(planes)` (multi-rank band mode) is called at the points where libvrs exchanges halo rows:
+        after the initial pass (G-buffer + reservoirs), between spatial iterations (reservoirs) and after the frame
+        (what the next frame's temporal reuse reads) — the schedule of vrs_render_frame."""
         L, f, s = lib(), self.f, self.scene.c
         y1 = self.H if y1 is None else y1
         cur_g, prev_g = f.g[self.cur], f.g[1 - self.cur]
         prev_r = f.res[self.final_res]
-        free = [i for i in range(3) if i != self.final_res]
-        out_r = f.res[free[0]]
+        src = (self.final_res + 1) % 3
         L.orc_pass_initial(C.byref(s), C.byref(gu), C.byref(ru), C.c_uint32(clock), y0, y1, Frame.gbuf(cur_g),
-                           Frame.gbuf(prev_g), Frame.rbuf(prev_r), Frame.rbuf(out_r), _p(f.trace))
-        src = free[0]
-        if ru.flags & FLAG_SPATIAL:
+                           Frame.gbuf(prev_g), Frame.rbuf(prev_r), Frame.rbuf(f.res[src]), _p(f.trace))
+        spatial = bool(ru.flags & FLAG_SPATIAL) and self.iters > 0
+        g_planes = [cur_g[k] for k in ("worldPos", "albedo", "normal", "matProps")]
+        r_planes = lambda i: [f.res[i]["info"], f.res[i]["weight"]]
+        if exchange and spatial:
+            exchange(g_planes + r_planes(src))
+        if spatial:
             for it in range(self.iters):
                 dst = (src + 1) % 3
                 L.orc_pass_spatial(C.byref(s), C.byref(ru), C.c_uint32(clock), C.c_uint32(it), y0, y1, Frame.gbuf(cur_g),
                                    Frame.rbuf(f.res[src]), Frame.rbuf(f.res[dst]))
                 src = dst
+                if exchange and it + 1 < self.iters:
+                    exchange(r_planes(src))
         L.orc_pass_shade(C.byref(s), C.byref(ru), C.byref(pc), C.c_uint32(clock), y0, y1, Frame.gbuf(cur_g),
                          Frame.rbuf(f.res[src]), _p(f.accum))
+        if exchange and (ru.flags & FLAG_TEMPORAL):
+            exchange((g_planes if not spatial else []) + r_planes(src))
         self.final_res = src
         self.last_g = self.cur
         self.cur = 1 - self.cur

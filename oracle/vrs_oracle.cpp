@@ -852,7 +852,8 @@ void orc_pass_shade(const orc_scene* s, const orc_restir_uniforms* ru, const orc
 
 // ------------------------------------------------------------------ brute-force reference estimator
 // E[ f(P, y) * Le(y) * G / pdf(y) * T(P, y) ] over (primary event P by delta tracking, light y by alias table,
-// T by ratio tracking); the same integrand the ReSTIR passes estimate, without reuse, clamp or emissive override.
+// T by ratio tracking); the same integrand the ReSTIR passes estimate (including the reference's emissive
+// override), without reuse and without the firefly clamp.
 void orc_path_trace(const orc_scene* s, const orc_global_uniforms* gu, const orc_restir_uniforms* ru, uint32_t spp,
                     uint32_t seed_base, float* out) {
   const uint32_t W = ru->screenSize[0], H = ru->screenSize[1];
@@ -877,6 +878,10 @@ void orc_path_trace(const orc_scene* s, const orc_global_uniforms* gu, const orc
         gi.albedoLum = luminance_common(gi.albedo[0], gi.albedo[1], gi.albedo[2]);
         gi.camPos = v3(ru->currCamPos[0], ru->currCamPos[1], ru->currCamPos[2]);
         gi.sampleSeed = 0;
+        if (gi.albedo[3] > 0.5f) {                  // restir_post.frag:82-84 emissive override is part of the shaded quantity
+          acc[0] += gi.albedo[0]; acc[1] += gi.albedo[1]; acc[2] += gi.albedo[2];
+          continue;
+        }
         float r1 = rnd(seed), r2 = rnd(seed);
         uint32_t sel; float pdf;
         aliasTableSample(s->table, s->ntable, r1, r2, sel, pdf);

@@ -1,0 +1,82 @@
+"""-m gpu (needs >= 2 GPUs, skipped otherwise): bands + NCCL halo exchange through the C ABI (vrs_comm_init) must give
+the same bits as one GPU rendering the whole frame."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    return port
+
+
+def worker(rank, world, port, flags, frames, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import vrs_pkg
+    V = vrs_pkg.load()
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    W, H = 480, 270
+    band = V.band_for_rank(H, rank, world)
+
+    def make(band_, device):
+        R = V.Renderer(W, H, spatial_iterations=2, band=band_, halo_rows=32, device=device)
+        R.loadVDB(common.asset("smoke"))
+        gi = R.gridInfo()
+        lo, hi = list(gi.world_bbox_min), list(gi.world_bbox_max)
+        lights = V.generate_point_lights(lo, hi, False, 64)
+        R.createRestirLights(lights)
+        R.m_restirUniforms.initialLightSampleCount = 16
+        R.m_restirUniforms.spatialNeighbors = 5
+        R.m_restirUniforms.flags = flags
+        ctr = [(a + b) * 0.5 for a, b in zip(lo, hi)]
+        return R, ctr
+
+    R, ctr = make(band, rank)
+    uid = [V.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    R.commInit(uid[0], rank, world)
+    full = make(None, 0)[0] if rank == 0 else None
+    for r_ in [R] + ([full] if full else []):
+        r_.CameraManip.setLookat(common.orbit_eye(ctr, 4.2, 0.2, 10.0), ctr)
+        r_.createRestirUniformBuffer()
+    ok = True
+    for f in range(frames):
+        eye = common.orbit_eye(ctr, 4.2, 0.2, 10.0 + 1.0 * f)
+        R.CameraManip.setLookat(eye, ctr)
+        R.renderFrame(clock=f)
+        mine = torch.from_numpy(R.readFrame())
+        parts = [torch.zeros((V.band_for_rank(H, r, world)[1] - V.band_for_rank(H, r, world)[0], W, 4)) for r in range(world)] if rank == 0 else None
+        dist.gather(mine, parts, dst=0)
+        if rank == 0:
+            full.CameraManip.setLookat(eye, ctr)
+            full.renderFrame(clock=f)
+            ref = full.readFrame()
+            got = torch.cat(parts, 0).numpy()
+            ok = ok and bool((got.view(np.uint32) == ref.view(np.uint32)).all())
+    if rank == 0:
+        open(os.path.join(out_dir, "result"), "w").write("ok" if ok else "mismatch")
+    dist.barrier()
+    R.destroy()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("flags", [1 | 2 | 4, 1 | 2])
+def test_nccl_bands_equal_single_gpu(flags, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(worker, args=(world, free_port(), flags, 4, str(tmp_path)), nprocs=world, join=True)
+    assert open(tmp_path / "result").read() == "ok"

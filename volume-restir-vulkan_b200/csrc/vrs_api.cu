@@ -494,6 +494,8 @@ vrs_status vrs_comm_unique_id(uint8_t id128[128]) {
 vrs_status vrs_comm_init(vrs_ctx* ctx, const uint8_t id128[128], int rank, int nranks) {
   if (!ctx || !id128 || rank < 0 || rank >= nranks) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
+  if (nranks > 1 && ctx->band_y1 - ctx->band_y0 < (int)ctx->cfg.halo_rows)
+    return fail(ctx, VRS_ERR_INVALID, "band shorter than halo_rows: halos are exchanged with adjacent ranks only");
   std::string err;
   ctx->comm = comm_create(id128, rank, nranks, err);
   if (!ctx->comm) return fail(ctx, VRS_ERR_COMM, err);
