@@ -169,6 +169,14 @@ vrs_status vrs_read_frame(vrs_ctx* ctx, float* rgba);                           
 vrs_status vrs_read_gbuffer(vrs_ctx* ctx, float* worldPos, float* albedo, float* normal, float* matProps); /* last rendered frame */
 vrs_status vrs_read_reservoirs(vrs_ctx* ctx, float* info, float* weight);               /* last written reservoir buffer */
 vrs_status vrs_read_trace(vrs_ctx* ctx, uint32_t* trace4);                              /* enable_trace only */
+/* Headless replacement of the swapchain present (nvvk::AppBaseVk::submitFrame, appbase_vk.cpp:437-475): the display
+ * image restir_post.frag:104 outputs — pow(accum, 1/0.8), clamped, 8 bits per channel RGBA — for band rows.
+ * vrs_present_async tonemaps into one of two device staging buffers on the context stream and copies it to `rgba8`
+ * (pinned host memory for real overlap) on a second stream, so the copy of frame i overlaps the render of frame i+1;
+ * vrs_present_wait blocks until every outstanding copy has landed. */
+vrs_status vrs_read_display(vrs_ctx* ctx, uint8_t* rgba8);
+vrs_status vrs_present_async(vrs_ctx* ctx, uint8_t* rgba8);
+vrs_status vrs_present_wait(vrs_ctx* ctx);
 /* Headless replacement of the swapchain present: write band rows as PFM (linear) or PPM (pow(c, 1/0.8), restir_post.frag:104). */
 vrs_status vrs_write_image(vrs_ctx* ctx, const char* path);
 

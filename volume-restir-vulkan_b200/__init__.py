@@ -29,7 +29,7 @@ EXPORTS = [
     "vrs_grid_sample_device", "vrs_set_lights", "vrs_set_triangle_lights", "vrs_get_alias_table", "vrs_create_alias_table",
     "vrs_generate_point_lights", "vrs_perspectiveVK", "vrs_look_at", "vrs_invert", "vrs_mat4_mul", "vrs_pass_initial",
     "vrs_pass_spatial", "vrs_pass_shade", "vrs_render_frame", "vrs_synchronize", "vrs_read_frame", "vrs_read_gbuffer",
-    "vrs_read_reservoirs", "vrs_read_trace", "vrs_write_image", "vrs_get_timings", "vrs_stream", "vrs_comm_unique_id",
+    "vrs_read_reservoirs", "vrs_read_trace", "vrs_read_display", "vrs_present_async", "vrs_present_wait", "vrs_write_image", "vrs_get_timings", "vrs_stream", "vrs_comm_unique_id",
     "vrs_comm_init", "vrs_band_for_rank",
 ]
 
@@ -118,7 +118,7 @@ def lib():
                      "vrs_grid_sample_device", "vrs_set_lights", "vrs_set_triangle_lights", "vrs_get_alias_table",
                      "vrs_pass_initial", "vrs_pass_spatial", "vrs_pass_shade", "vrs_render_frame", "vrs_synchronize",
                      "vrs_read_frame", "vrs_read_gbuffer", "vrs_read_reservoirs", "vrs_read_trace", "vrs_write_image",
-                     "vrs_get_timings", "vrs_comm_init"]:
+                     "vrs_get_timings", "vrs_comm_init", "vrs_read_display", "vrs_present_async", "vrs_present_wait"]:
             getattr(L, name).restype = C.c_int
         L.vrs_load_vdb.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.vrs_load_vrsg.argtypes = [C.c_void_p, C.c_char_p]
@@ -140,6 +140,9 @@ def lib():
         L.vrs_read_reservoirs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.vrs_read_trace.argtypes = [C.c_void_p, C.c_void_p]
         L.vrs_write_image.argtypes = [C.c_void_p, C.c_char_p]
+        L.vrs_read_display.argtypes = [C.c_void_p, C.c_void_p]
+        L.vrs_present_async.argtypes = [C.c_void_p, C.c_void_p]
+        L.vrs_present_wait.argtypes = [C.c_void_p]
         L.vrs_get_timings.argtypes = [C.c_void_p, C.c_void_p]
         L.vrs_stream.argtypes = [C.c_void_p]
         L.vrs_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -413,6 +416,18 @@ class Renderer:
         t = self._img(np.uint32)
         self._ck(lib().vrs_read_trace(self._ctx, _p(t)))
         return t
+
+    def readDisplay(self, out=None):
+        out = np.zeros((self.rows, self.width, 4), np.uint8) if out is None else out
+        self._ck(lib().vrs_read_display(self._ctx, _p(out)))
+        return out
+
+    def presentAsync(self, out):
+        """Headless swapchain present: tonemap + async device->host copy of the 8-bit frame into `out` (pinned)."""
+        self._ck(lib().vrs_present_async(self._ctx, _p(out)))
+
+    def presentWait(self):
+        self._ck(lib().vrs_present_wait(self._ctx))
 
     def writeImage(self, path):
         self._ck(lib().vrs_write_image(self._ctx, path.encode()))

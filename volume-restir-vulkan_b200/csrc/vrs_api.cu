@@ -47,6 +47,10 @@ struct vrs_ctx {
   std::vector<vrs_alias_table_cell> alias_host;
   void* d_lights = nullptr; void* d_alias = nullptr;
 
+  uchar4* display[2] = {nullptr, nullptr};   // device staging of the 8-bit display image (double-buffered)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t display_ready[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
+  uint32_t present_count = 0;
   Queues queues{};
   int persistent_blocks = 148 * 12;
 
@@ -113,6 +117,12 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
     if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) ctx->persistent_blocks = prop.multiProcessorCount * (getenv("VRS_BLOCKS_PER_SM") ? atoi(getenv("VRS_BLOCKS_PER_SM")) : 12);
   }
   for (int i = 0; i < 8; ++i) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
+  for (int i = 0; i < 2; ++i) {
+    if (!alloc((void**)&ctx->display[i], ctx->npix * 4)) return bail(VRS_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&ctx->display_ready[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
+  }
   cudaDeviceSynchronize();
   *out = ctx;
   return VRS_OK;
@@ -138,6 +148,12 @@ void vrs_destroy(vrs_ctx* ctx) {
     cudaFree(Q.hit_T); cudaFree(Q.shadow); cudaFree(Q.cand_ray); cudaFree(Q.shadow_ray);
   }
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(ctx->display[i]);
+    if (ctx->display_ready[i]) cudaEventDestroy(ctx->display_ready[i]);
+    if (ctx->copy_done[i]) cudaEventDestroy(ctx->copy_done[i]);
+  }
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -460,6 +476,32 @@ vrs_status vrs_read_trace(vrs_ctx* ctx, uint32_t* trace4) {
   vrs_status s = read_plane(ctx, ctx->trace, trace4, 16); if (s) return s;
   CK(cudaStreamSynchronize(ctx->stream));
   return VRS_OK;
+}
+
+vrs_status vrs_present_async(vrs_ctx* ctx, uint8_t* rgba8) {
+  if (!ctx || !rgba8) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const int b = (int)(ctx->present_count & 1u);
+  if (ctx->present_count >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_done[b], 0));   // staging buffer is free again
+  const size_t off = (size_t)(ctx->band_y0 - ctx->store_y0) * ctx->W, n = (size_t)(ctx->band_y1 - ctx->band_y0) * ctx->W;
+  launch_display(ctx->stream, ctx->accum + off, ctx->display[b], n);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->display_ready[b], ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->display_ready[b], 0));
+  CK(cudaMemcpyAsync(rgba8, ctx->display[b], n * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CK(cudaEventRecord(ctx->copy_done[b], ctx->copy_stream));
+  ctx->present_count++;
+  return VRS_OK;
+}
+vrs_status vrs_present_wait(vrs_ctx* ctx) {
+  if (!ctx) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->copy_stream));
+  return VRS_OK;
+}
+vrs_status vrs_read_display(vrs_ctx* ctx, uint8_t* rgba8) {
+  vrs_status s = vrs_present_async(ctx, rgba8); if (s) return s;
+  return vrs_present_wait(ctx);
 }
 
 vrs_status vrs_write_image(vrs_ctx* ctx, const char* path) {

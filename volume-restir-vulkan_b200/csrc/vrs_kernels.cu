@@ -327,6 +327,16 @@ __global__ void __launch_bounds__(256) k_shade(const GridDev G, const LightsDev 
   accum[idx] = out;
 }
 
+// restir_post.frag:104: outColor = pow(outColor, vec3(1.0f / 0.8f)) -> 8-bit RGBA for the headless "swapchain"
+__global__ void __launch_bounds__(256) k_display(const float4* __restrict__ accum, uchar4* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 c = accum[i];
+  float r = powf(fmaxf(c.x, 0.0f), 1.0f / 0.8f), g = powf(fmaxf(c.y, 0.0f), 1.0f / 0.8f), b = powf(fmaxf(c.z, 0.0f), 1.0f / 0.8f);
+  out[i] = make_uchar4((unsigned char)(fminf(r, 1.0f) * 255.0f + 0.5f), (unsigned char)(fminf(g, 1.0f) * 255.0f + 0.5f),
+                       (unsigned char)(fminf(b, 1.0f) * 255.0f + 0.5f), 255);
+}
+
 __global__ void k_sample_density(const GridDev G, const int* __restrict__ ijk, uint32_t n, float* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = density_at(G, ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2]);
@@ -359,6 +369,9 @@ void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const Fr
                   int y0, int y1, int store_y0) {
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_shade<<<grid, block, 0, s>>>(G, L, F, cur, rs, accum, y0, y1, store_y0);
+}
+void launch_display(cudaStream_t s, const float4* accum, uchar4* out, size_t n) {
+  k_display<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(accum, out, n);
 }
 void launch_sample_density(cudaStream_t s, const GridDev& G, const int* ijk, uint32_t n, float* out) {
   k_sample_density<<<(n + 255) / 256, 256, 0, s>>>(G, ijk, n, out);

@@ -18,5 +18,6 @@ void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams& F, Pl
                     int y0, int y1, int store_y0, int store_y1);
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, Planes cur, ResPlanes rs, float4* accum,
                   int y0, int y1, int store_y0);
+void launch_display(cudaStream_t s, const float4* accum, uchar4* out, size_t n);
 void launch_sample_density(cudaStream_t s, const GridDev& G, const int* ijk, uint32_t n, float* out);
 }  // namespace vrs
