@@ -31,7 +31,33 @@ WORKLOADS = {
                              desc="smoke.vdb 1920x1080, 64 lights, full spatiotemporal (k=5, 2 iterations)"),
     "smoke_4k_full": dict(asset="smoke", W=3840, H=2160, lights=10000, M=32, flags=1 | 2 | 4, k=5, iters=2,
                           desc="configs[3] shape on smoke.vdb: 3840x2160, 10k lights, full spatiotemporal"),
+    # the assets of configs[2..4] are missing blobs in the reference checkout: deterministic procedural stand-ins
+    "explosion_1080p_full": dict(asset="proc:explosion:296", W=1920, H=1080, lights=-1001, M=32, flags=1 | 2 | 4, k=5, iters=2,
+                                 desc="configs[2] on a procedural stand-in for explosion.vdb (~8M voxels): 1920x1080, <=1001 emissive-voxel lights, full spatiotemporal k=5 x2"),
+    "bunny_4k_full": dict(asset="proc:bunny_cloud:288", W=3840, H=2160, lights=10000, M=32, flags=1 | 2 | 4, k=5, iters=2,
+                          desc="configs[3] on a procedural stand-in for bunny_cloud.vdb (~1.2M voxels): 3840x2160, 10k lights, full spatiotemporal k=5 x2"),
 }
+
+
+def data_desc(wl):
+    if wl["asset"].startswith("proc:"):
+        return "synthetic: camera orbit + generated lights over a deterministic procedural stand-in grid (%s; the reference's asset is a missing blob)" % wl["asset"]
+    return "synthetic camera orbit + generated lights over the reference's %s.vdb grid (assets/%s.vrsg)" % (wl["asset"], wl["asset"])
+
+
+def asset_path(V, name):
+    """assets/<name>.vrsg, or a procedural stand-in generated (host-only, deterministic) into the scratch directory."""
+    if not name.startswith("proc:"):
+        return os.path.join(ROOT, "assets", name + ".vrsg")
+    _, kind, res = name.split(":")
+    d = os.path.join(os.environ.get("TMPDIR", "/tmp"), "vrs_assets")
+    os.makedirs(d, exist_ok=True)
+    path = os.path.join(d, "%s_%s.vrsg" % (kind, res))
+    if not os.path.exists(path):
+        tmp = path + ".%d.tmp" % os.getpid()
+        V.write_procedural_vrsg(kind, int(res), tmp)
+        os.replace(tmp, path)
+    return path
 BYTES_PER_PX = {"initial": 96, "temporal": 96, "spatial_iter": 128, "shade": 128}   # SURVEY.md §8d / BASELINE.md §4
 
 
@@ -88,7 +114,10 @@ def build_scene_inputs(V, wl, R):
     lo, hi = list(gi.world_bbox_min), list(gi.world_bbox_max)
     ctr = [(a + b) * 0.5 for a, b in zip(lo, hi)]
     ext = [(b - a) * 0.5 for a, b in zip(lo, hi)]
-    lights = V.generate_point_lights([c - e for c, e in zip(ctr, ext)], [c + e for c, e in zip(ctr, ext)], False, wl["lights"])
+    if wl["lights"] < 0:      # emissive-voxel lights (Renderer.cpp:1615-1637); "hot" = raw value above 85 % of the maximum
+        lights = R.collectEmissiveLights(0.85 * gi.max_density, -wl["lights"])
+    else:
+        lights = V.generate_point_lights([c - e for c, e in zip(ctr, ext)], [c + e for c, e in zip(ctr, ext)], False, wl["lights"])
     diag = math.sqrt(sum(e * e for e in ext))
     return lights, ctr, diag
 
@@ -111,8 +140,9 @@ def run_ours(args):
     W, H = wl["W"], wl["H"]
     band = V.band_for_rank(H, rank, world) if world > 1 else None
     R = V.Renderer(W, H, spatial_iterations=wl["iters"], band=band, halo_rows=32, device=local)
-    R.loadVDB(os.path.join(ROOT, "assets", wl["asset"] + ".vrsg"))
+    R.loadVDB(asset_path(V, wl["asset"]))
     lights, ctr, diag = build_scene_inputs(V, wl, R)
+    wl = dict(wl, lights=len(lights))
     R.createRestirLights(lights)
     if world > 1:
         uid = [V.comm_unique_id() if rank == 0 else None]
@@ -218,7 +248,7 @@ def run_ours(args):
             traffic = json.load(open(tp)).get("k_initial_dram_bytes_per_launch")
         line = {
             "metric": "ReSTIR frames/s", "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic camera orbit + generated lights over the reference's smoke.vdb grid (assets/smoke.vrsg)",
+            "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_desc(wl),
             "config": {"workload": wl["desc"], "name": args.workload, "resolution": [W, H], "M": wl["M"], "lights": wl["lights"], "flags": wl["flags"],
                        "spatial_iterations": wl["iters"], "partition": "bands x%d, halo 32 rows" % world if world > 1 else "single GPU",
                        "l2": "per-frame working set %.0f MB > 126 MB L2 (inputs larger than L2, no flush)" % (px * 240 / 1e6)},
@@ -253,14 +283,27 @@ def oracle_setup(workload):
     import vrs_pkg
     V = vrs_pkg.load()     # host-only helper (light generation) — no device use
     wl = WORKLOADS[workload]
-    g = grid_py.read_vrsg(os.path.join(ROOT, "assets", wl["asset"] + ".vrsg"))
+    g = grid_py.read_vrsg(asset_path(V, wl["asset"]))
     raw, vmin, _ = grid_py.dense_raw(g)
     dens = vdb_py.density_from_raw(raw, g.level_set, g.background)
     probe = O.OracleScene(dens, vmin, g.voxel_size, g.translation, np.ones((1, 8), np.float32))
     lo, hi = probe.world_bbox()
     ctr = [(a + b) * 0.5 for a, b in zip(lo, hi)]
     ext = [(b - a) * 0.5 for a, b in zip(lo, hi)]
-    lights = V.generate_point_lights([c - e for c, e in zip(ctr, ext)], [c + e for c, e in zip(ctr, ext)], False, wl["lights"])
+    if wl["lights"] < 0:      # emissive-voxel lights, Renderer.cpp:1615-1637 (first voxels in tree order above the threshold)
+        thr = np.float32(0.85) * np.float32(g.leaf_value.max())
+        sel = np.argwhere(g.leaf_mask & (g.leaf_value > thr))[:-wl["lights"]]
+        off = sel[:, 1]
+        ijk = g.leaf_origin[sel[:, 0]] + np.stack([off >> 6, (off >> 3) & 7, off & 7], 1)
+        lights = np.zeros((len(ijk), 8), np.float32)
+        for a in range(3):
+            lights[:, a] = np.float32(probe.c.A) * ijk[:, a].astype(np.float32) + np.float32(probe.c.B[a])
+        lights[:, 3] = 1.0
+        lights[:, 4:7] = [0.6, 0.2, 0.1]
+        lights[:, 7] = np.float32(0.2126) * np.float32(0.6) + np.float32(0.7152) * np.float32(0.2) + np.float32(0.0722) * np.float32(0.1)
+    else:
+        lights = V.generate_point_lights([c - e for c, e in zip(ctr, ext)], [c + e for c, e in zip(ctr, ext)], False, wl["lights"])
+    wl = dict(wl, lights=len(lights))
     scene = O.OracleScene(dens, vmin, g.voxel_size, g.translation, lights)
     diag = math.sqrt(sum(e * e for e in ext))
     return O, wl, scene, ctr, diag
@@ -306,7 +349,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "ReSTIR frames/s", "value": round(fps, 4), "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic camera orbit + generated lights over the reference's smoke.vdb grid (assets/smoke.vrsg)",
+        "data": data_desc(wl),
         "config": {"workload": wl["desc"], "name": args.workload, "resolution": [W, H], "M": wl["M"], "lights": wl["lights"], "flags": wl["flags"],
                    "spatial_iterations": wl["iters"]},
         "cpu_baseline": {"value": round(fps, 4), "unit": "frames/s", "cores": O.num_threads(), "kind": "port",

@@ -114,6 +114,8 @@ vrs_status vrs_convert_vdb(const char* vdb_path, const char* grid_name, const ch
 /* Deterministic procedural stand-ins for the assets missing from the reference checkout
  * (.MISSING_LARGE_BLOBS:1-4): kind 0 = "bunny_cloud", 1 = "explosion", 2 = "fire", 3 = "torus_knot_helix". */
 vrs_status vrs_make_procedural_grid(vrs_ctx* ctx, int kind, uint32_t resolution);
+/* Host-only: generate the same stand-in and write it as a `.vrsg` snapshot (no device needed). */
+vrs_status vrs_write_procedural_vrsg(int kind, uint32_t resolution, const char* vrsg_path);
 
 typedef struct {
   int32_t  bbox_min[3], bbox_max[3];    /* active-voxel bounding box (index space) */
@@ -133,6 +135,11 @@ vrs_status vrs_grid_sample_device(vrs_ctx* ctx, const int32_t* ijk, uint32_t n, 
 /* Renderer::createRestirLights (src/Renderer.cpp:1587-1691): upload point lights and build the alias
  * table with createAliasTable semantics (src/utils/restir_utils.cpp:90-155), pdf = emission_luminance.w. */
 vrs_status vrs_set_lights(vrs_ctx* ctx, const vrs_point_light* lights, uint32_t n);
+/* Emissive-voxel lights of Renderer::createRestirLights (src/Renderer.cpp:1615-1637): walk the active voxels in tree
+ * order, turn every voxel whose raw value exceeds `threshold` (the reference tests `temp > 275` on the temperature
+ * grid) into a point light at the voxel's world position with emission (0.6, 0.2, 0.1), stop after `max_lights`
+ * (the reference stops after 1001).  Host-side; fills `out` and returns the count. */
+vrs_status vrs_collect_emissive_lights(const vrs_ctx* ctx, float threshold, uint32_t max_lights, vrs_point_light* out, uint32_t* count);
 vrs_status vrs_set_triangle_lights(vrs_ctx* ctx, const vrs_triangle_light* lights, uint32_t n); /* VRS_ERR_UNSUPPORTED */
 vrs_status vrs_get_alias_table(const vrs_ctx* ctx, vrs_alias_table_cell* out, uint32_t n);
 

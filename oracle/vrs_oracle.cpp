@@ -734,7 +734,8 @@ void orc_pass_initial(const orc_scene* s, const orc_global_uniforms* gu, const o
             size_t pidx = size_t(fy) * W + size_t(fx);
             GInfo pg = ginfo_from_images(prev, pidx, ru->currCamPos);                  // prevGInfo.camPos = gInfo.camPos (:259)
             V3 pd = sub(gi.worldPos, pg.worldPos);
-            if (dot(pd, pd) < 0.01f) {
+            // a previous miss holds no data; the reference would reject it anyway (cleared normal fails :274)
+            if (!(prev.worldPos[pidx * 4 + 3] < 0.5f) && dot(pd, pd) < 0.01f) {
               V3 ad = v3(gi.albedo[0] - pg.albedo[0], gi.albedo[1] - pg.albedo[1], gi.albedo[2] - pg.albedo[2]);
               if (dot(ad, ad) < 0.01f) {
                 if (dot(gi.normal, pg.normal) > 0.5f) {

@@ -108,10 +108,11 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
   if (cfg->enable_trace && !alloc((void**)&ctx->trace, ctx->npix * 16)) return bail(VRS_ERR_CUDA);
   {
     Queues& Q = ctx->queues;
-    if (!alloc((void**)&Q.counters, 64) || !alloc((void**)&Q.cand, ctx->npix * 4) || !alloc((void**)&Q.hit_pix, ctx->npix * 4) ||
-        !alloc((void**)&Q.hit_t, ctx->npix * 4) || !alloc((void**)&Q.hit_vcode, ctx->npix * 4) || !alloc((void**)&Q.hit_seed, ctx->npix * 4) ||
-        !alloc((void**)&Q.hit_T, ctx->npix * 4) || !alloc((void**)&Q.shadow, ctx->npix * 4) ||
-        !alloc((void**)&Q.cand_ray, ctx->npix * 32) || !alloc((void**)&Q.shadow_ray, ctx->npix * 32))
+    const size_t ncompact = (ctx->npix + 2047) / 2048 + 1;
+    if (!alloc((void**)&Q.counters, 64) || !alloc((void**)&Q.cand, ctx->npix * 4) || !alloc((void**)&Q.cand_ray, ctx->npix * 32) ||
+        !alloc((void**)&Q.flag, ctx->npix + 16) || !alloc((void**)&Q.block_count, ncompact * 4) || !alloc((void**)&Q.hit_pix, ctx->npix * 4) ||
+        !alloc((void**)&Q.hit_seed, ctx->npix * 4) || !alloc((void**)&Q.hit_T, ctx->npix * 4) || !alloc((void**)&Q.shadow, ctx->npix * 4) ||
+        !alloc((void**)&Q.shadow_ray, ctx->npix * 32))
       return bail(VRS_ERR_CUDA);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) ctx->persistent_blocks = prop.multiProcessorCount * (getenv("VRS_BLOCKS_PER_SM") ? atoi(getenv("VRS_BLOCKS_PER_SM")) : 12);
@@ -144,8 +145,8 @@ void vrs_destroy(vrs_ctx* ctx) {
   cudaFree(ctx->accum); cudaFree(ctx->trace); cudaFree(ctx->d_lights); cudaFree(ctx->d_alias);
   {
     Queues& Q = ctx->queues;
-    cudaFree(Q.counters); cudaFree(Q.cand); cudaFree(Q.hit_pix); cudaFree(Q.hit_t); cudaFree(Q.hit_vcode); cudaFree(Q.hit_seed);
-    cudaFree(Q.hit_T); cudaFree(Q.shadow); cudaFree(Q.cand_ray); cudaFree(Q.shadow_ray);
+    cudaFree(Q.counters); cudaFree(Q.cand); cudaFree(Q.cand_ray); cudaFree(Q.flag); cudaFree(Q.block_count); cudaFree(Q.hit_pix);
+    cudaFree(Q.hit_seed); cudaFree(Q.hit_T); cudaFree(Q.shadow); cudaFree(Q.shadow_ray);
   }
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (int i = 0; i < 2; ++i) {
@@ -259,6 +260,14 @@ vrs_status vrs_make_procedural_grid(vrs_ctx* ctx, int kind, uint32_t resolution)
   return upload_grid(ctx);
 }
 
+vrs_status vrs_write_procedural_vrsg(int kind, uint32_t resolution, const char* vrsg_path) {
+  if (!vrsg_path) return VRS_ERR_INVALID;
+  HostGrid g; std::string err;
+  if (!make_procedural(kind, resolution, g, err)) return fail(nullptr, VRS_ERR_INVALID, err);
+  if (!write_vrsg(vrsg_path, g, err)) return fail(nullptr, VRS_ERR_IO, err);
+  return VRS_OK;
+}
+
 vrs_status vrs_get_grid_info(const vrs_ctx* ctx, vrs_grid_info* o) {
   if (!ctx || !o || !ctx->has_grid) return VRS_ERR_INVALID;
   const HostGrid& h = ctx->host_grid;
@@ -310,6 +319,25 @@ vrs_status vrs_set_lights(vrs_ctx* ctx, const vrs_point_light* lights, uint32_t 
   CK(cudaMemcpy(ctx->d_alias, ctx->alias_host.data(), (size_t)n * sizeof(vrs_alias_table_cell), cudaMemcpyHostToDevice));
   ctx->lights.lights = (const float4*)ctx->d_lights; ctx->lights.alias = (const float4*)ctx->d_alias;
   ctx->lights.nlights = (int)n; ctx->lights.ntable = (int)n;
+  return VRS_OK;
+}
+vrs_status vrs_collect_emissive_lights(const vrs_ctx* ctx, float threshold, uint32_t max_lights, vrs_point_light* out, uint32_t* count) {
+  if (!ctx || !ctx->has_grid || !out || !count) return VRS_ERR_INVALID;
+  const HostGrid& h = ctx->host_grid;
+  const GridDev& G = ctx->grid;
+  uint32_t n = 0;
+  for (size_t l = 0; l < h.nleaf() && n < max_lights; ++l)
+    for (int o = 0; o < 512 && n < max_lights; ++o) {
+      if (!((h.leaf_mask[l * 8 + (o >> 6)] >> (o & 63)) & 1)) continue;
+      if (!(h.leaf_value[l * 512 + o] > threshold)) continue;
+      const int ijk[3] = {h.leaf_origin[3 * l] + (o >> 6), h.leaf_origin[3 * l + 1] + ((o >> 3) & 7), h.leaf_origin[3 * l + 2] + (o & 7)};
+      vrs_point_light& p = out[n++];
+      for (int a = 0; a < 3; ++a) p.pos[a] = G.A * (float)ijk[a] + G.B[a];            // sphere centre, Renderer.cpp:1427-1431
+      p.pos[3] = 1.0f;
+      p.emission_luminance[0] = 0.6f; p.emission_luminance[1] = 0.2f; p.emission_luminance[2] = 0.1f;   // :1627
+      p.emission_luminance[3] = 0.2126f * 0.6f + 0.7152f * 0.2f + 0.0722f * 0.1f;                        // shader::luminance
+    }
+  *count = n;
   return VRS_OK;
 }
 vrs_status vrs_set_triangle_lights(vrs_ctx* ctx, const vrs_triangle_light*, uint32_t) {
@@ -371,8 +399,8 @@ vrs_status vrs_pass_spatial(vrs_ctx* ctx, const vrs_restir_uniforms* ru, uint32_
   cudaSetDevice(ctx->device);
   FrameParams F; vrs_status s = make_params(ctx, nullptr, ru, nullptr, clock, F); if (s) return s;
   int dst = (ctx->src_r + 1) % 3;
-  launch_spatial(ctx->stream, ctx->lights, F, planes_of(ctx, ctx->cur_g), res_of(ctx, ctx->src_r), res_of(ctx, dst), iteration, ctx->band_y0,
-                 ctx->band_y1, ctx->store_y0, ctx->store_y1);
+  launch_spatial(ctx->stream, ctx->lights, F, planes_of(ctx, ctx->cur_g), res_of(ctx, ctx->src_r), res_of(ctx, dst), ctx->queues, iteration,
+                 ctx->store_y0, ctx->store_y1, ctx->persistent_blocks);
   CK(cudaGetLastError());
   ctx->src_r = dst; ctx->timings.launches += 1;
   return VRS_OK;
@@ -454,21 +482,31 @@ vrs_status vrs_read_frame(vrs_ctx* ctx, float* rgba) {
   CK(cudaStreamSynchronize(ctx->stream));
   return VRS_OK;
 }
+// G-buffer / reservoir readback goes through k_export: miss pixels carry no data on the device
+static vrs_status export_planes(vrs_ctx* ctx, int g_index, int r_index, float* dst[6]) {
+  const size_t first = (size_t)(ctx->band_y0 - ctx->store_y0) * ctx->W, n = (size_t)(ctx->band_y1 - ctx->band_y0) * ctx->W;
+  float4* tmp = nullptr;
+  CK(cudaMalloc(&tmp, n * 16 * 6));
+  launch_export(ctx->stream, planes_of(ctx, g_index), res_of(ctx, r_index), tmp, first, n);
+  cudaError_t e = cudaGetLastError();
+  for (int p = 0; p < 6 && e == cudaSuccess; ++p)
+    if (dst[p]) e = cudaMemcpyAsync(dst[p], tmp + (size_t)p * n, n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(tmp);
+  if (e != cudaSuccess) { ctx->err = std::string("readback: ") + cudaGetErrorString(e); return VRS_ERR_CUDA; }
+  return VRS_OK;
+}
 vrs_status vrs_read_gbuffer(vrs_ctx* ctx, float* worldPos, float* albedo, float* normal, float* matProps) {
   if (!ctx) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  float* dst[4] = {worldPos, albedo, normal, matProps};
-  for (int p = 0; p < 4; ++p) { vrs_status s = read_plane(ctx, ctx->g_planes[ctx->last_g][p], dst[p], 16); if (s) return s; }
-  CK(cudaStreamSynchronize(ctx->stream));
-  return VRS_OK;
+  float* dst[6] = {worldPos, albedo, normal, matProps, nullptr, nullptr};
+  return export_planes(ctx, ctx->last_g, ctx->src_r, dst);
 }
 vrs_status vrs_read_reservoirs(vrs_ctx* ctx, float* info, float* weight) {
   if (!ctx) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  vrs_status s = read_plane(ctx, ctx->r_planes[ctx->src_r][0], info, 16); if (s) return s;
-  s = read_plane(ctx, ctx->r_planes[ctx->src_r][1], weight, 16); if (s) return s;
-  CK(cudaStreamSynchronize(ctx->stream));
-  return VRS_OK;
+  float* dst[6] = {nullptr, nullptr, nullptr, nullptr, info, weight};
+  return export_planes(ctx, ctx->last_g, ctx->src_r, dst);
 }
 vrs_status vrs_read_trace(vrs_ctx* ctx, uint32_t* trace4) {
   if (!ctx || !trace4 || !ctx->trace) return VRS_ERR_INVALID;

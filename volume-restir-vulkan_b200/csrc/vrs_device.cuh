@@ -57,18 +57,21 @@ struct Planes {                   // band-local RGBA32F planes (reference layout
 };
 struct ResPlanes { float4* info; float4* weight; };
 
-// Work queues of the initial pass (all indices are band-local pixel indices or hit slots)
+// Per-frame work lists (all indices are band-local pixel indices or hit slots).  Only pixels whose primary ray has a
+// real collision ("hits", listed in pixel order) carry G-buffer / reservoir data; for every other pixel the only word
+// anybody reads is worldPos.w = 0, which is what keeps the frame's HBM traffic proportional to the
+// part of the screen the volume covers.
 struct Queues {
-  uint32_t* counters;   // [0] candidates [1] hits [2] shadow rays [3] primary queue head [4] shadow queue head
-  uint32_t* cand;       // pixels whose primary ray enters the grid window
-  uint32_t* hit_pix;    // pixel of hit slot s
-  float* hit_t;         // free-flight distance of the primary collision
-  uint32_t* hit_vcode;  // collided voxel, linear code inside the window
-  uint32_t* hit_seed;   // RNG state carried between the kernels of the pass
-  float* hit_T;         // shadow transmittance estimate (1 when no shadow ray was needed)
-  uint32_t* shadow;     // hit slots that need a shadow ray
-  float4* cand_ray;     // 2 x float4 per candidate: clipped primary ray {o.xyz, t0}, {d.xyz, t1}
-  float4* shadow_ray;   // 2 x float4 per shadow-queue entry
+  uint32_t* counters;     // [0] candidates [1] hits [2] shadow rays [3] primary queue head [4] shadow queue head
+  uint32_t* cand;         // pixels whose primary ray enters the grid window
+  float4* cand_ray;       // 2 x float4 per candidate: clipped primary ray {o.xyz, t0}, {d.xyz, t1}
+  uint8_t* flag;          // per pixel: 1 = real collision found by k_primary
+  uint32_t* block_count;  // hit compaction: per 2048-pixel block count, then exclusive offset
+  uint32_t* hit_pix;      // pixel of hit slot s, ascending
+  uint32_t* hit_seed;     // RNG state carried between the kernels of the pass
+  float* hit_T;           // shadow transmittance estimate (1 when no shadow ray was needed)
+  uint32_t* shadow;       // hit slots that need a shadow ray
+  float4* shadow_ray;     // 2 x float4 per shadow-queue entry
 };
 
 // ------------------------------------------------------------------ small vector helpers
@@ -203,36 +206,85 @@ __device__ __forceinline__ void packReservoir(const Res& r, float4& info, float4
 }
 
 // ------------------------------------------------------------------ p-hat: headers/restirUtils.glsl (point lights)
-struct PHatGeom { V3 wi; float cosIn, cosOut, cosHalf, cosInHalf, geometry; bool back; };
-__device__ __forceinline__ PHatGeom phat_geometry(V3 lightPos, const GInfo& g) {  // :39-71
+// The terms of evaluatePHat / disneyBrdf* that depend only on the shading point (wo, cosOut and everything derived
+// from them) are computed once per pixel in ShadePre; the per-light remainder performs the same fp32 operations on
+// the same values in the same order, so the result is bit-identical to evaluating the reference expression per light.
+struct ShadePre {
+  V3 wo;
+  float cosOut, fresnelOut, smithOut, a;
+};
+__device__ __forceinline__ ShadePre shade_pre(const GInfo& g) {
+  ShadePre p;
+  p.wo = normalize(sub(g.camPos, g.worldPos));                        // restirUtils.glsl:62
+  p.cosOut = dot(g.normal, p.wo);                                     // :65
+  p.fresnelOut = schlickFresnel(p.cosOut);                            // disneyBRDF.glsl:28
+  p.a = gmax(0.001f, g.roughness * g.roughness);                      // disneyBRDF.glsl:53
+  p.smithOut = smithG_GGX(p.cosOut, p.a);                             // disneyBRDF.glsl:59
+  return p;
+}
+struct PHatGeom { float cosIn, cosHalf, cosInHalf, geometry; bool back; };
+__device__ __forceinline__ PHatGeom phat_geometry(V3 lightPos, const GInfo& g, const ShadePre& pre) {  // :39-71
   PHatGeom o;
   V3 wi = sub(lightPos, g.worldPos);
   o.back = dot(wi, g.normal) < 0.0f;
   float sqrDist = dot(wi, wi);
   wi = divs(wi, sqrtf(sqrDist));
-  V3 wo = normalize(sub(g.camPos, g.worldPos));
   o.cosIn = dot(g.normal, wi);
-  o.cosOut = dot(g.normal, wo);
-  V3 halfVec = normalize(add(wi, wo));
+  V3 halfVec = normalize(add(wi, pre.wo));
   o.cosHalf = dot(g.normal, halfVec);
   o.cosInHalf = dot(wi, halfVec);
   o.geometry = 1.0f * o.cosIn / sqrDist;
-  o.wi = wi;
   return o;
 }
-__device__ __forceinline__ float evaluatePHat(const LightsDev& L, uint32_t lightIdx, const GInfo& g) {   // :36-78
+// disneyBrdfDiffuseFactor (:25-33) and disneyBrdfSpecularFactors (:47-62) with the per-pixel terms taken from ShadePre
+__device__ __forceinline__ float diffuseFactorPre(const PHatGeom& q, const ShadePre& pre, float roughness, float metallic) {
+  float fresnelIn = schlickFresnel(q.cosIn);
+  float fd90 = 0.5f + 2.0f * q.cosInHalf * q.cosInHalf * roughness;
+  float fd = gmix(1.0f, fd90, fresnelIn) * gmix(1.0f, fd90, pre.fresnelOut);
+  return fd * (1.0f - metallic) / VRS_PI;
+}
+__device__ __forceinline__ void specularFactorsPre(const PHatGeom& q, const ShadePre& pre, float& fresnelInHalf, float& GsDs) {
+  fresnelInHalf = schlickFresnel(q.cosInHalf);
+  float Ds = GTR2(q.cosHalf, pre.a);
+  float Gs = smithG_GGX(q.cosIn, pre.a);
+  Gs *= pre.smithOut;
+  GsDs = Gs * Ds;
+}
+__device__ __forceinline__ float evaluatePHat(const LightsDev& L, uint32_t lightIdx, const GInfo& g, const ShadePre& pre) {   // :36-78
   float4 lp = __ldg(&L.lights[2 * lightIdx]);
   float4 le = __ldg(&L.lights[2 * lightIdx + 1]);
-  PHatGeom q = phat_geometry(v3(lp.x, lp.y, lp.z), g);
+  PHatGeom q = phat_geometry(v3(lp.x, lp.y, lp.z), g, pre);
   if (q.back) return 0.0f;
-  return le.w * disneyBrdfLuminance(q.cosIn, q.cosOut, q.cosHalf, q.cosInHalf, g.albedoLum, g.roughness, g.metallic) * q.geometry;
+  float brdf = 0.0f;                                                                  // disneyBrdfLuminance :98-110
+  if (!(q.cosIn < 0.0f)) {
+    float diffuse = g.albedoLum * diffuseFactorPre(q, pre, g.roughness, g.metallic);
+    float fih, gsds;
+    specularFactorsPre(q, pre, fih, gsds);
+    float specLum = gmix(0.04f, g.albedoLum, g.metallic);
+    float Fs = gmix(specLum, 1.0f, fih);
+    brdf = diffuse + Fs * gsds;
+  }
+  return le.w * brdf * q.geometry;
+}
+__device__ __forceinline__ float evaluatePHat(const LightsDev& L, uint32_t lightIdx, const GInfo& g) {
+  return evaluatePHat(L, lightIdx, g, shade_pre(g));
 }
 __device__ __forceinline__ V3 evaluatePHatFull(const LightsDev& L, uint32_t lightIdx, const GInfo& g) {  // :80-122
   float4 lp = __ldg(&L.lights[2 * lightIdx]);
   float4 le = __ldg(&L.lights[2 * lightIdx + 1]);
-  PHatGeom q = phat_geometry(v3(lp.x, lp.y, lp.z), g);
+  ShadePre pre = shade_pre(g);
+  PHatGeom q = phat_geometry(v3(lp.x, lp.y, lp.z), g, pre);
   if (q.back) return v3(0.0f, 0.0f, 0.0f);
-  V3 brdf = disneyBrdfColor(q.cosIn, q.cosOut, q.cosHalf, q.cosInHalf, v3(g.albedo[0], g.albedo[1], g.albedo[2]), g.roughness, g.metallic);
+  V3 brdf = v3(0.0f, 0.0f, 0.0f);                                                     // disneyBrdfColor :86-97
+  if (!(q.cosIn < 0.0f)) {
+    V3 albedo = v3(g.albedo[0], g.albedo[1], g.albedo[2]);
+    V3 diffuse = muls(albedo, diffuseFactorPre(q, pre, g.roughness, g.metallic));
+    float fih, gsds;
+    specularFactorsPre(q, pre, fih, gsds);
+    V3 specColor = v3(gmix(0.04f, albedo.x, g.metallic), gmix(0.04f, albedo.y, g.metallic), gmix(0.04f, albedo.z, g.metallic));
+    V3 Fs = v3(gmix(specColor.x, 1.0f, fih), gmix(specColor.y, 1.0f, fih), gmix(specColor.z, 1.0f, fih));
+    brdf = add(diffuse, muls(Fs, gsds));
+  }
   return muls(mul(v3(le.x, le.y, le.z), brdf), q.geometry);
 }
 
@@ -246,8 +298,8 @@ __device__ __forceinline__ void updateReservoir(Res& res, uint32_t lightIdx, int
   }
 }
 __device__ __forceinline__ void addSampleToReservoir(const LightsDev& L, Res& res, uint32_t lightIdx, int32_t lightKind,
-                                                     float lightPdf, const GInfo& g, uint32_t& seed) {   // :45-54
-  float pHat = evaluatePHat(L, lightIdx, g);
+                                                     float lightPdf, const GInfo& g, const ShadePre& pre, uint32_t& seed) {   // :45-54
+  float pHat = evaluatePHat(L, lightIdx, g, pre);
   float weight = pHat / lightPdf;
   res.M += 1;
   float w = (res.sumWeights + weight) / (float(res.M) * pHat);

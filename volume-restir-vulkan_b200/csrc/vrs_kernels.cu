@@ -14,20 +14,21 @@ static constexpr int FLAG_FINAL_VISIBILITY = 1 << 4, FLAG_FINALIZE_W = 1 << 5;
 static constexpr int MAX_NEIGHBORS = 16;
 
 // -------------------------------------------------------------------------------------------------
-// Initial pass — restir.rgen main (:136-290) on a volume, as five kernels over device-side work queues.
-// The pass is instruction-issue bound (ncu, profiles/r01_v1_*): what matters is how many of the 32 lanes do
-// useful work, so each stage runs on the smallest, densest set of lanes it can:
-//   A0 k_classify  every pixel: primary ray (:142-148) vs. the grid window; rays that miss it store the
-//                  empty G-buffer / reservoir at once (coalesced, HBM-bound), the rest go to a queue.
-//   A1 k_primary   persistent warps: delta-tracking raymarch of queued rays as a flattened state machine with
-//                  lane refill (a finished lane takes the next ray instead of idling until the warp drains).
-//   A2 k_ris       one thread per real collision, compact: G-buffer stores (:193-197), M-candidate RIS
-//                  (:203-227) — uniform trip count, no divergence.
-//   A3 k_shadow    persistent warps + refill: ratio-tracking transmittance toward the selected light (:229-235).
-//   A4 k_finish    one thread per collision: apply the transmittance, temporal merge (:237-284), pack (:286-289).
+// Initial pass — restir.rgen main (:136-290) on a volume, as a chain of kernels over device-side work lists.
+// The pass is instruction-issue bound (ncu, profiles/): what matters is how many of the 32 lanes do useful work and
+// how few bytes the empty part of the screen costs, so each stage runs on the smallest, densest set it can:
+//   A0 k_classify   every pixel: primary ray (:142-148) vs. the grid window; writes worldPos = 0 (the miss marker,
+//                   16 B/px) and queues the rays that enter the window.
+//   A1 k_primary    persistent warps: residual delta tracking of queued rays, unit steps batched per warp, lane
+//                   refill; a real collision leaves {t, voxel, RNG state, 1} in the pixel's worldPos slot.
+//   A2 k_hit_*      ordered stream compaction of the hit flags -> hit list in pixel order (coalesced consumers).
+//   A3 k_ris        one thread per hit: G-buffer stores (:193-197), M-candidate RIS (:203-227), shadow-ray set-up.
+//   A4 k_shadow     persistent warps: ratio-tracking transmittance toward the selected light (:229-235).
+//   A5 k_finish     one thread per hit: apply the transmittance, temporal merge (:237-284), pack (:286-289).
 // -------------------------------------------------------------------------------------------------
 enum { Q_CAND = 0, Q_HIT = 1, Q_SHADOW = 2, Q_PRIMARY_HEAD = 3, Q_SHADOW_HEAD = 4 };
 static constexpr int REFILL_MIN_IDLE = 16;
+static constexpr int COMPACT_BLOCK = 2048;      // pixels per compaction block (256 threads x 8 flags)
 
 __device__ __forceinline__ void primary_ray(const FrameParams& F, int x, int y, V3& org, V3& dir) {   // :142-148
   float ux = float(x) / float(F.W), uy = float(y) / float(F.H);
@@ -40,16 +41,7 @@ __device__ __forceinline__ void primary_ray(const FrameParams& F, int x, int y, 
   org = v3(o4[0], o4[1], o4[2]); dir = v3(d4[0], d4[1], d4[2]);
 }
 
-__device__ __forceinline__ void store_miss(const Planes& cur, const ResPlanes& outR, uint32_t* trace, size_t idx, uint32_t ntent,
-                                           uint32_t ncells, uint32_t seed) {
-  cur.worldPos[idx] = make_float4(0.f, 0.f, 0.f, 0.f); cur.albedo[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-  cur.normal[idx] = make_float4(0.f, 0.f, 0.f, 1.f); cur.mat[idx] = make_float4(0.f, 0.f, 1.f, 1.f);   // :193-197 on a miss
-  float4 a, b; packReservoir(newReservoir(), a, b);                                                      // SURVEY App. C-5
-  outR.info[idx] = a; outR.weight[idx] = b;
-  if (trace) { trace[idx * 4 + 0] = 0xFFFFFFFFu; trace[idx * 4 + 1] = ntent; trace[idx * 4 + 2] = ncells; trace[idx * 4 + 3] = seed; }
-}
-
-__global__ void __launch_bounds__(256) k_classify(const GridDev G, const FrameParams F, Planes cur, ResPlanes outR, Queues Q,
+__global__ void __launch_bounds__(256) k_classify(const GridDev G, const FrameParams F, Planes cur, Queues Q,
                                                   uint32_t* __restrict__ trace, int y0, int y1, int store_y0) {
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = y0 + blockIdx.y * 8 + threadIdx.y;
@@ -60,8 +52,12 @@ __global__ void __launch_bounds__(256) k_classify(const GridDev G, const FramePa
     idx = (size_t)(y - store_y0) * F.W + x;
     V3 org, dir; primary_ray(F, x, y, org, dir);
     enters = clip_ray(G, org, dir, 0.0001f, 100000.0f, seg);                       // :164-166 ray range
-    // every pixel starts as a miss (coalesced stores); k_ris overwrites the pixels that get a real collision
-    store_miss(cur, outR, trace, idx, 0u, 0u, pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_INITIAL));
+    cur.worldPos[idx] = make_float4(0.f, 0.f, 0.f, 0.f);                           // miss until k_primary says otherwise
+    Q.flag[idx] = 0;
+    if (trace) {
+      trace[idx * 4 + 0] = 0xFFFFFFFFu; trace[idx * 4 + 1] = 0u; trace[idx * 4 + 2] = 0u;
+      trace[idx * 4 + 3] = pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_INITIAL);
+    }
   }
   const unsigned b = __ballot_sync(0xffffffffu, enters);
   if (b) {
@@ -79,7 +75,7 @@ __global__ void __launch_bounds__(256) k_classify(const GridDev G, const FramePa
 }
 
 struct PrimaryJob {
-  const FrameParams& F; Queues Q; uint32_t* trace; int store_y0;
+  const FrameParams& F; Planes cur; Queues Q; uint32_t* trace; int store_y0;
   uint32_t idx;
   __device__ __forceinline__ bool fetch(const GridDev& G, uint32_t j, Ray<0>& ray, uint32_t& seed) {
     idx = Q.cand[j];
@@ -91,17 +87,71 @@ struct PrimaryJob {
   }
   __device__ __forceinline__ void retire(const GridDev& G, const Ray<0>& ray, uint32_t seed) {
     if (ray.hit) {
-      const uint32_t s = warp_append(&Q.counters[Q_HIT]);
-      Q.hit_pix[s] = idx; Q.hit_t[s] = ray.t; Q.hit_seed[s] = seed;
-      Q.hit_vcode[s] = uint32_t(ray.vox[0] - G.vmin[0]) + uint32_t(G.vdim[0]) * (uint32_t(ray.vox[1] - G.vmin[1]) + uint32_t(G.vdim[1]) * uint32_t(ray.vox[2] - G.vmin[2]));
+      const uint32_t vcode = uint32_t(ray.vox[0] - G.vmin[0]) + uint32_t(G.vdim[0]) * (uint32_t(ray.vox[1] - G.vmin[1]) + uint32_t(G.vdim[1]) * uint32_t(ray.vox[2] - G.vmin[2]));
+      cur.worldPos[idx] = make_float4(ray.t, __uint_as_float(vcode), __uint_as_float(seed), 1.0f);     // scratch until k_ris
+      Q.flag[idx] = 1;
     }
     if (trace) { trace[(size_t)idx * 4 + 1] = ray.ntent; trace[(size_t)idx * 4 + 2] = ray.ncells; trace[(size_t)idx * 4 + 3] = seed; }
   }
 };
 
-__global__ void __launch_bounds__(128) k_primary(const GridDev G, const FrameParams F, Queues Q, uint32_t* __restrict__ trace, int store_y0, int refill) {
-  PrimaryJob job{F, Q, trace, store_y0, 0u};
+__global__ void __launch_bounds__(128) k_primary(const GridDev G, const FrameParams F, Planes cur, Queues Q, uint32_t* __restrict__ trace,
+                                                 int store_y0, int refill) {
+  PrimaryJob job{F, cur, Q, trace, store_y0, 0u};
   march_loop<0>(G, job, &Q.counters[Q_PRIMARY_HEAD], Q.counters[Q_CAND], refill);
+}
+
+// ---- ordered compaction of the hit flags (count per block, scan the block counts, scatter in pixel order)
+__device__ __forceinline__ uint32_t flags8(const uint8_t* flag, size_t first, size_t n) {   // 8 consecutive flags as a bit mask
+  uint32_t m = 0;
+  if (first + 8 <= n) {
+    const uint2 v = *reinterpret_cast<const uint2*>(flag + first);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m |= ((v.x >> (8 * k)) & 0xffu) ? (1u << k) : 0u; m |= ((v.y >> (8 * k)) & 0xffu) ? (1u << (4 + k)) : 0u; }
+  } else {
+    for (int k = 0; k < 8; ++k) if (first + k < n && flag[first + k]) m |= 1u << k;
+  }
+  return m;
+}
+__global__ void __launch_bounds__(256) k_hit_count(const uint8_t* __restrict__ flag, size_t first_pix, size_t npix, uint32_t* __restrict__ block_count) {
+  __shared__ uint32_t s_warp[8];
+  const size_t base = first_pix + (size_t)blockIdx.x * COMPACT_BLOCK + (size_t)threadIdx.x * 8;
+  uint32_t c = base < first_pix + npix ? __popc(flags8(flag, base, first_pix + npix)) : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; block_count[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024) k_hit_scan(uint32_t* __restrict__ block_count, uint32_t nblocks, uint32_t* __restrict__ counters) {
+  __shared__ uint32_t s_part[1024];
+  const uint32_t per = (nblocks + 1023u) / 1024u;
+  const uint32_t lo = threadIdx.x * per, hi = min(lo + per, nblocks);
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; ++i) sum += block_count[i];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t acc = 0; for (int i = 0; i < 1024; ++i) { uint32_t v = s_part[i]; s_part[i] = acc; acc += v; } counters[Q_HIT] = acc; }
+  __syncthreads();
+  uint32_t acc = s_part[threadIdx.x];
+  for (uint32_t i = lo; i < hi; ++i) { uint32_t v = block_count[i]; block_count[i] = acc; acc += v; }
+}
+__global__ void __launch_bounds__(256) k_hit_scatter(const uint8_t* __restrict__ flag, size_t first_pix, size_t npix,
+                                                     const uint32_t* __restrict__ block_offset, uint32_t* __restrict__ hit_pix) {
+  __shared__ uint32_t s_warp[8];
+  const size_t base = first_pix + (size_t)blockIdx.x * COMPACT_BLOCK + (size_t)threadIdx.x * 8;
+  const uint32_t m = base < first_pix + npix ? flags8(flag, base, first_pix + npix) : 0u;
+  const uint32_t c = __popc(m);
+  uint32_t incl = c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t off = block_offset[blockIdx.x] + incl - c;
+  for (int w = 0; w < warp; ++w) off += s_warp[w];
+  uint32_t mm = m;
+  while (mm) { const int k = __ffs(mm) - 1; mm &= mm - 1; hit_pix[off++] = (uint32_t)(base + k); }
 }
 
 __global__ void __launch_bounds__(128) k_ris(const GridDev G, const LightsDev L, const FrameParams F, Planes cur, ResPlanes outR, Queues Q,
@@ -110,10 +160,11 @@ __global__ void __launch_bounds__(128) k_ris(const GridDev G, const LightsDev L,
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
     const uint32_t idx = Q.hit_pix[s];
     const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
-    uint32_t seed = Q.hit_seed[s];
+    const float4 scratch = cur.worldPos[idx];                                      // {t, voxel code, RNG state, 1} from k_primary
+    uint32_t seed = __float_as_uint(scratch.z);
     V3 org, dir; primary_ray(F, x, y, org, dir);
-    const V3 P = add(org, muls(dir, Q.hit_t[s]));
-    const uint32_t vcode = Q.hit_vcode[s];
+    const V3 P = add(org, muls(dir, scratch.x));
+    const uint32_t vcode = __float_as_uint(scratch.y);
     const int i = (int)(vcode % (uint32_t)G.vdim[0]) + G.vmin[0];
     const int j = (int)((vcode / (uint32_t)G.vdim[0]) % (uint32_t)G.vdim[1]) + G.vmin[1];
     const int k = (int)(vcode / ((uint32_t)G.vdim[0] * (uint32_t)G.vdim[1])) + G.vmin[2];
@@ -135,12 +186,13 @@ __global__ void __launch_bounds__(128) k_ris(const GridDev G, const LightsDev L,
     gi.sampleSeed = 0;
     Res res = newReservoir();
     if (dot(gi.normal, gi.normal) != 0.0f) {                                                           // :205
+      const ShadePre pre = shade_pre(gi);
       for (uint32_t c = 0; c < F.M; ++c) {                                                             // :206-226
         gi.sampleSeed = seed;                                                                          // :213
         float r1 = rnd(seed), r2 = rnd(seed);                                                          // :116, GLSL left-to-right
         uint32_t sel; float pdf;
         aliasTableSample(L, r1, r2, sel, pdf);
-        addSampleToReservoir(L, res, sel, 0, pdf, gi, seed);                                           // :224-225
+        addSampleToReservoir(L, res, sel, 0, pdf, gi, pre, seed);                                      // :224-225
       }
     }
     if ((F.flags & FLAG_FINALIZE_W) != 0 && res.w > 0.0f) res.w = res.sumWeights / (float(res.M) * res.pHat);
@@ -207,16 +259,18 @@ __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FramePa
         int fx = int(q[0]), fy = int(q[1]);
         if (fy >= store_y0 && fy < store_y1) {                                                         // rows held by this context
           size_t pidx = (size_t)(fy - store_y0) * F.W + (size_t)fx;
-          GInfo pg = ginfo_from_planes(prev, pidx, F.camPos);                                          // prevGInfo.camPos = gInfo.camPos (:259)
-          V3 pd = sub(gi.worldPos, pg.worldPos);
-          if (dot(pd, pd) < 0.01f) {
-            V3 ad = v3(gi.albedo[0] - pg.albedo[0], gi.albedo[1] - pg.albedo[1], gi.albedo[2] - pg.albedo[2]);
-            if (dot(ad, ad) < 0.01f) {
-              if (dot(gi.normal, pg.normal) > 0.5f) {
-                Res pr = unpackReservoir(prevR.info[pidx], prevR.weight[pidx]);                        // at prevFrag
-                uint32_t cap = uint32_t(F.temporalMult) * res.M;
-                if (cap < pr.M) pr.M = cap;
-                combineReservoirsGeom(L, res, pr, gi, pg, seed);
+          if (!(prev.worldPos[pidx].w < 0.5f)) {                 // a previous miss holds no data (its zero normal fails :274 anyway)
+            GInfo pg = ginfo_from_planes(prev, pidx, F.camPos);                                        // prevGInfo.camPos = gInfo.camPos (:259)
+            V3 pd = sub(gi.worldPos, pg.worldPos);
+            if (dot(pd, pd) < 0.01f) {
+              V3 ad = v3(gi.albedo[0] - pg.albedo[0], gi.albedo[1] - pg.albedo[1], gi.albedo[2] - pg.albedo[2]);
+              if (dot(ad, ad) < 0.01f) {
+                if (dot(gi.normal, pg.normal) > 0.5f) {
+                  Res pr = unpackReservoir(prevR.info[pidx], prevR.weight[pidx]);                      // at prevFrag
+                  uint32_t cap = uint32_t(F.temporalMult) * res.M;
+                  if (cap < pr.M) pr.M = cap;
+                  combineReservoirsGeom(L, res, pr, gi, pg, seed);
+                }
               }
             }
           }
@@ -230,25 +284,24 @@ __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FramePa
 }
 
 // -------------------------------------------------------------------------------------------------
-// Kernel B — spatial reuse: spatialReuse.comp main (:54-89) completed with the k-neighbour loop built on
-// combineReservoirs (reservoir.glsl:56-76), normalisation deferred to the finally selected sample.
+// Spatial reuse — spatialReuse.comp main (:54-89) completed with the k-neighbour loop built on combineReservoirs
+// (reservoir.glsl:56-76), normalisation deferred to the finally selected sample.  One thread per hit pixel (the
+// `exist < 0.5` early-out of :76-79 is the hit list); neighbour G-buffer / reservoir reads are gathers through L2.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_spatial(const LightsDev L, const FrameParams F, Planes cur, ResPlanes inR, ResPlanes outR,
-                                                 uint32_t iteration, int y0, int y1, int store_y0, int store_y1) {
-  const int x = blockIdx.x * 32 + threadIdx.x;
-  const int y = y0 + blockIdx.y * 8 + threadIdx.y;
-  if (x >= (int)F.W || y >= y1) return;
-  const size_t idx = (size_t)(y - store_y0) * F.W + x;
-  uint32_t seed = pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_SPATIAL0 + iteration);   // :58-59
-  float4 ri = inR.info[idx], rw = inR.weight[idx];
-  float exist = cur.worldPos[idx].w;
-  if (!(exist < 0.5f)) {                                                         // :76-79
-    Res res = unpackReservoir(ri, rw);
+__global__ void __launch_bounds__(128) k_spatial(const LightsDev L, const FrameParams F, Planes cur, ResPlanes inR, ResPlanes outR, Queues Q,
+                                                 uint32_t iteration, int store_y0, int store_y1) {
+  const uint32_t nhit = Q.counters[Q_HIT];
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
+    const uint32_t idx = Q.hit_pix[s];
+    const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
+    uint32_t seed = pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_SPATIAL0 + iteration);   // :58-59
+    Res res = unpackReservoir(inR.info[idx], inR.weight[idx]);
     GInfo gi = ginfo_from_planes(cur, idx, F.camPos);
     uint32_t Z = res.M;
     const float radius = F.spatialRadius;
     uint32_t k = F.spatialNeighbors; if (k > (uint32_t)MAX_NEIGHBORS) k = MAX_NEIGHBORS;
     uint32_t nb_idx[MAX_NEIGHBORS]; uint32_t nb_M[MAX_NEIGHBORS]; int nacc = 0;
+    const ShadePre pre = shade_pre(gi);
     for (uint32_t i = 0; i < k; ++i) {
       float r1 = rnd(seed), r2 = rnd(seed);
       float dx = (r1 * 2.0f - 1.0f) * radius, dy = (r2 * 2.0f - 1.0f) * radius;
@@ -268,7 +321,7 @@ __global__ void __launch_bounds__(256) k_spatial(const LightsDev L, const FrameP
       if (!(dot(gi.normal, ng.normal) > 0.5f)) continue;
       Res nr = unpackReservoir(inR.info[nidx], inR.weight[nidx]);
       res.M += nr.M;                                                             // reservoir.glsl:61-68
-      float pHat = evaluatePHat(L, nr.lightIndex, gi);
+      float pHat = evaluatePHat(L, nr.lightIndex, gi, pre);
       float weight = pHat * nr.w * float(nr.M);
       if (weight > 0.0f) updateReservoir(res, nr.lightIndex, nr.lightKind, weight, pHat, nr.w, seed, nr.sampleSeed);
       nb_idx[nacc] = (uint32_t)nidx; nb_M[nacc] = nr.M; ++nacc;
@@ -281,13 +334,14 @@ __global__ void __launch_bounds__(256) k_spatial(const LightsDev L, const FrameP
       }
       if (res.w > 0.0f) res.w = res.sumWeights / (float(Z) * res.pHat);          // :74-75
     }
-    packReservoir(res, ri, rw);
+    float4 a, b; packReservoir(res, a, b);
+    outR.info[idx] = a; outR.weight[idx] = b;
   }
-  outR.info[idx] = ri; outR.weight[idx] = rw;
 }
 
 // -------------------------------------------------------------------------------------------------
-// Kernel C — restir_post.frag main (:57-105): shade, emissive override, firefly clamp, running mean.
+// Final shade — restir_post.frag main (:57-105): shade, emissive override, firefly clamp, running mean.
+// Every pixel; a miss pixel costs its worldPos read (16 B) and the accumulation update only.
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_shade(const GridDev G, const LightsDev L, const FrameParams F, Planes cur, ResPlanes rs,
                                                float4* __restrict__ accum, int y0, int y1, int store_y0) {
@@ -295,14 +349,14 @@ __global__ void __launch_bounds__(256) k_shade(const GridDev G, const LightsDev 
   const int y = y0 + blockIdx.y * 8 + threadIdx.y;
   if (x >= (int)F.W || y >= y1) return;
   const size_t idx = (size_t)(y - store_y0) * F.W + x;
-  GInfo gi = ginfo_from_planes(cur, idx, F.camPos);
-  Res res = unpackReservoir(rs.info[idx], rs.weight[idx]);
-  gi.sampleSeed = res.sampleSeed;
-  float exist = cur.worldPos[idx].w;
+  const float4 wp = cur.worldPos[idx];
   V3 c;
-  if (exist < 0.5f) {
+  if (wp.w < 0.5f) {
     c = v3(F.clear[0], F.clear[1], F.clear[2]);
   } else {
+    GInfo gi = ginfo_from_planes(cur, idx, F.camPos);
+    Res res = unpackReservoir(rs.info[idx], rs.weight[idx]);
+    gi.sampleSeed = res.sampleSeed;
     V3 pHat = evaluatePHatFull(L, res.lightIndex, gi);
     c = add(v3(0.0f, 0.0f, 0.0f), muls(pHat, res.w));                            // :80-81
     if ((F.flags & FLAG_FINAL_VISIBILITY) != 0 && res.w > 0.0f) {
@@ -327,6 +381,23 @@ __global__ void __launch_bounds__(256) k_shade(const GridDev G, const LightsDev 
   accum[idx] = out;
 }
 
+// Readback helper: planes in the reference layout for EVERY pixel (miss pixels hold stale data on the device; what the
+// reference's images would contain there is the cleared G-buffer of restir.rgen:150-156,193-197 and an empty reservoir).
+__global__ void __launch_bounds__(256) k_export(Planes cur, ResPlanes rs, float4* __restrict__ out6, size_t first_pix, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t idx = first_pix + i;
+  const float4 wp = cur.worldPos[idx];
+  const bool hit = !(wp.w < 0.5f);
+  float4 a, b; packReservoir(newReservoir(), a, b);
+  out6[0 * n + i] = hit ? wp : make_float4(0.f, 0.f, 0.f, 0.f);
+  out6[1 * n + i] = hit ? cur.albedo[idx] : make_float4(0.f, 0.f, 0.f, 0.f);
+  out6[2 * n + i] = hit ? cur.normal[idx] : make_float4(0.f, 0.f, 0.f, 1.f);
+  out6[3 * n + i] = hit ? cur.mat[idx] : make_float4(0.f, 0.f, 1.f, 1.f);
+  out6[4 * n + i] = hit ? rs.info[idx] : a;
+  out6[5 * n + i] = hit ? rs.weight[idx] : b;
+}
+
 // restir_post.frag:104: outColor = pow(outColor, vec3(1.0f / 0.8f)) -> 8-bit RGBA for the headless "swapchain"
 __global__ void __launch_bounds__(256) k_display(const float4* __restrict__ accum, uchar4* __restrict__ out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -348,8 +419,14 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   static const int refill = getenv("VRS_REFILL") ? atoi(getenv("VRS_REFILL")) : REFILL_MIN_IDLE;
   cudaMemsetAsync(Q.counters, 0, 8 * sizeof(uint32_t), st);
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
-  k_classify<<<grid, block, 0, st>>>(G, F, cur, outR, Q, trace, y0, y1, store_y0);
-  k_primary<<<persistent_blocks, 128, 0, st>>>(G, F, Q, trace, store_y0, refill);
+  k_classify<<<grid, block, 0, st>>>(G, F, cur, Q, trace, y0, y1, store_y0);
+  k_primary<<<persistent_blocks, 128, 0, st>>>(G, F, cur, Q, trace, store_y0, refill);
+  // compaction runs over every stored row (8-byte aligned flag loads); flags outside the band rows stay 0
+  const size_t first_pix = 0, npix = (size_t)(store_y1 - store_y0) * F.W;
+  const uint32_t nblocks = (uint32_t)((npix + COMPACT_BLOCK - 1) / COMPACT_BLOCK);
+  k_hit_count<<<nblocks, 256, 0, st>>>(Q.flag, first_pix, npix, Q.block_count);
+  k_hit_scan<<<1, 1024, 0, st>>>(Q.block_count, nblocks, Q.counters);
+  k_hit_scatter<<<nblocks, 256, 0, st>>>(Q.flag, first_pix, npix, Q.block_count, Q.hit_pix);
   const bool vis = (F.flags & FLAG_VISIBILITY) != 0, temporal = (F.flags & FLAG_TEMPORAL) != 0;
   const int needs_finish = (vis || temporal) ? 1 : 0;
   k_ris<<<persistent_blocks, 128, 0, st>>>(G, L, F, cur, outR, Q, trace, store_y0, needs_finish);
@@ -358,17 +435,19 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
 }
 int initial_pass_launches(int flags) {
   const bool vis = (flags & FLAG_VISIBILITY) != 0, temporal = (flags & FLAG_TEMPORAL) != 0;
-  return 3 + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
+  return 6 + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
 }
-void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams& F, Planes cur, ResPlanes inR, ResPlanes outR, uint32_t iteration,
-                    int y0, int y1, int store_y0, int store_y1) {
-  dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
-  k_spatial<<<grid, block, 0, s>>>(L, F, cur, inR, outR, iteration, y0, y1, store_y0, store_y1);
+void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams& F, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
+                    uint32_t iteration, int store_y0, int store_y1, int persistent_blocks) {
+  k_spatial<<<persistent_blocks, 128, 0, s>>>(L, F, cur, inR, outR, Q, iteration, store_y0, store_y1);
 }
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, Planes cur, ResPlanes rs, float4* accum,
                   int y0, int y1, int store_y0) {
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_shade<<<grid, block, 0, s>>>(G, L, F, cur, rs, accum, y0, y1, store_y0);
+}
+void launch_export(cudaStream_t s, Planes cur, ResPlanes rs, float4* out6, size_t first_pix, size_t n) {
+  k_export<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cur, rs, out6, first_pix, n);
 }
 void launch_display(cudaStream_t s, const float4* accum, uchar4* out, size_t n) {
   k_display<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(accum, out, n);
