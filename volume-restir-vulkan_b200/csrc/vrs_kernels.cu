@@ -41,8 +41,9 @@ __device__ __forceinline__ void primary_ray(const FrameParams& F, int x, int y, 
   org = v3(o4[0], o4[1], o4[2]); dir = v3(d4[0], d4[1], d4[2]);
 }
 
-__global__ void __launch_bounds__(256) k_classify(const GridDev G, const FrameParams F, Planes cur, Queues Q,
+__global__ void __launch_bounds__(256) k_classify(const GridDev G, const FrameParams* __restrict__ Fp, Planes cur, Queues Q,
                                                   uint32_t* __restrict__ trace, int y0, int y1, int store_y0) {
+  const FrameParams& F = *Fp;
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = y0 + blockIdx.y * 8 + threadIdx.y;
   bool enters = false;
@@ -95,8 +96,9 @@ struct PrimaryJob {
   }
 };
 
-__global__ void __launch_bounds__(128) k_primary(const GridDev G, const FrameParams F, Planes cur, Queues Q, uint32_t* __restrict__ trace,
-                                                 int store_y0, int refill) {
+__global__ void __launch_bounds__(128) k_primary(const GridDev G, const FrameParams* __restrict__ Fp, Planes cur, Queues Q,
+                                                 uint32_t* __restrict__ trace, int store_y0, int refill) {
+  const FrameParams& F = *Fp;
   PrimaryJob job{F, cur, Q, trace, store_y0, 0u};
   march_loop<0>(G, job, &Q.counters[Q_PRIMARY_HEAD], Q.counters[Q_CAND], refill);
 }
@@ -154,8 +156,9 @@ __global__ void __launch_bounds__(256) k_hit_scatter(const uint8_t* __restrict__
   while (mm) { const int k = __ffs(mm) - 1; mm &= mm - 1; hit_pix[off++] = (uint32_t)(base + k); }
 }
 
-__global__ void __launch_bounds__(128) k_ris(const GridDev G, const LightsDev L, const FrameParams F, Planes cur, ResPlanes outR, Queues Q,
-                                             uint32_t* __restrict__ trace, int store_y0, int needs_finish) {
+__global__ void __launch_bounds__(128) k_ris(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
+                                             Queues Q, uint32_t* __restrict__ trace, int store_y0, int needs_finish) {
+  const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
     const uint32_t idx = Q.hit_pix[s];
@@ -236,8 +239,9 @@ __global__ void __launch_bounds__(128) k_shadow(const GridDev G, Queues Q, int r
   march_loop<1>(G, job, &Q.counters[Q_SHADOW_HEAD], Q.counters[Q_SHADOW], refill);
 }
 
-__global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FrameParams F, Planes cur, Planes prev, ResPlanes prevR,
+__global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, Planes prev, ResPlanes prevR,
                                                 ResPlanes outR, Queues Q, uint32_t* __restrict__ trace, int store_y0, int store_y1) {
+  const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
     const uint32_t idx = Q.hit_pix[s];
@@ -288,8 +292,9 @@ __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FramePa
 // (reservoir.glsl:56-76), normalisation deferred to the finally selected sample.  One thread per hit pixel (the
 // `exist < 0.5` early-out of :76-79 is the hit list); neighbour G-buffer / reservoir reads are gathers through L2.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_spatial(const LightsDev L, const FrameParams F, Planes cur, ResPlanes inR, ResPlanes outR, Queues Q,
-                                                 uint32_t iteration, int store_y0, int store_y1) {
+__global__ void __launch_bounds__(128) k_spatial(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes inR, ResPlanes outR,
+                                                 Queues Q, uint32_t iteration, int store_y0, int store_y1) {
+  const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
     const uint32_t idx = Q.hit_pix[s];
@@ -343,8 +348,9 @@ __global__ void __launch_bounds__(128) k_spatial(const LightsDev L, const FrameP
 // Final shade — restir_post.frag main (:57-105): shade, emissive override, firefly clamp, running mean.
 // Every pixel; a miss pixel costs its worldPos read (16 B) and the accumulation update only.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_shade(const GridDev G, const LightsDev L, const FrameParams F, Planes cur, ResPlanes rs,
+__global__ void __launch_bounds__(256) k_shade(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes rs,
                                                float4* __restrict__ accum, int y0, int y1, int store_y0) {
+  const FrameParams& F = *Fp;
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = y0 + blockIdx.y * 8 + threadIdx.y;
   if (x >= (int)F.W || y >= y1) return;
@@ -414,13 +420,16 @@ __global__ void k_sample_density(const GridDev G, const int* __restrict__ ijk, u
 }
 
 // ------------------------------------------------------------------------------------------------- launchers
-void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, Planes cur, Planes prev, ResPlanes prevR,
-                    ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1, int persistent_blocks) {
+// `F` is the host copy (launch geometry, which kernels run); `dF` is the same struct in device memory, read by the
+// kernels — so that a captured CUDA graph of the frame stays valid while the per-frame values change.
+void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, Planes prev,
+                    ResPlanes prevR, ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1,
+                    int persistent_blocks, cudaEvent_t prev_halo_ready) {
   static const int refill = getenv("VRS_REFILL") ? atoi(getenv("VRS_REFILL")) : REFILL_MIN_IDLE;
   cudaMemsetAsync(Q.counters, 0, 8 * sizeof(uint32_t), st);
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
-  k_classify<<<grid, block, 0, st>>>(G, F, cur, Q, trace, y0, y1, store_y0);
-  k_primary<<<persistent_blocks, 128, 0, st>>>(G, F, cur, Q, trace, store_y0, refill);
+  k_classify<<<grid, block, 0, st>>>(G, dF, cur, Q, trace, y0, y1, store_y0);
+  k_primary<<<persistent_blocks, 128, 0, st>>>(G, dF, cur, Q, trace, store_y0, refill);
   // compaction runs over every stored row (8-byte aligned flag loads); flags outside the band rows stay 0
   const size_t first_pix = 0, npix = (size_t)(store_y1 - store_y0) * F.W;
   const uint32_t nblocks = (uint32_t)((npix + COMPACT_BLOCK - 1) / COMPACT_BLOCK);
@@ -429,22 +438,24 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   k_hit_scatter<<<nblocks, 256, 0, st>>>(Q.flag, first_pix, npix, Q.block_count, Q.hit_pix);
   const bool vis = (F.flags & FLAG_VISIBILITY) != 0, temporal = (F.flags & FLAG_TEMPORAL) != 0;
   const int needs_finish = (vis || temporal) ? 1 : 0;
-  k_ris<<<persistent_blocks, 128, 0, st>>>(G, L, F, cur, outR, Q, trace, store_y0, needs_finish);
+  k_ris<<<persistent_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
   if (vis) k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill);
-  if (needs_finish) k_finish<<<persistent_blocks, 128, 0, st>>>(L, F, cur, prev, prevR, outR, Q, trace, store_y0, store_y1);
+  // the previous frame's halo rows (multi-GPU) are only needed by the temporal merge: everything above overlapped their exchange
+  if (needs_finish && prev_halo_ready) cudaStreamWaitEvent(st, prev_halo_ready, 0);
+  if (needs_finish) k_finish<<<persistent_blocks, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1);
 }
 int initial_pass_launches(int flags) {
   const bool vis = (flags & FLAG_VISIBILITY) != 0, temporal = (flags & FLAG_TEMPORAL) != 0;
   return 6 + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
 }
-void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams& F, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
+void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, int store_y0, int store_y1, int persistent_blocks) {
-  k_spatial<<<persistent_blocks, 128, 0, s>>>(L, F, cur, inR, outR, Q, iteration, store_y0, store_y1);
+  k_spatial<<<persistent_blocks, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1);
 }
-void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, Planes cur, ResPlanes rs, float4* accum,
-                  int y0, int y1, int store_y0) {
+void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, ResPlanes rs,
+                  float4* accum, int y0, int y1, int store_y0) {
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
-  k_shade<<<grid, block, 0, s>>>(G, L, F, cur, rs, accum, y0, y1, store_y0);
+  k_shade<<<grid, block, 0, s>>>(G, L, dF, cur, rs, accum, y0, y1, store_y0);
 }
 void launch_export(cudaStream_t s, Planes cur, ResPlanes rs, float4* out6, size_t first_pix, size_t n) {
   k_export<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cur, rs, out6, first_pix, n);
