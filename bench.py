@@ -184,9 +184,14 @@ def run_ours(args):
     wl = dict(wl, lights=len(lights))
     R.createRestirLights(lights)
     if world > 1:
-        uid = [V.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        R.commInit(uid[0], rank, world)
+        if args.exchange == "nccl":
+            uid = [V.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            R.commInit(uid[0], rank, world)
+        else:                                  # peer memory over NVLink: all-gather the CUDA-IPC handle blobs
+            blobs = [None] * world
+            dist.all_gather_object(blobs, R.peerExport())
+            R.peerConnect(rank, world, blobs)
     u = R.m_restirUniforms
     u.initialLightSampleCount, u.spatialNeighbors, u.flags = wl["M"], wl["k"], wl["flags"]
     radius = 1.25 * diag
@@ -197,7 +202,7 @@ def run_ours(args):
     L = V.lib()
     # Host inputs of every frame (camera uniforms, push constants) are produced up front by the Renderer methods that mirror
     # the reference's updateUniformBuffer / updateRestirUniformBuffer / updateFrame; a step then is the one C-ABI call.
-    n_frames = args.warmup + args.steps + 20 + 2 + min(max(3, args.steps), 200) + 12
+    n_frames = args.warmup + args.steps + 22 + 2 + min(max(3, args.steps), 200) + 12
     inputs = []
     for f in range(n_frames):
         R.CameraManip.setLookat(orbit_eye(ctr, radius, 0.0, 6.0 * f), ctr)
@@ -242,10 +247,13 @@ def run_ours(args):
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     # per-pass event times of a few more frames (the events are recorded inside vrs_render_frame)
+    barrier()
     probe = min(args.steps, 20)
-    for _ in range(probe):
+    for i in range(probe + 2):
         step()
         t = R.timings()
+        if i < 2:
+            continue                      # ranks re-align after the barrier
         pass_ms["initial"] += t.initial_ms; pass_ms["spatial"] += t.spatial_ms; pass_ms["shade"] += t.shade_ms; pass_ms["exchange"] += t.exchange_ms
         launches = t.launches
     for k_ in pass_ms:
@@ -282,6 +290,9 @@ def run_ours(args):
     e2e_ms = 1000.0 * e2e_s / e2e_steps
     if dist is not None:
         tt = torch.tensor([ms_step, e2e_ms, pass_ms["initial"], pass_ms["spatial"], pass_ms["shade"], pass_ms["exchange"]], device="cuda", dtype=torch.float64)
+        per_rank = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(per_rank, tt)
+        per_rank_initial = [round(float(t_[2]), 4) for t_ in per_rank]
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_step, e2e_ms = float(tt[0]), float(tt[1])
         pass_ms = {"initial": float(tt[2]), "spatial": float(tt[3]), "shade": float(tt[4]), "exchange": float(tt[5])}
@@ -316,6 +327,7 @@ def run_ours(args):
                     "result": "presented RGBA8 frame (vrs_present_async, double-buffered, pinned host memory)",
                     "rgba32f_sync_readback_ms_per_step": round(e2e_f32_ms, 4)},
             "gpu_launches": int(launches * args.steps), "clocks": clocks, "wall_s": round(t_wall, 3),
+            "per_rank_initial_ms": per_rank_initial if world > 1 else None,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.workload, frames=args.cpu_frames)
@@ -421,6 +433,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="smoke_1080p_temporal", choices=sorted(WORKLOADS))
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU halo exchange: NVLink peer-memory kernel or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=20)
     args = ap.parse_args()

@@ -197,6 +197,14 @@ void*      vrs_stream(vrs_ctx* ctx);                                            
 /* 128-byte ncclUniqueId produced on rank 0 and broadcast by the launcher (torch.distributed / MPI / file). */
 vrs_status vrs_comm_unique_id(uint8_t id128[128]);
 vrs_status vrs_comm_init(vrs_ctx* ctx, const uint8_t id128[128], int rank, int nranks);
+/* Peer-memory halo exchange (preferred on NVLink / NVSwitch boxes): no NCCL.  Every rank exports the CUDA IPC handles of
+ * its per-pixel planes, the launcher all-gathers the blobs (any transport), every rank opens its two neighbours' planes
+ * and from then on ONE kernel per exchange stores the boundary rows straight into the neighbours' halo rows over NVLink
+ * and releases a system-scope flag; consumers acquire the flag in a one-thread wait kernel.  Being plain kernels, the
+ * exchange is part of the captured CUDA graph of the frame. */
+#define VRS_PEER_BLOB_BYTES 1152
+vrs_status vrs_peer_export(vrs_ctx* ctx, uint8_t blob[VRS_PEER_BLOB_BYTES]);
+vrs_status vrs_peer_connect(vrs_ctx* ctx, int rank, int nranks, const uint8_t* all_blobs /* nranks x VRS_PEER_BLOB_BYTES */);
 /* Even band split of `height` rows over nranks (helper for launchers). */
 void       vrs_band_for_rank(uint32_t height, int rank, int nranks, uint32_t* y0, uint32_t* y1);
 

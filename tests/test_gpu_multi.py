@@ -1,5 +1,6 @@
-"""-m gpu (needs >= 2 GPUs, skipped otherwise): bands + NCCL halo exchange through the C ABI (vrs_comm_init) must give
-the same bits as one GPU rendering the whole frame."""
+"""-m gpu (needs >= 2 GPUs, skipped otherwise): bands + halo exchange through the C ABI — the NVLink peer-memory kernel
+(vrs_peer_connect, replayed inside the frame's CUDA graph) and NCCL send/recv (vrs_comm_init) — must give the same bits
+as one GPU rendering the whole frame."""
 import os
 import socket
 import sys
@@ -18,7 +19,7 @@ def free_port():
     return port
 
 
-def worker(rank, world, port, flags, frames, out_dir):
+def worker(rank, world, port, flags, frames, out_dir, mode):
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
     import torch.distributed as dist
@@ -43,9 +44,14 @@ def worker(rank, world, port, flags, frames, out_dir):
         return R, ctr
 
     R, ctr = make(band, rank)
-    uid = [V.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    R.commInit(uid[0], rank, world)
+    if mode == "nccl":
+        uid = [V.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        R.commInit(uid[0], rank, world)
+    else:
+        blobs = [None] * world
+        dist.all_gather_object(blobs, R.peerExport())
+        R.peerConnect(rank, world, blobs)
     full = make(None, 0)[0] if rank == 0 else None
     for r_ in [R] + ([full] if full else []):
         r_.CameraManip.setLookat(common.orbit_eye(ctr, 4.2, 0.2, 10.0), ctr)
@@ -71,12 +77,12 @@ def worker(rank, world, port, flags, frames, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("flags", [1 | 2 | 4, 1 | 2])
-def test_nccl_bands_equal_single_gpu(flags, tmp_path):
+@pytest.mark.parametrize("mode,flags", [("peer", 1 | 2 | 4), ("peer", 1 | 2), ("nccl", 1 | 2 | 4)])
+def test_bands_equal_single_gpu(mode, flags, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     world = 2
-    mp.spawn(worker, args=(world, free_port(), flags, 4, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(worker, args=(world, free_port(), flags, 14, str(tmp_path), mode), nprocs=world, join=True)
     assert open(tmp_path / "result").read() == "ok"

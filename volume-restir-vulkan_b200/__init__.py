@@ -19,6 +19,8 @@ LIB_PATH = os.path.join(HERE, "libvrs.so")
 VISIBILITY_REUSE_FLAG, TEMPORAL_REUSE_FLAG, SPATIAL_REUSE_FLAG, USE_ENVIRONMENT_FLAG = 1, 2, 4, 8
 FINAL_VISIBILITY_FLAG, FINALIZE_W_FLAG = 16, 32
 
+PEER_BLOB_BYTES = 1152
+
 STATUS = {0: "VRS_OK", 1: "VRS_ERR_INVALID", 2: "VRS_ERR_CUDA", 3: "VRS_ERR_IO", 4: "VRS_ERR_FORMAT",
           5: "VRS_ERR_UNSUPPORTED", 6: "VRS_ERR_COMM", 7: "VRS_ERR_NO_DEVICE"}
 
@@ -30,7 +32,7 @@ EXPORTS = [
     "vrs_generate_point_lights", "vrs_perspectiveVK", "vrs_look_at", "vrs_invert", "vrs_mat4_mul", "vrs_pass_initial",
     "vrs_pass_spatial", "vrs_pass_shade", "vrs_render_frame", "vrs_synchronize", "vrs_read_frame", "vrs_read_gbuffer",
     "vrs_read_reservoirs", "vrs_read_trace", "vrs_read_display", "vrs_present_async", "vrs_present_wait", "vrs_write_image", "vrs_get_timings", "vrs_stream", "vrs_comm_unique_id",
-    "vrs_comm_init", "vrs_band_for_rank",
+    "vrs_comm_init", "vrs_peer_export", "vrs_peer_connect", "vrs_band_for_rank",
 ]
 
 
@@ -148,6 +150,10 @@ def lib():
         L.vrs_get_timings.argtypes = [C.c_void_p, C.c_void_p]
         L.vrs_stream.argtypes = [C.c_void_p]
         L.vrs_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.vrs_peer_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.vrs_peer_export.restype = C.c_int
+        L.vrs_peer_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.vrs_peer_connect.restype = C.c_int
         L.vrs_create_alias_table.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.vrs_generate_point_lights.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
         L.vrs_band_for_rank.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -459,6 +465,19 @@ class Renderer:
 
     def stream(self):
         return lib().vrs_stream(self._ctx)
+
+    def peerExport(self):
+        """CUDA-IPC handles of this context's planes (bytes) for the peer-memory halo exchange."""
+        buf = (C.c_uint8 * PEER_BLOB_BYTES)()
+        self._ck(lib().vrs_peer_export(self._ctx, buf))
+        return bytes(buf)
+
+    def peerConnect(self, rank, nranks, blobs):
+        """blobs: the peerExport() bytes of every rank, in rank order (all-gathered by the launcher)."""
+        joined = b"".join(blobs)
+        assert len(joined) == nranks * PEER_BLOB_BYTES
+        buf = (C.c_uint8 * len(joined)).from_buffer_copy(joined)
+        self._ck(lib().vrs_peer_connect(self._ctx, rank, nranks, buf))
 
     def commInit(self, unique_id, rank, nranks):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)

@@ -69,6 +69,11 @@ struct vrs_ctx {
   vrs_timings timings{};
   bool timings_valid = false;
   Comm* comm = nullptr;
+  // peer-memory exchange (vrs_peer_connect): neighbours' planes opened through CUDA IPC
+  struct Peer { bool present = false; float4* g[2][4] = {{nullptr}}; float4* r[3][2] = {{nullptr}}; unsigned* flags = nullptr; int store_y0 = 0, store_y1 = 0, band_y0 = 0, band_y1 = 0; std::vector<void*> opened; };
+  Peer peer_up, peer_down;
+  bool peer_mode = false;
+  unsigned* xflags = nullptr;                // [0] flag written by the up neighbour, [1] by the down neighbour, [2] serial, [3] block counter, [4] error
   cudaStream_t comm_stream = nullptr;        // halo exchanges run here so that they can overlap the next kernels
   cudaEvent_t ev_halo_src = nullptr, ev_halo_done = nullptr;
 };
@@ -131,6 +136,7 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
     if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) ctx->persistent_blocks = prop.multiProcessorCount * (getenv("VRS_BLOCKS_PER_SM") ? atoi(getenv("VRS_BLOCKS_PER_SM")) : 12);
   }
   for (int i = 0; i < 8; ++i) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
+  if (!alloc((void**)&ctx->xflags, 64)) return bail(VRS_ERR_CUDA);
   if (!alloc((void**)&ctx->d_params, sizeof(FrameParams)) ||
       cudaHostAlloc((void**)&ctx->h_params, sizeof(FrameParams) * VRS_PARAM_SLOTS, cudaHostAllocDefault) != cudaSuccess) { ctx->err = "param alloc failed"; return bail(VRS_ERR_CUDA); }
   for (int i = 0; i < VRS_PARAM_SLOTS; ++i)
@@ -159,6 +165,8 @@ void vrs_destroy(vrs_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) comm_destroy(ctx->comm);
+  for (vrs_ctx::Peer* p : {&ctx->peer_up, &ctx->peer_down}) for (void* q : p->opened) cudaIpcCloseMemHandle(q);
+  cudaFree(ctx->xflags);
   free_grid(ctx);
   for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) cudaFree(ctx->g_planes[i][p]);
   for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) cudaFree(ctx->r_planes[i][p]);
@@ -413,6 +421,34 @@ static vrs_status upload_params(vrs_ctx* ctx, const FrameParams& F) {
 // Halo exchange on the communication stream, forked from and joined back into the main stream with events (the same
 // calls work under stream capture).  `wait_now` false leaves the join to the consumer (k_finish waits on ev_halo_done).
 static vrs_status exchange(vrs_ctx* ctx, bool gbuf, int g_index, int r_index, bool wait_now) {
+  if (ctx->peer_mode) {
+    // one kernel stores the boundary rows into both neighbours' halo rows (NVLink P2P) and publishes the serial;
+    // the wait kernel (consumer side) goes right before the first kernel that reads the halos
+    HaloPush H; memset(&H, 0, sizeof(H));
+    auto add = [&](float4* mine, float4* up, float4* down) { H.src[H.nplanes] = mine; H.up_dst[H.nplanes] = up; H.down_dst[H.nplanes] = down; H.nplanes++; };
+    if (gbuf) for (int p = 0; p < 4; ++p) add(ctx->g_planes[g_index][p], ctx->peer_up.present ? ctx->peer_up.g[g_index][p] : nullptr, ctx->peer_down.present ? ctx->peer_down.g[g_index][p] : nullptr);
+    if (r_index >= 0) for (int p = 0; p < 2; ++p) add(ctx->r_planes[r_index][p], ctx->peer_up.present ? ctx->peer_up.r[r_index][p] : nullptr, ctx->peer_down.present ? ctx->peer_down.r[r_index][p] : nullptr);
+    const int band_h = ctx->band_y1 - ctx->band_y0;
+    if (ctx->peer_up.present) {          // my first rows -> the rows just below the up neighbour's band
+      int rows = ctx->peer_up.store_y1 - ctx->peer_up.band_y1; if (rows > band_h) rows = band_h;
+      H.up_count = (size_t)rows * ctx->W; H.up_src_off = (size_t)(ctx->band_y0 - ctx->store_y0) * ctx->W;
+      H.up_dst_off = (size_t)(ctx->band_y0 - ctx->peer_up.store_y0) * ctx->W; H.up_flag = ctx->peer_up.flags + 1;     // "written by the down neighbour"
+    }
+    if (ctx->peer_down.present) {        // my last rows -> the rows just above the down neighbour's band
+      int rows = ctx->peer_down.band_y0 - ctx->peer_down.store_y0; if (rows > band_h) rows = band_h;
+      H.down_count = (size_t)rows * ctx->W; H.down_src_off = (size_t)(ctx->band_y1 - rows - ctx->store_y0) * ctx->W;
+      H.down_dst_off = (size_t)(ctx->band_y1 - rows - ctx->peer_down.store_y0) * ctx->W; H.down_flag = ctx->peer_down.flags + 0;   // "written by the up neighbour"
+    }
+    H.serial = ctx->xflags + 2; H.block_counter = ctx->xflags + 3;
+    launch_halo_push(ctx->stream, H, 64);
+    CK(cudaGetLastError());
+    ctx->timings.launches += 1;
+    if (wait_now) {
+      launch_halo_wait(ctx->stream, ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4);
+      CK(cudaGetLastError());
+    }
+    return VRS_OK;
+  }
   if (!ctx->comm) return VRS_OK;
   std::vector<float4*> planes;
   if (gbuf) for (int p = 0; p < 4; ++p) planes.push_back(ctx->g_planes[g_index][p]);
@@ -432,11 +468,12 @@ static cudaError_t mark(vrs_ctx* ctx, int i) {
   return ctx->capturing ? cudaEventRecordWithFlags(ctx->ev[i], ctx->stream, cudaEventRecordExternal) : cudaEventRecord(ctx->ev[i], ctx->stream);
 }
 
-static vrs_status enqueue_initial(vrs_ctx* ctx, const FrameParams& F, cudaEvent_t prev_halo_ready) {
+static vrs_status enqueue_initial(vrs_ctx* ctx, const FrameParams& F, cudaEvent_t prev_halo_ready, bool peer_wait = false) {
   int out = (ctx->final_r + 1) % 3;
+  const unsigned* pw[4] = {ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4};
   launch_initial(ctx->stream, ctx->grid, ctx->lights, F, ctx->d_params, planes_of(ctx, ctx->cur_g), planes_of(ctx, 1 - ctx->cur_g),
                  res_of(ctx, ctx->final_r), res_of(ctx, out), ctx->queues, ctx->trace, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1,
-                 ctx->persistent_blocks, prev_halo_ready);
+                 ctx->persistent_blocks, prev_halo_ready, peer_wait ? pw : nullptr);
   CK(cudaGetLastError());
   ctx->src_r = out; ctx->timings.launches += (uint32_t)initial_pass_launches(F.flags);
   return VRS_OK;
@@ -488,19 +525,21 @@ static vrs_status enqueue_frame(vrs_ctx* ctx, const FrameParams& F) {
   const bool spatial = (F.flags & VRS_RESTIR_SPATIAL_REUSE_FLAG) != 0 && ctx->cfg.spatial_iterations > 0;
   const bool temporal = (F.flags & VRS_RESTIR_TEMPORAL_REUSE_FLAG) != 0;
   CK(mark(ctx, 0));
+  const bool multi = ctx->comm != nullptr || ctx->peer_mode;
   bool halo_in_flight = false;
-  if (ctx->comm && temporal) {
+  if (multi && temporal) {
+    // the consumer-side join (event wait for NCCL, flag-wait kernel for peer memory) sits right before k_finish
     if ((s = exchange(ctx, !spatial, 1 - ctx->cur_g, ctx->final_r, false))) return s;
     halo_in_flight = true;
   }
-  if ((s = enqueue_initial(ctx, F, halo_in_flight ? ctx->ev_halo_done : nullptr))) return s;        // main.cpp:405-409
+  if ((s = enqueue_initial(ctx, F, halo_in_flight && !ctx->peer_mode ? ctx->ev_halo_done : nullptr, halo_in_flight && ctx->peer_mode))) return s;   // main.cpp:405-409
   CK(mark(ctx, 1));
-  if (ctx->comm && spatial && (s = exchange(ctx, true, ctx->cur_g, ctx->src_r, true))) return s;
+  if (multi && spatial && (s = exchange(ctx, true, ctx->cur_g, ctx->src_r, true))) return s;
   CK(mark(ctx, 2));
   if (spatial) {
     for (uint32_t it = 0; it < ctx->cfg.spatial_iterations; ++it) {                                   // main.cpp:410-413
       if ((s = enqueue_spatial(ctx, it))) return s;
-      if (ctx->comm && it + 1 < ctx->cfg.spatial_iterations && (s = exchange(ctx, false, 0, ctx->src_r, true))) return s;
+      if (multi && it + 1 < ctx->cfg.spatial_iterations && (s = exchange(ctx, false, 0, ctx->src_r, true))) return s;
     }
   }
   CK(mark(ctx, 3));
@@ -517,14 +556,15 @@ vrs_status vrs_render_frame(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
   ctx->timings.launches = 0;
   static const bool no_graph = getenv("VRS_NO_GRAPH") != nullptr;
   static const bool no_graph_comm = getenv("VRS_NO_GRAPH_COMM") != nullptr;
-  if (no_graph || (no_graph_comm && ctx->comm)) {
+  (void)no_graph_comm;
+  if (no_graph || ctx->comm) {     // NCCL send/recv under stream capture hangs here (NCCL 2.28.9): NCCL contexts launch eagerly
     if ((s = enqueue_frame(ctx, F))) return s;
     ctx->timings_valid = true;
     return VRS_OK;
   }
   // The launch sequence depends only on which buffers are current (6 ping-pong phases) and on the structural flags.
   const uint64_t key = (uint64_t)ctx->cur_g | ((uint64_t)ctx->final_r << 1) | ((uint64_t)(F.flags & 0x3f) << 3) | ((uint64_t)ctx->cfg.spatial_iterations << 9) |
-                       ((uint64_t)(ctx->comm ? 1 : 0) << 12);
+                       ((uint64_t)(ctx->comm ? 1 : 0) << 12) | ((uint64_t)(ctx->peer_mode ? 1 : 0) << 13);
   auto it = ctx->graphs.find(key);
   if (it == ctx->graphs.end() && ctx->seen[key]++ == 0) {
     // first frame of a phase runs eagerly: NCCL sets up its peer connections on first use, which must not happen under capture
@@ -680,6 +720,47 @@ vrs_status vrs_write_image(vrs_ctx* ctx, const char* path) {
 }
 
 // ------------------------------------------------------------------------------------------ multi-GPU
+// ---- peer-memory exchange set-up: blob = { band_y0, band_y1, store_y0, store_y1 (int32) | 15 x cudaIpcMemHandle_t }
+vrs_status vrs_peer_export(vrs_ctx* ctx, uint8_t blob[VRS_PEER_BLOB_BYTES]) {
+  if (!ctx || !blob) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  static_assert(16 + 15 * sizeof(cudaIpcMemHandle_t) <= VRS_PEER_BLOB_BYTES, "blob too small");
+  memset(blob, 0, VRS_PEER_BLOB_BYTES);
+  int32_t hdr[4] = {ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1};
+  memcpy(blob, hdr, 16);
+  cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)(blob + 16);
+  int k = 0;
+  for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) CK(cudaIpcGetMemHandle(&h[k++], ctx->g_planes[i][p]));
+  for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) CK(cudaIpcGetMemHandle(&h[k++], ctx->r_planes[i][p]));
+  CK(cudaIpcGetMemHandle(&h[k++], ctx->xflags));
+  return VRS_OK;
+}
+vrs_status vrs_peer_connect(vrs_ctx* ctx, int rank, int nranks, const uint8_t* all_blobs) {
+  if (!ctx || !all_blobs || rank < 0 || rank >= nranks) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (nranks > 1 && ctx->band_y1 - ctx->band_y0 < (int)ctx->cfg.halo_rows)
+    return fail(ctx, VRS_ERR_INVALID, "band shorter than halo_rows: halos are exchanged with adjacent ranks only");
+  auto open_peer = [&](int r, vrs_ctx::Peer& P) -> vrs_status {
+    const uint8_t* blob = all_blobs + (size_t)r * VRS_PEER_BLOB_BYTES;
+    int32_t hdr[4]; memcpy(hdr, blob, 16);
+    P.band_y0 = hdr[0]; P.band_y1 = hdr[1]; P.store_y0 = hdr[2]; P.store_y1 = hdr[3];
+    const cudaIpcMemHandle_t* h = (const cudaIpcMemHandle_t*)(blob + 16);
+    int k = 0;
+    auto open = [&](void** out) -> vrs_status { cudaIpcMemHandle_t hh; memcpy(&hh, &h[k++], sizeof(hh)); CK(cudaIpcOpenMemHandle(out, hh, cudaIpcMemLazyEnablePeerAccess)); P.opened.push_back(*out); return VRS_OK; };
+    vrs_status s;
+    for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) if ((s = open((void**)&P.g[i][p]))) return s;
+    for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) if ((s = open((void**)&P.r[i][p]))) return s;
+    if ((s = open((void**)&P.flags))) return s;
+    P.present = true;
+    return VRS_OK;
+  };
+  vrs_status s;
+  if (rank > 0 && (s = open_peer(rank - 1, ctx->peer_up))) return s;
+  if (rank + 1 < nranks && (s = open_peer(rank + 1, ctx->peer_down))) return s;
+  ctx->peer_mode = nranks > 1;
+  return VRS_OK;
+}
+
 vrs_status vrs_comm_unique_id(uint8_t id128[128]) {
   std::string err;
   if (!comm_unique_id(id128, err)) return fail(nullptr, VRS_ERR_COMM, err);

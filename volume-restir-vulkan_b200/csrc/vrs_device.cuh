@@ -74,6 +74,20 @@ struct Queues {
   float4* shadow_ray;     // 2 x float4 per shadow-queue entry
 };
 
+// One peer-memory halo exchange: rows of `src` planes -> the up / down neighbour's planes (peer pointers, null = no neighbour)
+struct HaloPush {
+  const float4* src[6];
+  float4* up_dst[6];
+  float4* down_dst[6];
+  int nplanes;
+  size_t up_src_off, up_dst_off, up_count;         // in float4 elements
+  size_t down_src_off, down_dst_off, down_count;
+  unsigned* up_flag;                               // "from below" flag in the up neighbour's memory
+  unsigned* down_flag;                             // "from above" flag in the down neighbour's memory
+  unsigned* serial;                                // this rank's exchange counter (device)
+  unsigned* block_counter;
+};
+
 // ------------------------------------------------------------------ small vector helpers
 struct V3 { float x, y, z; };
 __device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }

@@ -387,6 +387,47 @@ __global__ void __launch_bounds__(256) k_shade(const GridDev G, const LightsDev 
   accum[idx] = out;
 }
 
+// -------------------------------------------------------------------------------------------------
+// Peer-memory halo exchange: boundary rows of up to 6 planes are stored straight into the neighbours' halo rows over
+// NVLink (P2P stores), then the last block publishes the exchange serial with a system-scope release; the consumer side
+// is k_halo_wait (one thread acquiring the flag the neighbour wrote).  No NCCL, capturable in the frame's CUDA graph.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_halo_push(HaloPush H) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x, tid0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int p = 0; p < H.nplanes; ++p) {
+    if (H.up_dst[p]) for (size_t i = tid0; i < H.up_count; i += stride) H.up_dst[p][H.up_dst_off + i] = H.src[p][H.up_src_off + i];
+    if (H.down_dst[p]) for (size_t i = tid0; i < H.down_count; i += stride) H.down_dst[p][H.down_dst_off + i] = H.src[p][H.down_src_off + i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(H.block_counter, 1u);
+    if (ticket == gridDim.x - 1) {                       // every block's stores are fenced: publish
+      *H.block_counter = 0u;
+      const unsigned serial = *H.serial + 1u;
+      *H.serial = serial;
+      __threadfence_system();
+      if (H.up_flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(H.up_flag), "r"(serial) : "memory");
+      if (H.down_flag) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(H.down_flag), "r"(serial) : "memory");
+    }
+  }
+}
+__global__ void k_halo_wait(const unsigned* serial, const unsigned* flag_from_up, const unsigned* flag_from_down, unsigned* error) {
+  const unsigned want = *serial;
+  for (int side = 0; side < 2; ++side) {
+    const unsigned* f = side == 0 ? flag_from_up : flag_from_down;
+    if (!f) continue;
+    unsigned v = 0;
+    long long spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int)(v - want) >= 0) break;
+      __nanosleep(200);
+      if (++spins > 20000000LL) { *error = 1u; break; }   // ~4 s: give up instead of hanging the GPU
+    }
+  }
+}
+
 // Readback helper: planes in the reference layout for EVERY pixel (miss pixels hold stale data on the device; what the
 // reference's images would contain there is the cleared G-buffer of restir.rgen:150-156,193-197 and an empty reservoir).
 __global__ void __launch_bounds__(256) k_export(Planes cur, ResPlanes rs, float4* __restrict__ out6, size_t first_pix, size_t n) {
@@ -424,7 +465,7 @@ __global__ void k_sample_density(const GridDev G, const int* __restrict__ ijk, u
 // kernels — so that a captured CUDA graph of the frame stays valid while the per-frame values change.
 void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, Planes prev,
                     ResPlanes prevR, ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1,
-                    int persistent_blocks, cudaEvent_t prev_halo_ready) {
+                    int persistent_blocks, cudaEvent_t prev_halo_ready, const unsigned* const* peer_wait) {
   static const int refill = getenv("VRS_REFILL") ? atoi(getenv("VRS_REFILL")) : REFILL_MIN_IDLE;
   cudaMemsetAsync(Q.counters, 0, 8 * sizeof(uint32_t), st);
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
@@ -442,6 +483,7 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   if (vis) k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill);
   // the previous frame's halo rows (multi-GPU) are only needed by the temporal merge: everything above overlapped their exchange
   if (needs_finish && prev_halo_ready) cudaStreamWaitEvent(st, prev_halo_ready, 0);
+  if (needs_finish && peer_wait) k_halo_wait<<<1, 1, 0, st>>>(peer_wait[0], peer_wait[1], peer_wait[2], const_cast<unsigned*>(peer_wait[3]));
   if (needs_finish) k_finish<<<persistent_blocks, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1);
 }
 int initial_pass_launches(int flags) {
@@ -456,6 +498,10 @@ void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const Fr
                   float4* accum, int y0, int y1, int store_y0) {
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_shade<<<grid, block, 0, s>>>(G, L, dF, cur, rs, accum, y0, y1, store_y0);
+}
+void launch_halo_push(cudaStream_t s, const HaloPush& H, int blocks) { k_halo_push<<<blocks, 256, 0, s>>>(H); }
+void launch_halo_wait(cudaStream_t s, const unsigned* serial, const unsigned* from_up, const unsigned* from_down, unsigned* error) {
+  k_halo_wait<<<1, 1, 0, s>>>(serial, from_up, from_down, error);
 }
 void launch_export(cudaStream_t s, Planes cur, ResPlanes rs, float4* out6, size_t first_pix, size_t n) {
   k_export<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cur, rs, out6, first_pix, n);
