@@ -1,0 +1,112 @@
+"""-m gpu: edge cases of the hot path against the oracle — ragged image sizes, degenerate parameters, empty views,
+level-set input, per-pass API, headless present."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+def render_pair(V, O, name, W, H, n_lights, flags, frames=2, M=8, k=3, iters=1, eye_scale=1.4, radius=12.0, look_away=False):
+    R, OR, ctr, diag = common.setup_pair(V, O, name, W, H, n_lights, iterations=iters)
+    u = R.m_restirUniforms
+    u.initialLightSampleCount, u.spatialNeighbors, u.spatialRadius, u.flags = M, k, radius, flags
+    eye = common.orbit_eye(ctr, eye_scale * diag, 0.1 * diag, 75.0)
+    target = ctr if not look_away else [2 * e - c for e, c in zip(eye, ctr)]
+    R.CameraManip.setLookat(eye, target)
+    R.createRestirUniformBuffer()
+    for f in range(frames):
+        R.renderFrame(clock=f + 3)
+        gu, ru, pc = common.oracle_uniforms(O, R)
+        pc.initialize = R._last_initialize
+        ref = OR.render(gu, ru, pc, f + 3).copy()
+    return R, OR, ref
+
+
+def assert_same(R, OR, ref):
+    img = R.readFrame()
+    assert (common.u32(img) == common.u32(ref)).all()
+    g, go = R.readGBuffer(), OR.gbuffer()
+    for p in g:
+        assert (common.u32(g[p]) == common.u32(go[p])).all(), p
+    r, ro = R.readReservoirs(), OR.reservoirs()
+    hit = go["worldPos"][..., 3] > 0.5
+    assert (common.u32(r["info"])[hit] == common.u32(ro["info"])[hit]).all()
+    assert (common.u32(r["weight"])[hit] == common.u32(ro["weight"])[hit]).all()
+    assert (R.readTrace() == OR.f.trace).all()
+
+
+@pytest.mark.parametrize("W,H", [(33, 17), (257, 129), (8, 8), (1, 1)])
+def test_ragged_sizes(V, O, W, H):
+    R, OR, ref = render_pair(V, O, "smoke", W, H, 7, V.VISIBILITY_REUSE_FLAG | V.TEMPORAL_REUSE_FLAG | V.SPATIAL_REUSE_FLAG)
+    assert_same(R, OR, ref)
+    R.destroy()
+
+
+def test_camera_looking_away_sees_nothing(V, O):
+    R, OR, ref = render_pair(V, O, "smoke", 64, 48, 4, 7, look_away=True)
+    assert_same(R, OR, ref)
+    assert R.readGBuffer()["worldPos"][..., 3].sum() == 0 and R.readFrame()[..., :3].sum() == 0
+    R.destroy()
+
+
+def test_camera_inside_volume(V, O):
+    R, OR, ref = render_pair(V, O, "cube", 96, 64, 3, 7, eye_scale=0.2)
+    assert_same(R, OR, ref)
+    assert R.readGBuffer()["worldPos"][..., 3].mean() > 0.9
+    R.destroy()
+
+
+@pytest.mark.parametrize("M,k,iters", [(1, 1, 1), (64, 16, 4), (32, 0, 2)])
+def test_parameter_extremes(V, O, M, k, iters):
+    R, OR, ref = render_pair(V, O, "smoke", 96, 64, 1, 7, M=M, k=k, iters=iters, frames=3)
+    assert_same(R, OR, ref)
+    R.destroy()
+
+
+def test_per_pass_api_equals_render_frame(V, O):
+    flags = V.VISIBILITY_REUSE_FLAG | V.TEMPORAL_REUSE_FLAG | V.SPATIAL_REUSE_FLAG
+    A, _, ctr, diag = common.setup_pair(V, O, "smoke", 128, 72, 16, iterations=2)
+    B, _, _, _ = common.setup_pair(V, O, "smoke", 128, 72, 16, iterations=2)
+    for R in (A, B):
+        R.m_restirUniforms.initialLightSampleCount, R.m_restirUniforms.spatialNeighbors, R.m_restirUniforms.flags = 8, 4, flags
+        R.CameraManip.setLookat(common.orbit_eye(ctr, 1.3 * diag, 0.0, 10.0), ctr)
+        R.createRestirUniformBuffer()
+    for f in range(8):                       # long enough to replay captured graphs on A
+        for R in (A, B):
+            R.CameraManip.setLookat(common.orbit_eye(ctr, 1.3 * diag, 0.0, 10.0 + f), ctr)
+            R.updateUniformBuffer(); R.updateRestirUniformBuffer(); R.updateFrame()
+        A.submit(f)                          # vrs_render_frame (CUDA-graph path)
+        B.passInitial(f); B.passSpatial(f, 0); B.passSpatial(f, 1); B.passShade(f)   # RestirPass / SpatialReusePass / restirDrawPost
+        assert (common.u32(A.readFrame()) == common.u32(B.readFrame())).all(), f
+    A.destroy(); B.destroy()
+
+
+def test_present_matches_accumulation(V, O):
+    R, OR, ref = render_pair(V, O, "smoke", 160, 90, 16, 3)
+    disp = R.readDisplay()
+    exp = np.clip(np.power(np.maximum(ref[..., :3], 0.0), 1.0 / 0.8), 0.0, 1.0) * 255.0 + 0.5     # restir_post.frag:104
+    assert np.abs(disp[..., :3].astype(np.int32) - exp.astype(np.int32)).max() <= 1 and (disp[..., 3] == 255).all()
+    R.destroy()
+
+
+def test_errors_are_reported(V, O):
+    R = V.Renderer(32, 32)
+    with pytest.raises(V.VrsError) as e:
+        R.submit(0)                                       # no grid yet
+    assert e.value.status == 1
+    with pytest.raises(V.VrsError) as e:
+        R.loadVDB("/nonexistent.vdb")
+    assert e.value.status == 3
+    R.loadVDB(common.asset("smoke"))
+    R.createRestirLights(np.ones((2, 8), np.float32))
+    R.m_restirUniforms.pointLightCount = 5                # inconsistent with the uploaded lights
+    R.updateUniformBuffer(); R.createRestirUniformBuffer()
+    with pytest.raises(V.VrsError):
+        R.submit(0)
+    s = V.lib().vrs_set_triangle_lights(R._ctx, None, 0)
+    assert s == 5                                         # VRS_ERR_UNSUPPORTED
+    R.destroy()
