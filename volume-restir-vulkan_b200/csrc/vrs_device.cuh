@@ -547,7 +547,7 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t* counter) {
 // Per iteration the warp executes ONE kind of unit step, the kind more lanes are waiting for, so divergent lanes are
 // batched instead of serialised; lanes whose ray retired are refilled from the job queue once enough are idle.
 template <int MODE, class Job>
-__device__ __forceinline__ void march_loop(const GridDev& G, Job& job, uint32_t* head, uint32_t njobs, int refill_min_idle) {
+__device__ __forceinline__ void march_loop(const GridDev& G, Job& job, uint32_t* head, uint32_t njobs, int refill_min_idle, int cells_per_decision) {
   const unsigned full = 0xffffffffu;
   Ray<MODE> ray;
   int st = RAY_DONE;
@@ -566,7 +566,7 @@ __device__ __forceinline__ void march_loop(const GridDev& G, Job& job, uint32_t*
     if (busy == 0) break;
     if (bc == 0 || __popc(bs) >= __popc(bc)) {
 #pragma unroll 1
-      for (int r = 0; r < 2; ++r)           // two cell visits per scheduling decision (they are cheap)
+      for (int r = 0; r < cells_per_decision; ++r)   // a few cell visits per scheduling decision (they are cheap)
         if (st == RAY_SKIP) { st = ray.cell_step(G); if (st == RAY_DONE) job.retire(G, ray, seed); }
     } else {
       if (st == RAY_COLLIDE) { st = ray.collide_step(G, seed); if (st == RAY_DONE) job.retire(G, ray, seed); }

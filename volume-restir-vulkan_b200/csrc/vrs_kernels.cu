@@ -21,13 +21,14 @@ static constexpr int MAX_NEIGHBORS = 16;
 //                   16 B/px) and queues the rays that enter the window.
 //   A1 k_primary    persistent warps: residual delta tracking of queued rays, unit steps batched per warp, lane
 //                   refill; a real collision leaves {t, voxel, RNG state, 1} in the pixel's worldPos slot.
-//   A2 k_hit_*      ordered stream compaction of the hit flags -> hit list in pixel order (coalesced consumers).
+//   A2 k_hit_compact stream compaction of the hit flags -> hit list, pixel order inside 2048-pixel blocks (coalesced consumers).
 //   A3 k_ris        one thread per hit: G-buffer stores (:193-197), M-candidate RIS (:203-227), shadow-ray set-up.
 //   A4 k_shadow     persistent warps: ratio-tracking transmittance toward the selected light (:229-235).
 //   A5 k_finish     one thread per hit: apply the transmittance, temporal merge (:237-284), pack (:286-289).
 // -------------------------------------------------------------------------------------------------
 enum { Q_CAND = 0, Q_HIT = 1, Q_SHADOW = 2, Q_PRIMARY_HEAD = 3, Q_SHADOW_HEAD = 4 };
 static constexpr int REFILL_MIN_IDLE = 16;
+static constexpr int CELLS_PER_DECISION = 2;
 static constexpr int COMPACT_BLOCK = 2048;      // pixels per compaction block (256 threads x 8 flags)
 
 __device__ __forceinline__ void primary_ray(const FrameParams& F, int x, int y, V3& org, V3& dir) {   // :142-148
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(128) k_primary(const GridDev G, const FramePar
                                                  uint32_t* __restrict__ trace, int store_y0, int refill) {
   const FrameParams& F = *Fp;
   PrimaryJob job{F, cur, Q, trace, store_y0, 0u};
-  march_loop<0>(G, job, &Q.counters[Q_PRIMARY_HEAD], Q.counters[Q_CAND], refill);
+  march_loop<0>(G, job, &Q.counters[Q_PRIMARY_HEAD], Q.counters[Q_CAND], refill & 0xff, refill >> 8);
 }
 
 // ---- ordered compaction of the hit flags (count per block, scan the block counts, scatter in pixel order)
@@ -115,34 +116,15 @@ __device__ __forceinline__ uint32_t flags8(const uint8_t* flag, size_t first, si
   }
   return m;
 }
-__global__ void __launch_bounds__(256) k_hit_count(const uint8_t* __restrict__ flag, size_t first_pix, size_t npix, uint32_t* __restrict__ block_count) {
+// One-kernel compaction: every 2048-pixel block keeps its hits contiguous and in pixel order (that is what the
+// consumers' coalescing needs); the blocks' base offsets come from one atomicAdd each, so the order of the blocks in the
+// list is arbitrary — results do not depend on it, every hit pixel is processed independently.
+__global__ void __launch_bounds__(256) k_hit_compact(const uint8_t* __restrict__ flag, size_t npix, uint32_t* __restrict__ counters,
+                                                     uint32_t* __restrict__ hit_pix) {
   __shared__ uint32_t s_warp[8];
-  const size_t base = first_pix + (size_t)blockIdx.x * COMPACT_BLOCK + (size_t)threadIdx.x * 8;
-  uint32_t c = base < first_pix + npix ? __popc(flags8(flag, base, first_pix + npix)) : 0u;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; block_count[blockIdx.x] = t; }
-}
-__global__ void __launch_bounds__(1024) k_hit_scan(uint32_t* __restrict__ block_count, uint32_t nblocks, uint32_t* __restrict__ counters) {
-  __shared__ uint32_t s_part[1024];
-  const uint32_t per = (nblocks + 1023u) / 1024u;
-  const uint32_t lo = threadIdx.x * per, hi = min(lo + per, nblocks);
-  uint32_t sum = 0;
-  for (uint32_t i = lo; i < hi; ++i) sum += block_count[i];
-  s_part[threadIdx.x] = sum;
-  __syncthreads();
-  if (threadIdx.x == 0) { uint32_t acc = 0; for (int i = 0; i < 1024; ++i) { uint32_t v = s_part[i]; s_part[i] = acc; acc += v; } counters[Q_HIT] = acc; }
-  __syncthreads();
-  uint32_t acc = s_part[threadIdx.x];
-  for (uint32_t i = lo; i < hi; ++i) { uint32_t v = block_count[i]; block_count[i] = acc; acc += v; }
-}
-__global__ void __launch_bounds__(256) k_hit_scatter(const uint8_t* __restrict__ flag, size_t first_pix, size_t npix,
-                                                     const uint32_t* __restrict__ block_offset, uint32_t* __restrict__ hit_pix) {
-  __shared__ uint32_t s_warp[8];
-  const size_t base = first_pix + (size_t)blockIdx.x * COMPACT_BLOCK + (size_t)threadIdx.x * 8;
-  const uint32_t m = base < first_pix + npix ? flags8(flag, base, first_pix + npix) : 0u;
+  __shared__ uint32_t s_base;
+  const size_t base = (size_t)blockIdx.x * COMPACT_BLOCK + (size_t)threadIdx.x * 8;
+  const uint32_t m = base < npix ? flags8(flag, base, npix) : 0u;
   const uint32_t c = __popc(m);
   uint32_t incl = c;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -150,7 +132,13 @@ __global__ void __launch_bounds__(256) k_hit_scatter(const uint8_t* __restrict__
   for (int o = 1; o < 32; o <<= 1) { uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
   if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
-  uint32_t off = block_offset[blockIdx.x] + incl - c;
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int w = 0; w < 8; ++w) total += s_warp[w];
+    s_base = total ? atomicAdd(&counters[Q_HIT], total) : 0u;
+  }
+  __syncthreads();
+  uint32_t off = s_base + incl - c;
   for (int w = 0; w < warp; ++w) off += s_warp[w];
   uint32_t mm = m;
   while (mm) { const int k = __ffs(mm) - 1; mm &= mm - 1; hit_pix[off++] = (uint32_t)(base + k); }
@@ -236,7 +224,7 @@ struct ShadowJob {
 
 __global__ void __launch_bounds__(128) k_shadow(const GridDev G, Queues Q, int refill) {
   ShadowJob job{Q, 0u};
-  march_loop<1>(G, job, &Q.counters[Q_SHADOW_HEAD], Q.counters[Q_SHADOW], refill);
+  march_loop<1>(G, job, &Q.counters[Q_SHADOW_HEAD], Q.counters[Q_SHADOW], refill & 0xff, refill >> 8);
 }
 
 __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, Planes prev, ResPlanes prevR,
@@ -466,17 +454,17 @@ __global__ void k_sample_density(const GridDev G, const int* __restrict__ ijk, u
 void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, Planes prev,
                     ResPlanes prevR, ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1,
                     int persistent_blocks, cudaEvent_t prev_halo_ready, const unsigned* const* peer_wait) {
-  static const int refill = getenv("VRS_REFILL") ? atoi(getenv("VRS_REFILL")) : REFILL_MIN_IDLE;
+  // tuning knobs of the persistent raymarch kernels: idle lanes that trigger a refill | cell visits per scheduling decision << 8
+  static const int refill = (getenv("VRS_REFILL") ? atoi(getenv("VRS_REFILL")) : REFILL_MIN_IDLE) |
+                            ((getenv("VRS_CELLS") ? atoi(getenv("VRS_CELLS")) : CELLS_PER_DECISION) << 8);
   cudaMemsetAsync(Q.counters, 0, 8 * sizeof(uint32_t), st);
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_classify<<<grid, block, 0, st>>>(G, dF, cur, Q, trace, y0, y1, store_y0);
   k_primary<<<persistent_blocks, 128, 0, st>>>(G, dF, cur, Q, trace, store_y0, refill);
   // compaction runs over every stored row (8-byte aligned flag loads); flags outside the band rows stay 0
-  const size_t first_pix = 0, npix = (size_t)(store_y1 - store_y0) * F.W;
+  const size_t npix = (size_t)(store_y1 - store_y0) * F.W;
   const uint32_t nblocks = (uint32_t)((npix + COMPACT_BLOCK - 1) / COMPACT_BLOCK);
-  k_hit_count<<<nblocks, 256, 0, st>>>(Q.flag, first_pix, npix, Q.block_count);
-  k_hit_scan<<<1, 1024, 0, st>>>(Q.block_count, nblocks, Q.counters);
-  k_hit_scatter<<<nblocks, 256, 0, st>>>(Q.flag, first_pix, npix, Q.block_count, Q.hit_pix);
+  k_hit_compact<<<nblocks, 256, 0, st>>>(Q.flag, npix, Q.counters, Q.hit_pix);
   const bool vis = (F.flags & FLAG_VISIBILITY) != 0, temporal = (F.flags & FLAG_TEMPORAL) != 0;
   const int needs_finish = (vis || temporal) ? 1 : 0;
   k_ris<<<persistent_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
@@ -488,7 +476,7 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
 }
 int initial_pass_launches(int flags) {
   const bool vis = (flags & FLAG_VISIBILITY) != 0, temporal = (flags & FLAG_TEMPORAL) != 0;
-  return 6 + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
+  return 4 + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
 }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, int store_y0, int store_y1, int persistent_blocks) {
