@@ -1,0 +1,143 @@
+"""not gpu: generated .vdb fixtures (oracle/vdb_write.py) drive the product's C++ reader (vrs_convert_vdb) and the oracle's
+numpy reader through the on-disk variants the two shipped assets never use: ZIP blocks, fp32 values, node-mask metadata
+codes 0..6, internal / root tiles, negative coordinates, several grids per file, file versions 222-224, and malformed input."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+
+
+def spec_value(g, i, j, k):
+    o = (i & ~7, j & ~7, k & ~7)
+    if o in g.leaves:
+        v, m = g.leaves[o]
+        off = ((i & 7) << 6) | ((j & 7) << 3) | (k & 7)
+        return float(v[off])
+    for (to, lg, tv, _a) in g.tiles:
+        s = 1 << lg
+        if to[0] <= i < to[0] + s and to[1] <= j < to[1] + s and to[2] <= k < to[2] + s:
+            return float(tv)
+    return float(g.background)
+
+
+def build_cases():
+    import vdb_write as W
+    rng = np.random.default_rng(11)
+    cases = []
+    for half, comp, version in [(False, W.COMPRESS_ZIP | W.COMPRESS_ACTIVE_MASK, 224), (True, W.COMPRESS_ACTIVE_MASK, 222),
+                                (False, 0, 223), (True, W.COMPRESS_ZIP, 224)]:
+        g = W.Grid("density", background=0.0, half=half, compression=comp, voxel_size=0.25, translation=(1.0, -2.0, 3.5))
+        for o in [(-16, 0, 8), (-8, 0, 8), (0, 0, 0), (8, 8, 8), (120, 120, 120), (128, 0, 0), (-4096, 8, 16), (4096, -8, 0)]:
+            m = rng.uniform(size=512) < 0.4
+            v = np.where(m, rng.uniform(0.1, 3.0, 512), 0.0)
+            g.set_leaf(o, v, m)
+        g.add_tile((16, 0, 8), 3, 0.75, True)         # active 8^3 tile
+        g.add_tile((256, 128, 0), 7, 1.5, True)       # active 128^3 tile
+        cases.append((g, version))
+    # level set with +-background inactive values (codes 1 and 3), inactive interior tiles
+    bg = np.float32(0.15)
+    g = W.Grid("ls", background=bg, half=False, compression=W.COMPRESS_ACTIVE_MASK | W.COMPRESS_ZIP, voxel_size=0.05, grid_class="level set")
+    idx = np.arange(512); x = idx >> 6
+    m = (x >= 3) & (x <= 5)
+    g.set_leaf((0, 0, 0), np.where(m, (x - 4) * 0.05, np.where(x < 3, -bg, bg)), m)              # code 3
+    g.set_leaf((-8, 0, 0), np.where(m, -0.01, -bg), m)                                             # code 1
+    g.set_leaf((8, 0, 0), np.where(m, 0.02, bg), m)                                                # code 0
+    g.add_tile((-16, 0, 0), 3, -bg, False)                                                         # inactive interior tile
+    cases.append((g, 224))
+    # explicit inactive values: codes 2, 4, 5, 6
+    g = W.Grid("odd", background=0.5, half=False, compression=W.COMPRESS_ACTIVE_MASK, voxel_size=1.0)
+    m = rng.uniform(size=512) < 0.3
+    act = rng.uniform(1, 2, 512)
+    g.set_leaf((0, 0, 0), np.where(m, act, 7.25), m)                                               # code 2
+    g.set_leaf((8, 0, 0), np.where(m, act, np.where(idx % 2 == 0, 0.5, 9.0)), m)                   # code 4
+    g.set_leaf((16, 0, 0), np.where(m, act, np.where(idx % 3 == 0, 3.0, 4.0)), m)                  # code 5
+    g.set_leaf((24, 0, 0), np.where(m, act, (idx % 5).astype(np.float32)), m)                      # code 6
+    g.add_tile((0, 4096, 0), 12, 2.5, False)                                                       # inactive root tile with a value
+    cases.append((g, 224))
+    return cases
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_both_readers_reproduce_the_written_grid(V, tmp_path, case):
+    import grid_py
+    import vdb_py
+    import vdb_write as W
+    g, version = build_cases()[case]
+    path = str(tmp_path / "fixture.vdb")
+    W.write_vdb(path, [g], version=version)
+    # oracle reader
+    pg = vdb_py.read_vdb(path)
+    assert pg.topology_end == pg.block_pos and pg.buffers_end == pg.end_pos
+    dense_py, vmin, vdim = pg.dense_raw()
+    # product reader
+    out = str(tmp_path / "fixture.vrsg")
+    V.convert_vdb(path, out)
+    sg = grid_py.read_vrsg(out)
+    dense_cc, vmin2, vdim2 = grid_py.dense_raw(sg)
+    assert vmin == vmin2 and vdim == vdim2
+    assert dense_py.tobytes() == dense_cc.tobytes()
+    assert abs(sg.voxel_size - g.voxel_size) < 1e-12 and bool(sg.level_set) == (g.grid_class == "level set")
+    if g.translation is not None:
+        assert np.allclose(sg.translation, g.translation)
+    # ground truth at random points inside the window and at every leaf corner
+    rng = np.random.default_rng(case)
+    pts = [tuple(int(rng.integers(vmin[a], vmin[a] + vdim[a])) for a in range(3)) for _ in range(min(4000, int(np.prod(vdim))))]
+    pts += [o for o in g.leaves] + [(o[0] + 7, o[1] + 7, o[2] + 7) for o in g.leaves]
+    for (i, j, k) in pts:
+        x, y, z = i - vmin[0], j - vmin[1], k - vmin[2]
+        if 0 <= x < vdim[0] and 0 <= y < vdim[1] and 0 <= z < vdim[2]:
+            assert float(dense_py[z, y, x]) == spec_value(g, i, j, k), (i, j, k)
+    active = sum(int(m.sum()) for _v, m in g.leaves.values()) + sum((1 << lg) ** 3 for (_o, lg, _v, a) in g.tiles if a)
+    assert pg.active_voxel_count() == active and int(sg.leaf_mask.sum()) == sum(int(m.sum()) for _v, m in g.leaves.values())
+
+
+def test_grid_selection_by_name_and_errors(V, tmp_path):
+    import grid_py
+    import vdb_write as W
+    a = W.Grid("density", background=0.0)
+    a.set_leaf((0, 0, 0), np.full(512, 1.0), np.ones(512, bool))
+    b = W.Grid("temperature", background=0.0)
+    b.set_leaf((8, 0, 0), np.full(512, 300.0), np.ones(512, bool))
+    path = str(tmp_path / "two.vdb")
+    W.write_vdb(path, [a, b])
+    V.convert_vdb(path, str(tmp_path / "first.vrsg"))                       # first float grid
+    V.convert_vdb(path, str(tmp_path / "temp.vrsg"), grid_name="temperature")
+    assert grid_py.read_vrsg(str(tmp_path / "first.vrsg")).leaf_origin.tolist() == [[0, 0, 0]]
+    g2 = grid_py.read_vrsg(str(tmp_path / "temp.vrsg"))
+    assert g2.leaf_origin.tolist() == [[8, 0, 0]] and float(g2.leaf_value[0, 0]) == 300.0
+    with pytest.raises(V.VrsError) as e:
+        V.convert_vdb(path, str(tmp_path / "x.vrsg"), grid_name="velocity")
+    assert e.value.status == 4
+    # truncated file, blosc flag, old file version
+    raw = open(path, "rb").read()
+    (tmp_path / "trunc.vdb").write_bytes(raw[:len(raw) // 2])
+    with pytest.raises(V.VrsError) as e:
+        V.convert_vdb(str(tmp_path / "trunc.vdb"), str(tmp_path / "x.vrsg"))
+    assert e.value.status == 4
+    c = W.Grid("density", compression=4 | 2)                                   # COMPRESS_BLOSC
+    c.set_leaf((0, 0, 0), np.full(512, 1.0), np.ones(512, bool))
+    W.write_vdb(str(tmp_path / "blosc.vdb"), [c])
+    with pytest.raises(V.VrsError) as e:
+        V.convert_vdb(str(tmp_path / "blosc.vdb"), str(tmp_path / "x.vrsg"))
+    assert e.value.status == 4 and "Blosc" in str(e.value)
+    W.write_vdb(str(tmp_path / "old.vdb"), [a], version=220)
+    with pytest.raises(V.VrsError) as e:
+        V.convert_vdb(str(tmp_path / "old.vdb"), str(tmp_path / "x.vrsg"))
+    assert e.value.status == 4 and "222" in str(e.value)
+
+
+def test_procedural_standins_are_deterministic(V, tmp_path):
+    import grid_py
+    a, b = str(tmp_path / "a.vrsg"), str(tmp_path / "b.vrsg")
+    V.write_procedural_vrsg("torus_knot_helix", 64, a)
+    V.write_procedural_vrsg("torus_knot_helix", 64, b)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    for kind in ("bunny_cloud", "explosion", "fire"):
+        V.write_procedural_vrsg(kind, 64, a)
+        g = grid_py.read_vrsg(a)
+        assert len(g.leaf_origin) > 10 and 0.0 < float(g.leaf_value.max()) < 10.0 and not g.level_set
+        assert (g.leaf_value[~g.leaf_mask] == 0).all()
+    with pytest.raises(V.VrsError):
+        V.write_procedural_vrsg(0, 30, a)
