@@ -350,7 +350,7 @@ inline TrackResult track(const Grid& g, V3 org, V3 dir, float tmin, float tmax, 
           if (u2 * mu_d < dens) { R.hit = true; R.t = t; R.vox[0] = vx[0]; R.vox[1] = vx[1]; R.vox[2] = vx[2]; return R; }
         } else {
           R.T = R.T * (1.0f - dens / mu_d);
-          if (!(R.T > 0.0f)) { R.T = 0.0f; return R; }
+          if (!(R.T > 1e-5f)) { R.T = 0.0f; return R; }     // opaque for every practical purpose: stop marching
         }
         tau = neglog1m(rnd(seed));
       }

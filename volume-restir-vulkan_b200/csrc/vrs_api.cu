@@ -224,16 +224,7 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
   }
   for (size_t t = 0; t < h.tile_value.size(); ++t) { tile_density[t] = h.density_from_raw(h.tile_value[t]); if (tile_density[t] > gmaxd) gmaxd = tile_density[t]; }
   ctx->max_density = gmaxd;
-  auto stage = [&](const void* src, size_t bytes, const void** dst) -> bool {
-    void* p = nullptr;
-    size_t sz = bytes ? bytes : 16;
-    if (cudaMalloc(&p, sz) != cudaSuccess) return false;
-    ctx->grid_allocs.push_back(p); ctx->grid_bytes += sz;
-    if (bytes && cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return false;
-    *dst = p;
-    return true;
-  };
-  // dense directory over the window's cells
+  // dense directory over the window's cells (the top tree levels flattened once more for the raymarch)
   const size_t ncell = (size_t)G.cdim[0] * G.cdim[1] * G.cdim[2];
   if (ncell > ((size_t)1 << 30)) { free_grid(ctx); return fail(ctx, VRS_ERR_UNSUPPORTED, "grid window exceeds 2^30 cells"); }
   std::vector<float> dir_max(ncell); std::vector<int32_t> dir_leaf(ncell);
@@ -253,13 +244,44 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
         dir_leaf[ci] = c;
         dir_max[ci] = c < 0 ? tile_density[~c] : leaf_max[c];
       }
+  // One slab for every grid table, so that a single L2 access-policy window can pin the whole grid: the per-pixel
+  // buffers stream through L2 every frame (hundreds of MB) and would otherwise evict the few MB every ray keeps re-reading.
+  struct Part { const void* src; size_t bytes; const void** dst; };
   G.nroot = (int)(h.root.size() / 4);
-  bool ok = stage(h.root.data(), h.root.size() * 4, (const void**)&G.root) && stage(h.i5.data(), h.i5.size() * 4, (const void**)&G.i5) &&
-            stage(h.i4.data(), h.i4.size() * 4, (const void**)&G.i4) &&
-            stage(tile_density.data(), tile_density.size() * 4, (const void**)&G.tile_density) &&
-            stage(leaf_max.data(), leaf_max.size() * 4, (const void**)&G.leaf_max) && stage(atlas.data(), atlas.size() * 4, (const void**)&G.atlas) &&
-            stage(dir_max.data(), dir_max.size() * 4, (const void**)&G.dir_max) && stage(dir_leaf.data(), dir_leaf.size() * 4, (const void**)&G.dir_leaf);
-  if (!ok) { free_grid(ctx); return fail(ctx, VRS_ERR_CUDA, "grid staging failed"); }
+  Part parts[] = {{h.root.data(), h.root.size() * 4, (const void**)&G.root}, {h.i5.data(), h.i5.size() * 4, (const void**)&G.i5},
+                  {h.i4.data(), h.i4.size() * 4, (const void**)&G.i4}, {tile_density.data(), tile_density.size() * 4, (const void**)&G.tile_density},
+                  {leaf_max.data(), leaf_max.size() * 4, (const void**)&G.leaf_max}, {dir_max.data(), dir_max.size() * 4, (const void**)&G.dir_max},
+                  {dir_leaf.data(), dir_leaf.size() * 4, (const void**)&G.dir_leaf}, {atlas.data(), atlas.size() * 4, (const void**)&G.atlas}};
+  size_t total = 0;
+  for (const Part& p : parts) total += (p.bytes + 255) & ~(size_t)255;
+  char* slab = nullptr;
+  if (cudaMalloc((void**)&slab, total ? total : 256) != cudaSuccess) { free_grid(ctx); return fail(ctx, VRS_ERR_CUDA, "grid staging failed (cudaMalloc)"); }
+  ctx->grid_allocs.push_back(slab); ctx->grid_bytes = total;
+  size_t off = 0;
+  for (const Part& p : parts) {
+    if (p.bytes && cudaMemcpy(slab + off, p.src, p.bytes, cudaMemcpyHostToDevice) != cudaSuccess) { free_grid(ctx); return fail(ctx, VRS_ERR_CUDA, "grid staging failed (copy)"); }
+    *p.dst = slab + off;
+    off += (p.bytes + 255) & ~(size_t)255;
+  }
+  // persisting-L2 window over the slab (hot part first: directory + atlas sit at the end, tables are tiny except i5)
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && !getenv("VRS_NO_L2_WINDOW")) {
+      size_t want = total < (size_t)prop.persistingL2CacheMaxSize ? total : (size_t)prop.persistingL2CacheMaxSize;
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaStreamAttrValue attr; memset(&attr, 0, sizeof(attr));
+      size_t win = total < (size_t)prop.accessPolicyMaxWindowSize ? total : (size_t)prop.accessPolicyMaxWindowSize;
+      attr.accessPolicyWindow.base_ptr = slab;
+      attr.accessPolicyWindow.num_bytes = win;
+      attr.accessPolicyWindow.hitRatio = win <= want ? 1.0f : (float)want / (float)win;
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();       // best effort: the window is an optimisation, never an error
+    }
+  }
+  for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);   // captured pointers are stale now
+  ctx->graphs.clear(); ctx->seen.clear();
   ctx->has_grid = true;
   return VRS_OK;
 }

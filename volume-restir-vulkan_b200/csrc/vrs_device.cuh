@@ -498,7 +498,7 @@ struct Ray {
       if (u2 * mu_d < dens) { hit = true; vox[0] = vx; vox[1] = vy; vox[2] = vz; return RAY_DONE; }
     } else {
       T = T * (1.0f - dens / mu_d);
-      if (!(T > 0.0f)) { T = 0.0f; return RAY_DONE; }
+      if (!(T > 1e-5f)) { T = 0.0f; return RAY_DONE; }      // opaque for every practical purpose: stop marching
     }
     tau = neglog1m(rnd(seed));
     return consume(G);
