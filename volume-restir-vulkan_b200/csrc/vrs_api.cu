@@ -155,6 +155,12 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
   return VRS_OK;
 }
 
+static void invalidate_graphs(vrs_ctx* ctx) {
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  ctx->graphs.clear(); ctx->seen.clear();
+}
+
 static void free_grid(vrs_ctx* ctx) {
   for (void* p : ctx->grid_allocs) cudaFree(p);
   ctx->grid_allocs.clear(); ctx->has_grid = false; ctx->grid_bytes = 0;
@@ -280,8 +286,7 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
       cudaGetLastError();       // best effort: the window is an optimisation, never an error
     }
   }
-  for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);   // captured pointers are stale now
-  ctx->graphs.clear(); ctx->seen.clear();
+  invalidate_graphs(ctx);   // captured pointers are stale now
   ctx->has_grid = true;
   return VRS_OK;
 }
@@ -368,6 +373,7 @@ vrs_status vrs_set_lights(vrs_ctx* ctx, const vrs_point_light* lights, uint32_t 
   for (uint32_t i = 0; i < n; ++i) pdf[i] = lights[i].emission_luminance[3];      // Renderer.cpp:1653-1657
   ctx->alias_host.resize(n);
   vrs_create_alias_table(pdf.data(), n, ctx->alias_host.data());
+  invalidate_graphs(ctx);   // captured frames point at the old light buffers
   cudaFree(ctx->d_lights); cudaFree(ctx->d_alias); ctx->d_lights = ctx->d_alias = nullptr;
   CK(cudaMalloc(&ctx->d_lights, (size_t)n * sizeof(vrs_point_light)));
   CK(cudaMalloc(&ctx->d_alias, (size_t)n * sizeof(vrs_alias_table_cell)));
