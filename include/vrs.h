@@ -140,6 +140,11 @@ vrs_status vrs_set_lights(vrs_ctx* ctx, const vrs_point_light* lights, uint32_t 
  * grid) into a point light at the voxel's world position with emission (0.6, 0.2, 0.1), stop after `max_lights`
  * (the reference stops after 1001).  Host-side; fills `out` and returns the count. */
 vrs_status vrs_collect_emissive_lights(const vrs_ctx* ctx, float threshold, uint32_t max_lights, vrs_point_light* out, uint32_t* count);
+/* The same rule on a temperature grid read straight from a `.vdb` (multi-grid files: density is rendered, temperature only
+ * feeds the lights): vdb/vdb.cpp:809-812 computes temp = log(T) + 273.15 per active voxel and Renderer.cpp:1623 keeps
+ * temp > 275.  Host-only; positions use `cfg`'s world placement (only world_scale / world_translate are read). */
+vrs_status vrs_vdb_emissive_lights(const char* vdb_path, const char* grid_name, const vrs_config* cfg, uint32_t max_lights,
+                                   vrs_point_light* out, uint32_t* count);
 vrs_status vrs_set_triangle_lights(vrs_ctx* ctx, const vrs_triangle_light* lights, uint32_t n); /* VRS_ERR_UNSUPPORTED */
 vrs_status vrs_get_alias_table(const vrs_ctx* ctx, vrs_alias_table_cell* out, uint32_t n);
 

@@ -141,3 +141,36 @@ def test_procedural_standins_are_deterministic(V, tmp_path):
         assert (g.leaf_value[~g.leaf_mask] == 0).all()
     with pytest.raises(V.VrsError):
         V.write_procedural_vrsg(0, 30, a)
+
+
+def test_emissive_voxel_lights_from_temperature_grid(V, tmp_path):
+    """density + temperature in one file; lights come from temp = log(T) + 273.15 > 275 (vdb.cpp:811,
+    Renderer.cpp:1615-1637), in tree order, at most 1001, emission (0.6, 0.2, 0.1)."""
+    import vdb_write as W
+    rng = np.random.default_rng(2)
+    dens = W.Grid("density", background=0.0, voxel_size=0.5, translation=(1.0, 2.0, 3.0))
+    temp = W.Grid("temperature", background=0.0, voxel_size=0.5, translation=(1.0, 2.0, 3.0))
+    T = {}
+    for o in [(0, 0, 0), (8, 0, 0), (-8, 16, 24)]:
+        m = rng.uniform(size=512) < 0.5
+        dens.set_leaf(o, np.where(m, 1.0, 0.0), m)
+        t = np.where(m, rng.uniform(0.5, 20.0, 512), 0.0).astype(np.float32)
+        temp.set_leaf(o, t, m)
+        T[o] = (t, m)
+    path = str(tmp_path / "fire.vdb")
+    W.write_vdb(path, [dens, temp])
+    lights = V.vdb_emissive_lights(path, "temperature", max_lights=1001)
+    # expected set: every active voxel with log(T) + 273.15 > 275
+    want = set()
+    for o, (t, m) in T.items():
+        for off in np.nonzero(m)[0]:
+            if np.float32(np.float64(np.log(np.float32(t[off]))) + 273.15) > np.float32(275.0):
+                ijk = (o[0] + (off >> 6), o[1] + ((off >> 3) & 7), o[2] + (off & 7))
+                want.add(tuple(np.float32(np.float32(np.float64(np.float32(0.05)) * 0.5) * np.float32(c) + np.float32(np.float64(np.float32(0.05)) * tr + np.float64(np.float32(wt))))
+                               for c, tr, wt in zip(ijk, (1.0, 2.0, 3.0), (-2.5, 0.5, 0.0))))
+    got = set(tuple(np.float32(v) for v in l[:3]) for l in lights)
+    assert len(lights) == min(len(want), 1001) and (got <= want)
+    assert np.allclose(lights[:, 4:7], [0.6, 0.2, 0.1]) and np.allclose(lights[:, 3], 1.0)
+    assert np.allclose(lights[:, 7], 0.2126 * 0.6 + 0.7152 * 0.2 + 0.0722 * 0.1)
+    assert len(V.vdb_emissive_lights(path, "temperature", max_lights=5)) == 5
+    assert len(V.vdb_emissive_lights(path, "density")) == 0               # log(1) + 273.15 < 275

@@ -28,7 +28,7 @@ STATUS = {0: "VRS_OK", 1: "VRS_ERR_INVALID", 2: "VRS_ERR_CUDA", 3: "VRS_ERR_IO",
 EXPORTS = [
     "vrs_default_config", "vrs_default_restir_uniforms", "vrs_create", "vrs_destroy", "vrs_last_error", "vrs_abi_version",
     "vrs_load_vdb", "vrs_load_vrsg", "vrs_convert_vdb", "vrs_make_procedural_grid", "vrs_write_procedural_vrsg", "vrs_get_grid_info", "vrs_grid_get_value",
-    "vrs_grid_sample_device", "vrs_set_lights", "vrs_collect_emissive_lights", "vrs_set_triangle_lights", "vrs_get_alias_table", "vrs_create_alias_table",
+    "vrs_grid_sample_device", "vrs_set_lights", "vrs_collect_emissive_lights", "vrs_vdb_emissive_lights", "vrs_set_triangle_lights", "vrs_get_alias_table", "vrs_create_alias_table",
     "vrs_generate_point_lights", "vrs_perspectiveVK", "vrs_look_at", "vrs_invert", "vrs_mat4_mul", "vrs_pass_initial",
     "vrs_pass_spatial", "vrs_pass_shade", "vrs_render_frame", "vrs_synchronize", "vrs_read_frame", "vrs_read_gbuffer",
     "vrs_read_reservoirs", "vrs_read_trace", "vrs_read_display", "vrs_present_async", "vrs_present_wait", "vrs_write_image", "vrs_get_timings", "vrs_stream", "vrs_comm_unique_id",
@@ -117,7 +117,7 @@ def lib():
         L.vrs_destroy.argtypes = [C.c_void_p]
         L.vrs_destroy.restype = None
         for name in ["vrs_load_vdb", "vrs_load_vrsg", "vrs_make_procedural_grid", "vrs_write_procedural_vrsg", "vrs_get_grid_info", "vrs_grid_get_value",
-                     "vrs_grid_sample_device", "vrs_set_lights", "vrs_collect_emissive_lights", "vrs_set_triangle_lights", "vrs_get_alias_table",
+                     "vrs_grid_sample_device", "vrs_set_lights", "vrs_collect_emissive_lights", "vrs_vdb_emissive_lights", "vrs_set_triangle_lights", "vrs_get_alias_table",
                      "vrs_pass_initial", "vrs_pass_spatial", "vrs_pass_shade", "vrs_render_frame", "vrs_synchronize",
                      "vrs_read_frame", "vrs_read_gbuffer", "vrs_read_reservoirs", "vrs_read_trace", "vrs_write_image",
                      "vrs_get_timings", "vrs_comm_init", "vrs_read_display", "vrs_present_async", "vrs_present_wait"]:
@@ -222,6 +222,22 @@ def write_procedural_vrsg(kind, resolution, path):
     s = lib().vrs_write_procedural_vrsg(k, resolution, path.encode())
     if s:
         raise VrsError(s, lib().vrs_last_error(None).decode())
+
+
+def vdb_emissive_lights(vdb_path, grid_name="temperature", max_lights=1001, world_scale=0.05, world_translate=(-2.5, 0.5, 0.0)):
+    """Emissive-voxel lights of Renderer::createRestirLights from a temperature grid of a .vdb file (host-only)."""
+    L = lib()
+    cfg = Config()
+    L.vrs_default_config(C.byref(cfg), 1, 1)
+    cfg.world_scale = world_scale
+    cfg.world_translate[:] = list(world_translate)
+    out = np.zeros((max_lights, 8), np.float32)
+    n = C.c_uint32()
+    L.vrs_vdb_emissive_lights.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    s = L.vrs_vdb_emissive_lights(vdb_path.encode(), grid_name.encode() if grid_name else None, C.byref(cfg), max_lights, _p(out), C.byref(n))
+    if s:
+        raise VrsError(s, L.vrs_last_error(None).decode())
+    return out[:n.value].copy()
 
 
 def band_for_rank(height, rank, nranks):

@@ -402,6 +402,30 @@ vrs_status vrs_collect_emissive_lights(const vrs_ctx* ctx, float threshold, uint
   *count = n;
   return VRS_OK;
 }
+vrs_status vrs_vdb_emissive_lights(const char* vdb_path, const char* grid_name, const vrs_config* cfg, uint32_t max_lights,
+                                   vrs_point_light* out, uint32_t* count) {
+  if (!vdb_path || !cfg || !out || !count) return VRS_ERR_INVALID;
+  HostGrid h; std::string err;
+  if (!read_vdb(vdb_path, grid_name, h, err)) return fail(nullptr, err.rfind("cannot open", 0) == 0 ? VRS_ERR_IO : VRS_ERR_FORMAT, err);
+  const float A = (float)((double)cfg->world_scale * h.voxel_size);
+  float B[3];
+  for (int a = 0; a < 3; ++a) B[a] = (float)((double)cfg->world_scale * h.translation[a] + (double)cfg->world_translate[a]);
+  uint32_t n = 0;
+  for (size_t l = 0; l < h.nleaf() && n < max_lights; ++l)
+    for (int o = 0; o < 512 && n < max_lights; ++o) {
+      if (!((h.leaf_mask[l * 8 + (o >> 6)] >> (o & 63)) & 1)) continue;
+      const float temp = (float)((double)logf(h.leaf_value[l * 512 + o]) + 273.15);            // vdb.cpp:811
+      if (!(temp > 275.0f)) continue;                                                           // Renderer.cpp:1623
+      const int ijk[3] = {h.leaf_origin[3 * l] + (o >> 6), h.leaf_origin[3 * l + 1] + ((o >> 3) & 7), h.leaf_origin[3 * l + 2] + (o & 7)};
+      vrs_point_light& p = out[n++];
+      for (int a = 0; a < 3; ++a) p.pos[a] = A * (float)ijk[a] + B[a];
+      p.pos[3] = 1.0f;
+      p.emission_luminance[0] = 0.6f; p.emission_luminance[1] = 0.2f; p.emission_luminance[2] = 0.1f;   // Renderer.cpp:1627
+      p.emission_luminance[3] = 0.2126f * 0.6f + 0.7152f * 0.2f + 0.0722f * 0.1f;
+    }
+  *count = n;
+  return VRS_OK;
+}
 vrs_status vrs_set_triangle_lights(vrs_ctx* ctx, const vrs_triangle_light*, uint32_t) {
   return fail(ctx, VRS_ERR_UNSUPPORTED, "triangle lights belong to the mesh path (SURVEY.md §8f rank 4), not the volume hot path");
 }
