@@ -60,7 +60,7 @@ def test_camera_inside_volume(V, O):
     R.destroy()
 
 
-@pytest.mark.parametrize("M,k,iters", [(1, 1, 1), (64, 16, 4), (32, 0, 2)])
+@pytest.mark.parametrize("M,k,iters", [(1, 1, 1), (64, 16, 4), (32, 0, 2), (7, 2, 1), (40, 3, 1), (100, 1, 1)])
 def test_parameter_extremes(V, O, M, k, iters):
     R, OR, ref = render_pair(V, O, "smoke", 96, 64, 1, 7, M=M, k=k, iters=iters, frames=3)
     assert_same(R, OR, ref)

@@ -264,10 +264,9 @@ __device__ __forceinline__ void specularFactorsPre(const PHatGeom& q, const Shad
   Gs *= pre.smithOut;
   GsDs = Gs * Ds;
 }
-__device__ __forceinline__ float evaluatePHat(const LightsDev& L, uint32_t lightIdx, const GInfo& g, const ShadePre& pre) {   // :36-78
-  float4 lp = __ldg(&L.lights[2 * lightIdx]);
-  float4 le = __ldg(&L.lights[2 * lightIdx + 1]);
-  PHatGeom q = phat_geometry(v3(lp.x, lp.y, lp.z), g, pre);
+// evaluatePHat (:36-78) for a point light already fetched: position and luminance (PointLight.emission_luminance.w)
+__device__ __forceinline__ float evaluatePHatLight(V3 lightPos, float lum, const GInfo& g, const ShadePre& pre) {
+  PHatGeom q = phat_geometry(lightPos, g, pre);
   if (q.back) return 0.0f;
   float brdf = 0.0f;                                                                  // disneyBrdfLuminance :98-110
   if (!(q.cosIn < 0.0f)) {
@@ -278,7 +277,12 @@ __device__ __forceinline__ float evaluatePHat(const LightsDev& L, uint32_t light
     float Fs = gmix(specLum, 1.0f, fih);
     brdf = diffuse + Fs * gsds;
   }
-  return le.w * brdf * q.geometry;
+  return lum * brdf * q.geometry;
+}
+__device__ __forceinline__ float evaluatePHat(const LightsDev& L, uint32_t lightIdx, const GInfo& g, const ShadePre& pre) {   // :36-78
+  float4 lp = __ldg(&L.lights[2 * lightIdx]);
+  float4 le = __ldg(&L.lights[2 * lightIdx + 1]);
+  return evaluatePHatLight(v3(lp.x, lp.y, lp.z), le.w, g, pre);
 }
 __device__ __forceinline__ float evaluatePHat(const LightsDev& L, uint32_t lightIdx, const GInfo& g) {
   return evaluatePHat(L, lightIdx, g, shade_pre(g));
@@ -331,12 +335,19 @@ __device__ __forceinline__ void combineReservoirsGeom(const LightsDev& L, Res& s
   if (self.w > 0.0f) self.w = self.sumWeights / (float(Z) * self.pHat);
 }
 
-__device__ __forceinline__ void aliasTableSample(const LightsDev& L, float r1, float r2, uint32_t& index, float& prob) {   // restir.rgen:97-110
+// aliasTableSample (restir.rgen:97-110) in two halves so that callers can overlap the cell fetch with other work
+__device__ __forceinline__ uint32_t aliasColumn(const LightsDev& L, float r1) {
   uint32_t col = uint32_t(float(L.ntable) * r1);
   uint32_t last = uint32_t(L.ntable - 1);
   if (last < col) col = last;
-  float4 c = __ldg(&L.alias[col]);
+  return col;
+}
+__device__ __forceinline__ void aliasPick(float4 c, uint32_t col, float r2, uint32_t& index, float& prob) {
   if (c.y > r2) { index = col; prob = c.z; } else { index = (uint32_t)__float_as_int(c.x); prob = c.w; }
+}
+__device__ __forceinline__ void aliasTableSample(const LightsDev& L, float r1, float r2, uint32_t& index, float& prob) {
+  const uint32_t col = aliasColumn(L, r1);
+  aliasPick(__ldg(&L.alias[col]), col, r2, index, prob);
 }
 
 // ------------------------------------------------------------------ sparse grid lookups (flattened Tree_float_5_4_3)
@@ -546,9 +557,16 @@ __device__ __forceinline__ uint32_t warp_append(uint32_t* counter) {
 // Warp-level scheduler of the persistent raymarch kernels.  Each lane owns one ray (Job supplies fetch / retire).
 // Per iteration the warp executes ONE kind of unit step, the kind more lanes are waiting for, so divergent lanes are
 // batched instead of serialised; lanes whose ray retired are refilled from the job queue once enough are idle.
+// `lane_limit` (<= 32) caps how many lanes of a warp hold rays: when a launch has few rays (a narrow band of a multi-GPU
+// frame) they are spread over more warps, so that the per-ray serial chain is hidden by other warps instead of
+// setting the kernel's duration.  Which ray runs in which lane never changes a result.
 template <int MODE, class Job>
-__device__ __forceinline__ void march_loop(const GridDev& G, Job& job, uint32_t* head, uint32_t njobs, int refill_min_idle, int cells_per_decision) {
+__device__ __forceinline__ void march_loop(const GridDev& G, Job& job, uint32_t* head, uint32_t njobs, int refill_min_idle, int cells_per_decision,
+                                           int lane_limit) {
   const unsigned full = 0xffffffffu;
+  const unsigned limit_mask = lane_limit >= 32 ? full : ((1u << lane_limit) - 1u);
+  const bool eligible = ((limit_mask >> (threadIdx.x & 31)) & 1u) != 0;
+  if (refill_min_idle > (lane_limit + 1) / 2) refill_min_idle = (lane_limit + 1) / 2;
   Ray<MODE> ray;
   int st = RAY_DONE;
   uint32_t seed = 0;
@@ -556,8 +574,8 @@ __device__ __forceinline__ void march_loop(const GridDev& G, Job& job, uint32_t*
   for (;;) {
     const unsigned bs = __ballot_sync(full, st == RAY_SKIP), bc = __ballot_sync(full, st == RAY_COLLIDE);
     const unsigned busy = bs | bc;
-    if (!queue_empty && (__popc(~busy) >= refill_min_idle || busy == 0)) {
-      const bool want = st == RAY_DONE;
+    if (!queue_empty && (__popc(~busy & limit_mask) >= refill_min_idle || busy == 0)) {
+      const bool want = st == RAY_DONE && eligible;
       const uint32_t j = warp_fetch(head, want);
       if (want && j < njobs) st = job.fetch(G, j, ray, seed) ? RAY_SKIP : RAY_DONE;
       queue_empty = __any_sync(full, want && j >= njobs);
@@ -572,6 +590,13 @@ __device__ __forceinline__ void march_loop(const GridDev& G, Job& job, uint32_t*
       if (st == RAY_COLLIDE) { st = ray.collide_step(G, seed); if (st == RAY_DONE) job.retire(G, ray, seed); }
     }
   }
+}
+// lanes per warp for `njobs` rays on a grid of `nwarps` persistent warps: fill `target_warps` warps before widening
+__device__ __forceinline__ int lanes_for(uint32_t njobs, uint32_t nwarps, uint32_t target_warps) {
+  if (target_warps > nwarps) target_warps = nwarps;
+  if (target_warps == 0) return 32;
+  uint32_t l = (njobs + target_warps - 1) / target_warps;
+  return l < 4u ? 4 : (l > 32u ? 32 : (int)l);
 }
 
 __device__ __forceinline__ float ratio_track(const GridDev& G, V3 P, V3 L, uint32_t& seed) {

@@ -29,6 +29,7 @@ static constexpr int MAX_NEIGHBORS = 16;
 enum { Q_CAND = 0, Q_HIT = 1, Q_SHADOW = 2, Q_PRIMARY_HEAD = 3, Q_SHADOW_HEAD = 4 };
 static constexpr int REFILL_MIN_IDLE = 16;
 static constexpr int CELLS_PER_DECISION = 2;
+static constexpr int MIN_WARPS_PER_SM = 16;     // small launches are spread over at least this many warps per SM
 static constexpr int COMPACT_BLOCK = 2048;      // pixels per compaction block (256 threads x 8 flags)
 
 __device__ __forceinline__ void primary_ray(const FrameParams& F, int x, int y, V3& org, V3& dir) {   // :142-148
@@ -101,7 +102,8 @@ __global__ void __launch_bounds__(128) k_primary(const GridDev G, const FramePar
                                                  uint32_t* __restrict__ trace, int store_y0, int refill) {
   const FrameParams& F = *Fp;
   PrimaryJob job{F, cur, Q, trace, store_y0, 0u};
-  march_loop<0>(G, job, &Q.counters[Q_PRIMARY_HEAD], Q.counters[Q_CAND], refill & 0xff, refill >> 8);
+  const uint32_t njobs = Q.counters[Q_CAND], nwarps = gridDim.x * (blockDim.x >> 5);
+  march_loop<0>(G, job, &Q.counters[Q_PRIMARY_HEAD], njobs, refill & 0xff, (refill >> 8) & 0xff, lanes_for(njobs, nwarps, (uint32_t)(refill >> 16)));
 }
 
 // ---- ordered compaction of the hit flags (count per block, scan the block counts, scatter in pixel order)
@@ -144,7 +146,9 @@ __global__ void __launch_bounds__(256) k_hit_compact(const uint8_t* __restrict__
   while (mm) { const int k = __ffs(mm) - 1; mm &= mm - 1; hit_pix[off++] = (uint32_t)(base + k); }
 }
 
-__global__ void __launch_bounds__(128) k_ris(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
+// Reference form of the RIS stage: one thread per hit pixel runs the M-candidate loop serially (kept selectable with
+// VRS_RIS=thread for A/B measurements; k_ris_coop below is the default and produces the same bits).
+__global__ void __launch_bounds__(128) k_ris_thread(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
                                              Queues Q, uint32_t* __restrict__ trace, int store_y0, int needs_finish) {
   const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
@@ -208,6 +212,222 @@ __global__ void __launch_bounds__(128) k_ris(const GridDev G, const LightsDev L,
   }
 }
 
+
+// ---- A3, cooperative form.  The candidates of restir.rgen:206-226 are independent except for the running sum of the
+// streaming reservoir, so a warp takes a group of up to 32 hit pixels and turns the work 90 degrees twice:
+//   step 1  lane = pixel      gradient normal, G-buffer stores, per-pixel shading terms -> shared memory
+//   phase A lane = candidate  (one pixel at a time) LCG jump to draw 3c, alias sample, light fetch, the
+//                             dot(wi, n) < 0 early-out of restirUtils.glsl:42-44; survivors are appended to a work list
+//   phase B lane = list entry the expensive remainder of evaluatePHat on 32 surviving (pixel, candidate) pairs of
+//                             ANY pixels of the group: no lane idles behind a culled candidate
+//   step 3  lane = pixel      the serial part of updateReservoir (sum, weight / sum, compare with the third draw)
+// Every candidate's arithmetic is the reference expression on the same values, and the running sum is added in
+// candidate order, so the reservoir is bit-identical to the serial loop; w of the selected candidate is
+// (sumW at selection) / (float(c + 1) * pHat), exactly what reservoir.glsl:51 left in it.
+// The group size shrinks when a launch has few hits (multi-GPU bands), which shortens the serial chain per warp.
+struct RisSmem {
+  float w[32 * 33];                                  // candidate weights [pixel][candidate of the chunk], padded
+  uint32_t l_pc[64]; float l_pdf[64], l_lp[3][64], l_lew[64];   // phase-B work list (ring): (pixel, candidate), pdf, light position, luminance
+  float P[3][32], n[3][32], wo[3][32], fresnelOut[32], smithOut[32], albedoLum[32];
+  uint32_t seed0[32];                                // RNG state at the first candidate of the current chunk
+};
+
+__global__ void __launch_bounds__(128, 6) k_ris_coop(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
+                                                  Queues Q, uint32_t* __restrict__ trace, int store_y0, int needs_finish, int target_warps) {
+  __shared__ RisSmem sm_all[4];
+  RisSmem& sm = sm_all[threadIdx.x >> 5];
+  const FrameParams& F = *Fp;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const uint32_t nhit = Q.counters[Q_HIT];
+  const uint32_t nwarps = gridDim.x * 4u, warp = blockIdx.x * 4u + (threadIdx.x >> 5);
+  const uint32_t gsz = (uint32_t)lanes_for(nhit, nwarps, (uint32_t)target_warps);
+  const uint32_t M = F.M;
+  // LCG jump by 3 * lane draws: state' = jA * state + jC
+  uint32_t jA = 1u, jC = 0u;
+  for (int i = 0; i < 3 * lane; ++i) { jA = jA * 1664525u; jC = jC * 1664525u + 1013904223u; }
+  const float pre_a = gmax(0.001f, G.roughness * G.roughness);                     // disneyBRDF.glsl:53 (roughness is per grid)
+
+  for (uint32_t g0 = warp * gsz; g0 < nhit; g0 += nwarps * gsz) {
+    const uint32_t npix = nhit - g0 < gsz ? nhit - g0 : gsz;
+    const uint32_t s = g0 + (uint32_t)lane;
+    const bool pix = (uint32_t)lane < npix;
+    // ---------------- step 1: lane = pixel
+    uint32_t idx = 0, vcode = 0, seed = 0;
+    bool valid = false;
+    if (pix) {
+      idx = Q.hit_pix[s];
+      const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
+      const float4 scratch = cur.worldPos[idx];                                    // {t, voxel code, RNG state, 1} from k_primary
+      seed = __float_as_uint(scratch.z);
+      V3 org, dir; primary_ray(F, x, y, org, dir);
+      const V3 P = add(org, muls(dir, scratch.x));
+      vcode = __float_as_uint(scratch.y);
+      const int i = (int)(vcode % (uint32_t)G.vdim[0]) + G.vmin[0];
+      const int j = (int)((vcode / (uint32_t)G.vdim[0]) % (uint32_t)G.vdim[1]) + G.vmin[1];
+      const int k = (int)(vcode / ((uint32_t)G.vdim[0] * (uint32_t)G.vdim[1])) + G.vmin[2];
+      const float dens = density_at(G, i, j, k);
+      V3 grad = v3(density_at(G, i + 1, j, k) - density_at(G, i - 1, j, k), density_at(G, i, j + 1, k) - density_at(G, i, j - 1, k),
+                   density_at(G, i, j, k + 1) - density_at(G, i, j, k - 1));
+      const float gg = dot(grad, grad);
+      V3 n;
+      if (gg > 0.0f) { float l = sqrtf(gg); n = v3(-grad.x / l, -grad.y / l, -grad.z / l); }
+      else n = v3(-dir.x, -dir.y, -dir.z);
+      const float4 al = voxel_albedo(dens);
+      cur.worldPos[idx] = make_float4(P.x, P.y, P.z, 1.0f); cur.albedo[idx] = al;                      // :193-197
+      cur.normal[idx] = make_float4(n.x, n.y, n.z, 1.0f); cur.mat[idx] = make_float4(G.roughness, G.metallic, 1.0f, 1.0f);
+      GInfo gi;
+      gi.normal = n; gi.worldPos = P; gi.metallic = G.metallic; gi.roughness = G.roughness;
+      gi.camPos = v3(F.camPos[0], F.camPos[1], F.camPos[2]);                                           // :183
+      valid = dot(gi.normal, gi.normal) != 0.0f;                                                       // :205
+      const ShadePre pre = shade_pre(gi);
+      sm.P[0][lane] = P.x; sm.P[1][lane] = P.y; sm.P[2][lane] = P.z;
+      sm.n[0][lane] = n.x; sm.n[1][lane] = n.y; sm.n[2][lane] = n.z;
+      sm.wo[0][lane] = pre.wo.x; sm.wo[1][lane] = pre.wo.y; sm.wo[2][lane] = pre.wo.z;
+      sm.fresnelOut[lane] = pre.fresnelOut; sm.smithOut[lane] = pre.smithOut;
+      sm.albedoLum[lane] = luminance_common(al.x, al.y, al.z);                                         // :182
+      sm.seed0[lane] = seed;
+    }
+    const unsigned vmask = __ballot_sync(full, valid);
+    __syncwarp();
+
+    float sumW = 0.0f, sel_sumW = 0.0f;
+    uint32_t selc = 0xFFFFFFFFu, sel_seed = 0u;
+    for (uint32_t c0 = 0; c0 < M; c0 += 32u) {
+      const bool cact = c0 + (uint32_t)lane < M;
+      uint32_t head = 0u, tail = 0u;
+      unsigned rem = vmask;
+      // Phase A is a three-stage software pipeline over the pixels of the group, so that the two dependent L2 fetches of
+      // a candidate (alias cell -> light) are in flight while the warp works on the pixels before it:
+      //   stage 1 draws r1, r2 of pixel pN and requests its alias cells      (consumed one iteration later)
+      //   stage 2 picks the light of pixel pA and requests it                (consumed one iteration later)
+      //   stage 3 culls the candidates of pixel pL behind the surface and appends the others to the phase-B list
+      int pA = -1, pL = -1;
+      uint32_t colA = 0u, selL = 0u; float r2A = 0.0f, pdfL = 0.0f, lewL = 0.0f;
+      float4 cellA = make_float4(0.f, 0.f, 0.f, 0.f), lpL = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (;;) {
+        int pN2 = pA; uint32_t selN = 0u; float pdfN = 0.0f, lewN = 0.0f; float4 lpN = lpL;
+        if (pA >= 0) {                                                                                 // stage 2
+          aliasPick(cellA, colA, r2A, selN, pdfN);
+          lpN = __ldg(&L.lights[2 * selN]);
+          lewN = __ldg(reinterpret_cast<const float*>(L.lights) + 8 * (size_t)selN + 7);
+        }
+        int pN1 = -1; uint32_t colN = 0u; float r2N = 0.0f; float4 cellN = cellA;
+        if (rem) {                                                                                     // stage 1
+          pN1 = __ffs(rem) - 1; rem &= rem - 1u;
+          uint32_t st = jA * sm.seed0[pN1] + jC;
+          const float r1 = rnd(st); r2N = rnd(st);                                                     // :116, GLSL left-to-right
+          colN = aliasColumn(L, r1);
+          cellN = __ldg(&L.alias[colN]);
+        }
+        if (pL >= 0) {                                                                                 // stage 3
+          const int p = pL;
+          const V3 wi = sub(v3(lpL.x, lpL.y, lpL.z), v3(sm.P[0][p], sm.P[1][p], sm.P[2][p]));          // restirUtils.glsl:41-44
+          const bool back = dot(wi, v3(sm.n[0][p], sm.n[1][p], sm.n[2][p])) < 0.0f;
+          if (cact && back) {                                                                          // pHat = 0 -> weight = 0 / pdf
+            float wz = 0.0f;
+            if (!(pdfL > 0.0f)) wz = 0.0f / pdfL;
+            sm.w[p * 33 + lane] = wz;
+          }
+          const bool keep = cact && !back;
+          const unsigned m = __ballot_sync(full, keep);
+          if (keep) {
+            const uint32_t e = (tail + (uint32_t)__popc(m & lt_mask)) & 63u;
+            sm.l_pc[e] = ((uint32_t)p << 8) | (uint32_t)lane; sm.l_pdf[e] = pdfL;
+            sm.l_lp[0][e] = lpL.x; sm.l_lp[1][e] = lpL.y; sm.l_lp[2][e] = lpL.z; sm.l_lew[e] = lewL;
+          }
+          tail += (uint32_t)__popc(m);
+        }
+        const bool flush = pN1 < 0 && pN2 < 0;
+        __syncwarp();
+        while (tail - head >= 32u || (flush && tail != head)) {
+          // ---------------- phase B: lane = work-list entry (no global loads: the light travels in the list)
+          const uint32_t cnt = tail - head < 32u ? tail - head : 32u;
+          if ((uint32_t)lane < cnt) {
+            const uint32_t e = (head + (uint32_t)lane) & 63u;
+            const uint32_t pc = sm.l_pc[e];
+            const float pdf = sm.l_pdf[e];
+            const int p = (int)(pc >> 8), c = (int)(pc & 255u);
+            GInfo g;
+            g.worldPos = v3(sm.P[0][p], sm.P[1][p], sm.P[2][p]);
+            g.normal = v3(sm.n[0][p], sm.n[1][p], sm.n[2][p]);
+            g.albedoLum = sm.albedoLum[p]; g.roughness = G.roughness; g.metallic = G.metallic;
+            ShadePre pre;
+            pre.wo = v3(sm.wo[0][p], sm.wo[1][p], sm.wo[2][p]);
+            pre.fresnelOut = sm.fresnelOut[p]; pre.smithOut = sm.smithOut[p]; pre.a = pre_a; pre.cosOut = 0.0f;
+            const float pHat = evaluatePHatLight(v3(sm.l_lp[0][e], sm.l_lp[1][e], sm.l_lp[2][e]), sm.l_lew[e], g, pre);
+            sm.w[p * 33 + c] = pHat / pdf;                                                             // reservoir.glsl:47
+          }
+          head += cnt;
+          __syncwarp();
+        }
+        if (flush) break;
+        pL = pN2; selL = selN; pdfL = pdfN; lpL = lpN; lewL = lewN;
+        pA = pN1; colA = colN; r2A = r2N; cellA = cellN;
+      }
+      // ---------------- step 3: lane = pixel, the serial part of updateReservoir (reservoir.glsl:30-43) for this chunk
+      if (valid) {
+        const uint32_t cn = M - c0 < 32u ? M - c0 : 32u;
+        for (uint32_t cc = 0; cc < cn; ++cc) {
+          const uint32_t sb = seed;                                                                    // gi.sampleSeed (:213)
+          lcg(seed); lcg(seed);
+          const float wt = sm.w[lane * 33 + (int)cc];
+          sumW += wt;
+          const float replacePossibility = wt / sumW;
+          if (rnd(seed) < replacePossibility) { selc = c0 + cc; sel_seed = sb; sel_sumW = sumW; }
+        }
+        sm.seed0[lane] = seed;
+      }
+      __syncwarp();
+    }
+
+    // ---------------- lane = pixel: the selected candidate, visibility set-up, stores
+    if (pix) {
+      const V3 P = v3(sm.P[0][lane], sm.P[1][lane], sm.P[2][lane]);
+      Res res = newReservoir();
+      if (valid) {
+        res.M = M; res.sumWeights = sumW;
+        if (selc != 0xFFFFFFFFu) {
+          uint32_t st = sel_seed;
+          const float r1 = rnd(st), r2 = rnd(st);
+          uint32_t sel; float pdf;
+          aliasTableSample(L, r1, r2, sel, pdf);
+          GInfo g;
+          g.worldPos = P; g.normal = v3(sm.n[0][lane], sm.n[1][lane], sm.n[2][lane]);
+          g.albedoLum = sm.albedoLum[lane]; g.roughness = G.roughness; g.metallic = G.metallic;
+          ShadePre pre;
+          pre.wo = v3(sm.wo[0][lane], sm.wo[1][lane], sm.wo[2][lane]);
+          pre.fresnelOut = sm.fresnelOut[lane]; pre.smithOut = sm.smithOut[lane]; pre.a = pre_a; pre.cosOut = 0.0f;
+          const float pHat = evaluatePHat(L, sel, g, pre);
+          res.lightIndex = sel; res.lightKind = 0; res.pHat = pHat; res.sampleSeed = sel_seed;
+          res.w = sel_sumW / (float(selc + 1u) * pHat);                                                // reservoir.glsl:51
+        }
+      }
+      if ((F.flags & FLAG_FINALIZE_W) != 0 && res.w > 0.0f) res.w = res.sumWeights / (float(res.M) * res.pHat);
+      float4 a, b; packReservoir(res, a, b);
+      outR.info[idx] = a; outR.weight[idx] = b;
+      Q.hit_seed[s] = seed; Q.hit_T[s] = 1.0f;
+      if (trace) { trace[(size_t)idx * 4 + 0] = vcode; if (!needs_finish) trace[(size_t)idx * 4 + 3] = seed; }
+      if ((F.flags & FLAG_VISIBILITY) != 0 && res.w > 0.0f) {                                            // shadow ray of ratio_track()
+        const float4 lp = __ldg(&L.lights[2 * res.lightIndex]);
+        V3 sd = sub(v3(lp.x, lp.y, lp.z), P);
+        const float dist = sqrtf(dot(sd, sd));
+        RaySeg seg;
+        bool march = dist > 0.0f;
+        if (march) { sd = divs(sd, dist); march = clip_ray(G, P, sd, 0.0f, dist, seg); }
+        if (march) {                        // otherwise T = 1 and the RNG state is untouched
+          const uint32_t q = warp_append(&Q.counters[Q_SHADOW]);
+          Q.shadow[q] = s;
+          Q.shadow_ray[2 * q] = make_float4(seg.o[0], seg.o[1], seg.o[2], seg.t0);
+          Q.shadow_ray[2 * q + 1] = make_float4(seg.d[0], seg.d[1], seg.d[2], seg.t1);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 struct ShadowJob {
   Queues Q;
   uint32_t s;
@@ -224,7 +444,8 @@ struct ShadowJob {
 
 __global__ void __launch_bounds__(128) k_shadow(const GridDev G, Queues Q, int refill) {
   ShadowJob job{Q, 0u};
-  march_loop<1>(G, job, &Q.counters[Q_SHADOW_HEAD], Q.counters[Q_SHADOW], refill & 0xff, refill >> 8);
+  const uint32_t njobs = Q.counters[Q_SHADOW], nwarps = gridDim.x * (blockDim.x >> 5);
+  march_loop<1>(G, job, &Q.counters[Q_SHADOW_HEAD], njobs, refill & 0xff, (refill >> 8) & 0xff, lanes_for(njobs, nwarps, (uint32_t)(refill >> 16)));
 }
 
 __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, Planes prev, ResPlanes prevR,
@@ -455,8 +676,18 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
                     ResPlanes prevR, ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1,
                     int persistent_blocks, cudaEvent_t prev_halo_ready, const unsigned* const* peer_wait) {
   // tuning knobs of the persistent raymarch kernels: idle lanes that trigger a refill | cell visits per scheduling decision << 8
+  // | warps that a small launch is spread over (lanes_for) << 16
+  static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+  static const int target_warps = sms * (getenv("VRS_MIN_WARPS_PER_SM") ? atoi(getenv("VRS_MIN_WARPS_PER_SM")) : MIN_WARPS_PER_SM);
+  static const int ris_blocks = [] {   // one resident wave of the cooperative RIS kernel
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ris_coop, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    if (getenv("VRS_RIS_BLOCKS_PER_SM")) per_sm = atoi(getenv("VRS_RIS_BLOCKS_PER_SM"));
+    return sms * per_sm;
+  }();
   static const int refill = (getenv("VRS_REFILL") ? atoi(getenv("VRS_REFILL")) : REFILL_MIN_IDLE) |
-                            ((getenv("VRS_CELLS") ? atoi(getenv("VRS_CELLS")) : CELLS_PER_DECISION) << 8);
+                            ((getenv("VRS_CELLS") ? atoi(getenv("VRS_CELLS")) : CELLS_PER_DECISION) << 8) | (target_warps << 16);
+  static const bool ris_thread = getenv("VRS_RIS") && getenv("VRS_RIS")[0] == 't';
   cudaMemsetAsync(Q.counters, 0, 8 * sizeof(uint32_t), st);
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_classify<<<grid, block, 0, st>>>(G, dF, cur, Q, trace, y0, y1, store_y0);
@@ -467,7 +698,8 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   k_hit_compact<<<nblocks, 256, 0, st>>>(Q.flag, npix, Q.counters, Q.hit_pix);
   const bool vis = (F.flags & FLAG_VISIBILITY) != 0, temporal = (F.flags & FLAG_TEMPORAL) != 0;
   const int needs_finish = (vis || temporal) ? 1 : 0;
-  k_ris<<<persistent_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
+  if (ris_thread) k_ris_thread<<<persistent_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
+  else k_ris_coop<<<ris_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, target_warps);
   if (vis) k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill);
   // the previous frame's halo rows (multi-GPU) are only needed by the temporal merge: everything above overlapped their exchange
   if (needs_finish && prev_halo_ready) cudaStreamWaitEvent(st, prev_halo_ready, 0);
