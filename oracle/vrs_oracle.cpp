@@ -772,8 +772,12 @@ void orc_pass_spatial(const orc_scene* s, const orc_restir_uniforms* ru, uint32_
         GInfo gi = ginfo_from_images(cur, idx, ru->currCamPos);
         uint32_t Z = res.M;
         size_t nb_idx[MAX_NEIGHBORS]; uint32_t nb_M[MAX_NEIGHBORS]; int nacc = 0;
+        // the 2k offset draws come first, the selection draws of updateReservoir after them: a neighbour's position in
+        // the RNG stream then does not depend on the neighbours before it
+        float off[MAX_NEIGHBORS][2];
+        for (uint32_t i = 0; i < k; ++i) { off[i][0] = rnd(seed); off[i][1] = rnd(seed); }
         for (uint32_t i = 0; i < k; ++i) {
-          float r1 = rnd(seed), r2 = rnd(seed);
+          float r1 = off[i][0], r2 = off[i][1];
           float dx = (r1 * 2.0f - 1.0f) * radius, dy = (r2 * 2.0f - 1.0f) * radius;
           if (dx * dx + dy * dy > radius * radius) continue;
           int ox = int(dx), oy = int(dy);

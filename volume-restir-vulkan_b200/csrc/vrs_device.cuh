@@ -459,42 +459,41 @@ struct Ray {
     tau = neglog1m(rnd(seed));
   }
 
-  // leave the current cell along `axis` (branch-free over the axis); returns false when the ray is finished
-  __device__ __forceinline__ bool advance(const GridDev& G) {
-    t = tcell;
-    if (last) return false;
-    c[0] += axis == 0 ? (d[0] > 0.0f ? 1 : -1) : 0;
-    c[1] += axis == 1 ? (d[1] > 0.0f ? 1 : -1) : 0;
-    c[2] += axis == 2 ? (d[2] > 0.0f ? 1 : -1) : 0;
-    if ((unsigned)c[0] >= (unsigned)G.cdim[0] || (unsigned)c[1] >= (unsigned)G.cdim[1] || (unsigned)c[2] >= (unsigned)G.cdim[2]) return false;
-    tn[0] = axis == 0 ? tn[0] + dt[0] : tn[0];
-    tn[1] = axis == 1 ? tn[1] + dt[1] : tn[1];
-    tn[2] = axis == 2 ? tn[2] + dt[2] : tn[2];
-    return true;
-  }
-
-  // does the carried sample run out inside the current cell?  (else it is consumed and the cell is left)
-  __device__ __forceinline__ int consume(const GridDev& G) {
-    float seg = (tcell - t) * mu;
-    if (tau < seg) return RAY_COLLIDE;
-    tau = tau - seg;
-    return advance(G) ? RAY_SKIP : RAY_DONE;
-  }
-
-  __device__ __forceinline__ int cell_step(const GridDev& G) {
+  // The unit steps are split so that the scheduler (march_loop) runs ONE copy of the common tail for whichever kind
+  // of step the warp executes, and so that empty and non-empty cells take the same path (no divergence between them):
+  //   cell_head()    enter the current cell: exit time / axis, one directory load (majorant, 0 = empty)
+  //   collide()      the tentative collision where tau ran out: brick load, accept test / T update, fresh tau
+  //   tail()         does the carried sample run out before the cell's exit?  else consume it and step to the next cell
+  __device__ __forceinline__ void cell_head(const GridDev& G) {
     ncells += 1;
     axis = 0; tcell = tn[0];
     if (tn[1] < tcell) { tcell = tn[1]; axis = 1; }
     if (tn[2] < tcell) { tcell = tn[2]; axis = 2; }
     last = false;
     if (!(tcell < t1)) { tcell = t1; last = true; }
-    const int ci = (c[2] * G.cdim[1] + c[1]) * G.cdim[0] + c[0];
-    mu_d = __ldg(&G.dir_max[ci]);
-    if (mu_d > 0.0f) { cell = ci; mu = mu_d * G.density_scale; return consume(G); }
-    return advance(G) ? RAY_SKIP : RAY_DONE;
+    cell = (c[2] * G.cdim[1] + c[1]) * G.cdim[0] + c[0];
+    mu_d = __ldg(&G.dir_max[cell]);
+    mu = mu_d > 0.0f ? mu_d * G.density_scale : 0.0f;        // empty cell: seg = 0 below, tau is untouched (x - 0 = x)
   }
 
-  __device__ __forceinline__ int collide_step(const GridDev& G, uint32_t& seed) {
+  __device__ __forceinline__ int tail(const GridDev& G) {
+    const float seg = (tcell - t) * mu;
+    if (tau < seg) return RAY_COLLIDE;
+    tau = tau - seg;
+    t = tcell;                                               // leave the cell along `axis` (branch-free over the axis)
+    if (last) return RAY_DONE;
+    c[0] += axis == 0 ? (d[0] > 0.0f ? 1 : -1) : 0;
+    c[1] += axis == 1 ? (d[1] > 0.0f ? 1 : -1) : 0;
+    c[2] += axis == 2 ? (d[2] > 0.0f ? 1 : -1) : 0;
+    if ((unsigned)c[0] >= (unsigned)G.cdim[0] || (unsigned)c[1] >= (unsigned)G.cdim[1] || (unsigned)c[2] >= (unsigned)G.cdim[2]) return RAY_DONE;
+    tn[0] = axis == 0 ? tn[0] + dt[0] : tn[0];
+    tn[1] = axis == 1 ? tn[1] + dt[1] : tn[1];
+    tn[2] = axis == 2 ? tn[2] + dt[2] : tn[2];
+    return RAY_SKIP;
+  }
+
+  // false = the ray ended at this collision (primary: real collision found; shadow: opaque)
+  __device__ __forceinline__ bool collide(const GridDev& G, uint32_t& seed) {
     t = t + tau / mu;
     ntent += 1;
     int vlo0 = G.vmin[0] + c[0] * 8, vlo1 = G.vmin[1] + c[1] * 8, vlo2 = G.vmin[2] + c[2] * 8;
@@ -506,14 +505,17 @@ struct Ray {
     float dens = leaf < 0 ? mu_d : __ldg(&G.atlas[(size_t)leaf * 512 + (((vx & 7) << 6) | ((vy & 7) << 3) | (vz & 7))]);
     if (MODE == 0) {
       float u2 = rnd(seed);
-      if (u2 * mu_d < dens) { hit = true; vox[0] = vx; vox[1] = vy; vox[2] = vz; return RAY_DONE; }
+      if (u2 * mu_d < dens) { hit = true; vox[0] = vx; vox[1] = vy; vox[2] = vz; return false; }
     } else {
       T = T * (1.0f - dens / mu_d);
-      if (!(T > 1e-5f)) { T = 0.0f; return RAY_DONE; }      // opaque for every practical purpose: stop marching
+      if (!(T > 1e-5f)) { T = 0.0f; return false; }          // opaque for every practical purpose: stop marching
     }
     tau = neglog1m(rnd(seed));
-    return consume(G);
+    return true;
   }
+
+  __device__ __forceinline__ int cell_step(const GridDev& G) { cell_head(G); return tail(G); }
+  __device__ __forceinline__ int collide_step(const GridDev& G, uint32_t& seed) { return collide(G, seed) ? tail(G) : RAY_DONE; }
 };
 
 // Nested-loop form for one-ray-per-thread callers (k_shade's optional final visibility): runs a Ray to completion.
@@ -564,8 +566,8 @@ template <int MODE, class Job>
 __device__ __forceinline__ void march_loop(const GridDev& G, Job& job, uint32_t* head, uint32_t njobs, int refill_min_idle, int cells_per_decision,
                                            int lane_limit) {
   const unsigned full = 0xffffffffu;
-  const unsigned limit_mask = lane_limit >= 32 ? full : ((1u << lane_limit) - 1u);
-  const bool eligible = ((limit_mask >> (threadIdx.x & 31)) & 1u) != 0;
+  if (lane_limit > 32) lane_limit = 32;
+  const bool eligible = (int)(threadIdx.x & 31) < lane_limit;
   if (refill_min_idle > (lane_limit + 1) / 2) refill_min_idle = (lane_limit + 1) / 2;
   Ray<MODE> ray;
   int st = RAY_DONE;
@@ -573,21 +575,27 @@ __device__ __forceinline__ void march_loop(const GridDev& G, Job& job, uint32_t*
   bool queue_empty = false;
   for (;;) {
     const unsigned bs = __ballot_sync(full, st == RAY_SKIP), bc = __ballot_sync(full, st == RAY_COLLIDE);
-    const unsigned busy = bs | bc;
-    if (!queue_empty && (__popc(~busy & limit_mask) >= refill_min_idle || busy == 0)) {
+    const int nS = __popc(bs), nC = __popc(bc);
+    if (!queue_empty && (lane_limit - nS - nC >= refill_min_idle || (bs | bc) == 0)) {   // only lanes below the limit ever hold rays
       const bool want = st == RAY_DONE && eligible;
       const uint32_t j = warp_fetch(head, want);
       if (want && j < njobs) st = job.fetch(G, j, ray, seed) ? RAY_SKIP : RAY_DONE;
       queue_empty = __any_sync(full, want && j >= njobs);
       continue;
     }
-    if (busy == 0) break;
-    if (bc == 0 || __popc(bs) >= __popc(bc)) {
+    if ((bs | bc) == 0) break;
+    const bool cells = nS >= nC;
 #pragma unroll 1
-      for (int r = 0; r < cells_per_decision; ++r)   // a few cell visits per scheduling decision (they are cheap)
-        if (st == RAY_SKIP) { st = ray.cell_step(G); if (st == RAY_DONE) job.retire(G, ray, seed); }
-    } else {
-      if (st == RAY_COLLIDE) { st = ray.collide_step(G, seed); if (st == RAY_DONE) job.retire(G, ray, seed); }
+    for (int r = 0; r < cells_per_decision; ++r) {         // a few cell visits per scheduling decision (they are cheap)
+      bool run = false;
+      if (cells) {
+        if (st == RAY_SKIP) { ray.cell_head(G); run = true; }
+      } else if (st == RAY_COLLIDE) {
+        run = ray.collide(G, seed);
+        if (!run) { st = RAY_DONE; job.retire(G, ray, seed); }
+      }
+      if (run) { st = ray.tail(G); if (st == RAY_DONE) job.retire(G, ray, seed); }
+      if (!cells) break;
     }
   }
 }
@@ -597,6 +605,20 @@ __device__ __forceinline__ int lanes_for(uint32_t njobs, uint32_t nwarps, uint32
   if (target_warps == 0) return 32;
   uint32_t l = (njobs + target_warps - 1) / target_warps;
   return l < 4u ? 4 : (l > 32u ? 32 : (int)l);
+}
+// Pixels per group for the cooperative kernels, whose time per group is proportional to its size: small launches are
+// spread over `target_warps` warps (as lanes_for); large ones get equal groups, so that every warp of the resident grid
+// runs the same number of equally sized groups (no partial last round).
+__device__ __forceinline__ uint32_t group_size_for(uint32_t nitems, uint32_t nwarps, uint32_t target_warps, uint32_t max_group) {
+  if (target_warps > nwarps) target_warps = nwarps;
+  if (target_warps == 0 || nwarps == 0) return max_group;
+  uint32_t g = (nitems + target_warps - 1) / target_warps;
+  if (g > max_group) {
+    const uint32_t per_warp = (nitems + nwarps - 1) / nwarps;
+    const uint32_t rounds = (per_warp + max_group - 1) / max_group;
+    g = rounds ? (per_warp + rounds - 1) / rounds : max_group;
+  }
+  return g < 4u ? 4u : (g > max_group ? max_group : g);
 }
 
 __device__ __forceinline__ float ratio_track(const GridDev& G, V3 P, V3 L, uint32_t& seed) {

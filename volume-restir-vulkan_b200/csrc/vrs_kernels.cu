@@ -98,7 +98,7 @@ struct PrimaryJob {
   }
 };
 
-__global__ void __launch_bounds__(128) k_primary(const GridDev G, const FrameParams* __restrict__ Fp, Planes cur, Queues Q,
+__global__ void __launch_bounds__(128, 9) k_primary(const GridDev G, const FrameParams* __restrict__ Fp, Planes cur, Queues Q,
                                                  uint32_t* __restrict__ trace, int store_y0, int refill) {
   const FrameParams& F = *Fp;
   PrimaryJob job{F, cur, Q, trace, store_y0, 0u};
@@ -213,6 +213,100 @@ __global__ void __launch_bounds__(128) k_ris_thread(const GridDev G, const Light
 }
 
 
+// One thread per hit pixel, M-candidate loop with the light-table fetches software-pipelined two candidates ahead.
+__global__ void __launch_bounds__(128, 6) k_ris_prefetch(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
+                                             Queues Q, uint32_t* __restrict__ trace, int store_y0, int needs_finish) {
+  const FrameParams& F = *Fp;
+  const uint32_t nhit = Q.counters[Q_HIT];
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
+    const uint32_t idx = Q.hit_pix[s];
+    const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
+    const float4 scratch = cur.worldPos[idx];                                      // {t, voxel code, RNG state, 1} from k_primary
+    uint32_t seed = __float_as_uint(scratch.z);
+    V3 org, dir; primary_ray(F, x, y, org, dir);
+    const V3 P = add(org, muls(dir, scratch.x));
+    const uint32_t vcode = __float_as_uint(scratch.y);
+    const int i = (int)(vcode % (uint32_t)G.vdim[0]) + G.vmin[0];
+    const int j = (int)((vcode / (uint32_t)G.vdim[0]) % (uint32_t)G.vdim[1]) + G.vmin[1];
+    const int k = (int)(vcode / ((uint32_t)G.vdim[0] * (uint32_t)G.vdim[1])) + G.vmin[2];
+    const float dens = density_at(G, i, j, k);
+    V3 grad = v3(density_at(G, i + 1, j, k) - density_at(G, i - 1, j, k), density_at(G, i, j + 1, k) - density_at(G, i, j - 1, k),
+                 density_at(G, i, j, k + 1) - density_at(G, i, j, k - 1));
+    const float gg = dot(grad, grad);
+    V3 n;
+    if (gg > 0.0f) { float l = sqrtf(gg); n = v3(-grad.x / l, -grad.y / l, -grad.z / l); }
+    else n = v3(-dir.x, -dir.y, -dir.z);
+    const float4 al = voxel_albedo(dens);
+    cur.worldPos[idx] = make_float4(P.x, P.y, P.z, 1.0f); cur.albedo[idx] = al;                        // :193-197
+    cur.normal[idx] = make_float4(n.x, n.y, n.z, 1.0f); cur.mat[idx] = make_float4(G.roughness, G.metallic, 1.0f, 1.0f);
+    GInfo gi;
+    gi.albedo[0] = al.x; gi.albedo[1] = al.y; gi.albedo[2] = al.z; gi.albedo[3] = al.w;
+    gi.normal = n; gi.worldPos = P; gi.metallic = G.metallic; gi.roughness = G.roughness;
+    gi.albedoLum = luminance_common(al.x, al.y, al.z);                                                 // :182
+    gi.camPos = v3(F.camPos[0], F.camPos[1], F.camPos[2]);                                             // :183
+    gi.sampleSeed = 0;
+    Res res = newReservoir();
+    if (dot(gi.normal, gi.normal) != 0.0f) {                                                           // :205
+      const ShadePre pre = shade_pre(gi);
+      // The draws of candidate c are draws 3c+1..3c+3 of the pixel's LCG stream whatever the data, so a second RNG state
+      // runs ahead of the loop: the alias cell of candidate c+2 and the light of candidate c+1 are requested while
+      // candidate c is evaluated, which takes the two dependent L2 fetches (restir.rgen:97-134) off the critical path.
+      uint32_t sP = seed;
+      uint32_t selA, colB; float pdfA, lewA, r2B; float4 lpA, cellB;
+      {
+        const float r1 = rnd(sP), r2 = rnd(sP); lcg(sP);
+        aliasTableSample(L, r1, r2, selA, pdfA);
+        lpA = __ldg(&L.lights[2 * selA]); lewA = __ldg(reinterpret_cast<const float*>(L.lights) + 8 * (size_t)selA + 7);
+        const float q1 = rnd(sP); r2B = rnd(sP); lcg(sP);
+        colB = aliasColumn(L, q1); cellB = __ldg(&L.alias[colB]);
+      }
+      uint32_t selM = 0u; float selSumW = 0.0f;
+      const uint32_t M = F.M;
+      for (uint32_t c = 0; c < M; ++c) {                                                               // :206-226
+        uint32_t selN; float pdfN;
+        aliasPick(cellB, colB, r2B, selN, pdfN);                                                       // candidate c+1: light request
+        const float4 lpN = __ldg(&L.lights[2 * selN]);
+        const float lewN = __ldg(reinterpret_cast<const float*>(L.lights) + 8 * (size_t)selN + 7);
+        { const float q1 = rnd(sP); r2B = rnd(sP); lcg(sP); colB = aliasColumn(L, q1); cellB = __ldg(&L.alias[colB]); }   // candidate c+2: alias request
+        const uint32_t sampleSeed = seed;                                                              // :213
+        lcg(seed); lcg(seed);                                                                          // r1, r2 were drawn by the look-ahead state
+        const float pHat = evaluatePHatLight(v3(lpA.x, lpA.y, lpA.z), lewA, gi, pre);                  // reservoir.glsl:45-54
+        const float weight = pHat / pdfA;
+        res.M += 1;
+        res.sumWeights += weight;                                                                      // reservoir.glsl:30-43
+        const float replacePossibility = weight / res.sumWeights;
+        if (rnd(seed) < replacePossibility) {
+          res.lightIndex = selA; res.lightKind = 0; res.pHat = pHat; res.sampleSeed = sampleSeed;
+          selM = res.M; selSumW = res.sumWeights;                                                      // w = (sumW + weight) / (M * pHat), formed once below
+        }
+        selA = selN; pdfA = pdfN; lpA = lpN; lewA = lewN;
+      }
+      if (selM != 0u) res.w = selSumW / (float(selM) * res.pHat);                                      // reservoir.glsl:51
+    }
+    if ((F.flags & FLAG_FINALIZE_W) != 0 && res.w > 0.0f) res.w = res.sumWeights / (float(res.M) * res.pHat);
+    float4 a, b; packReservoir(res, a, b);
+    outR.info[idx] = a; outR.weight[idx] = b;
+    Q.hit_seed[s] = seed; Q.hit_T[s] = 1.0f;
+    if (trace) { trace[(size_t)idx * 4 + 0] = vcode; if (!needs_finish) trace[(size_t)idx * 4 + 3] = seed; }
+    if ((F.flags & FLAG_VISIBILITY) != 0 && res.w > 0.0f) {                                              // shadow ray of ratio_track()
+      const float4 lp = __ldg(&L.lights[2 * res.lightIndex]);
+      V3 sd = sub(v3(lp.x, lp.y, lp.z), P);
+      const float dist = sqrtf(dot(sd, sd));
+      RaySeg seg;
+      bool march = dist > 0.0f;
+      if (march) { sd = divs(sd, dist); march = clip_ray(G, P, sd, 0.0f, dist, seg); }
+      if (march) {                        // otherwise T = 1 and the RNG state is untouched
+        const uint32_t q = warp_append(&Q.counters[Q_SHADOW]);
+        Q.shadow[q] = s;
+        Q.shadow_ray[2 * q] = make_float4(seg.o[0], seg.o[1], seg.o[2], seg.t0);
+        Q.shadow_ray[2 * q + 1] = make_float4(seg.d[0], seg.d[1], seg.d[2], seg.t1);
+      }
+    }
+  }
+}
+
+
+
 // ---- A3, cooperative form.  The candidates of restir.rgen:206-226 are independent except for the running sum of the
 // streaming reservoir, so a warp takes a group of up to 32 hit pixels and turns the work 90 degrees twice:
 //   step 1  lane = pixel      gradient normal, G-buffer stores, per-pixel shading terms -> shared memory
@@ -242,7 +336,7 @@ __global__ void __launch_bounds__(128, 6) k_ris_coop(const GridDev G, const Ligh
   const unsigned lt_mask = (1u << lane) - 1u;
   const uint32_t nhit = Q.counters[Q_HIT];
   const uint32_t nwarps = gridDim.x * 4u, warp = blockIdx.x * 4u + (threadIdx.x >> 5);
-  const uint32_t gsz = (uint32_t)lanes_for(nhit, nwarps, (uint32_t)target_warps);
+  const uint32_t gsz = group_size_for(nhit, nwarps, (uint32_t)target_warps, 32u);
   const uint32_t M = F.M;
   // LCG jump by 3 * lane draws: state' = jA * state + jC
   uint32_t jA = 1u, jC = 0u;
@@ -442,7 +536,7 @@ struct ShadowJob {
   __device__ __forceinline__ void retire(const GridDev&, const Ray<1>& ray, uint32_t seed) { Q.hit_T[s] = ray.T; Q.hit_seed[s] = seed; }
 };
 
-__global__ void __launch_bounds__(128) k_shadow(const GridDev G, Queues Q, int refill) {
+__global__ void __launch_bounds__(128, 9) k_shadow(const GridDev G, Queues Q, int refill) {
   ShadowJob job{Q, 0u};
   const uint32_t njobs = Q.counters[Q_SHADOW], nwarps = gridDim.x * (blockDim.x >> 5);
   march_loop<1>(G, job, &Q.counters[Q_SHADOW_HEAD], njobs, refill & 0xff, (refill >> 8) & 0xff, lanes_for(njobs, nwarps, (uint32_t)(refill >> 16)));
@@ -501,7 +595,8 @@ __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FramePa
 // (reservoir.glsl:56-76), normalisation deferred to the finally selected sample.  One thread per hit pixel (the
 // `exist < 0.5` early-out of :76-79 is the hit list); neighbour G-buffer / reservoir reads are gathers through L2.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_spatial(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes inR, ResPlanes outR,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_spatial_thread(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes inR, ResPlanes outR,
                                                  Queues Q, uint32_t iteration, int store_y0, int store_y1) {
   const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
@@ -516,24 +611,26 @@ __global__ void __launch_bounds__(128) k_spatial(const LightsDev L, const FrameP
     uint32_t k = F.spatialNeighbors; if (k > (uint32_t)MAX_NEIGHBORS) k = MAX_NEIGHBORS;
     uint32_t nb_idx[MAX_NEIGHBORS]; uint32_t nb_M[MAX_NEIGHBORS]; int nacc = 0;
     const ShadePre pre = shade_pre(gi);
+    uint32_t sO = seed;                                                           // the 2k offset draws come first:
+    for (uint32_t i = 0; i < 2u * k; ++i) lcg(seed);                              // `seed` continues behind them with the selection draws
     for (uint32_t i = 0; i < k; ++i) {
-      float r1 = rnd(seed), r2 = rnd(seed);
+      float r1 = rnd(sO), r2 = rnd(sO);
       float dx = (r1 * 2.0f - 1.0f) * radius, dy = (r2 * 2.0f - 1.0f) * radius;
-      if (dx * dx + dy * dy > radius * radius) continue;
       int ox = int(dx), oy = int(dy);
-      if (ox == 0 && oy == 0) continue;
       int nx = x + ox, ny = y + oy;
-      if (nx < 0 || ny < 0 || nx >= (int)F.W || ny >= (int)F.H) continue;
-      if (ny < store_y0 || ny >= store_y1) continue;                             // outside the rows held (halo too small)
-      size_t nidx = (size_t)(ny - store_y0) * F.W + (size_t)nx;
-      if (cur.worldPos[nidx].w < 0.5f) continue;
-      GInfo ng = ginfo_from_planes(cur, nidx, F.camPos);
-      V3 pd = sub(gi.worldPos, ng.worldPos);
+      const bool inside = !(dx * dx + dy * dy > radius * radius) && !(ox == 0 && oy == 0) && nx >= 0 && ny >= 0 && nx < (int)F.W && ny < (int)F.H &&
+                          ny >= store_y0 && ny < store_y1;                          // (rows outside the ones held: halo too small)
+      // all planes of the neighbour are requested at once (from this pixel's own slot when the offset is rejected outright)
+      size_t nidx = inside ? (size_t)(ny - store_y0) * F.W + (size_t)nx : (size_t)idx;
+      const float4 nwp = cur.worldPos[nidx], na = cur.albedo[nidx], nn = cur.normal[nidx], ri = inR.info[nidx], rw = inR.weight[nidx];
+      if (!inside) continue;
+      if (nwp.w < 0.5f) continue;
+      V3 pd = sub(gi.worldPos, v3(nwp.x, nwp.y, nwp.z));
       if (!(dot(pd, pd) < 0.01f)) continue;
-      V3 ad = v3(gi.albedo[0] - ng.albedo[0], gi.albedo[1] - ng.albedo[1], gi.albedo[2] - ng.albedo[2]);
+      V3 ad = v3(gi.albedo[0] - na.x, gi.albedo[1] - na.y, gi.albedo[2] - na.z);
       if (!(dot(ad, ad) < 0.01f)) continue;
-      if (!(dot(gi.normal, ng.normal) > 0.5f)) continue;
-      Res nr = unpackReservoir(inR.info[nidx], inR.weight[nidx]);
+      if (!(dot(gi.normal, v3(nn.x, nn.y, nn.z)) > 0.5f)) continue;
+      Res nr = unpackReservoir(ri, rw);
       res.M += nr.M;                                                             // reservoir.glsl:61-68
       float pHat = evaluatePHat(L, nr.lightIndex, gi, pre);
       float weight = pHat * nr.w * float(nr.M);
@@ -550,6 +647,182 @@ __global__ void __launch_bounds__(128) k_spatial(const LightsDev L, const FrameP
     }
     float4 a, b; packReservoir(res, a, b);
     outR.info[idx] = a; outR.weight[idx] = b;
+  }
+}
+
+
+// ---- Spatial reuse, cooperative form.  Which neighbours a pixel merges, and what each contributes, is independent per
+// (pixel, neighbour) pair once the offset draws come first; only the running sum of updateReservoir is serial.  A warp
+// takes a group of hit pixels and works on PAIRS, so that rejected neighbours (outside the disk, missed, dissimilar)
+// cost no lane time in the expensive parts:
+//   step 1  lane = pixel  own reservoir + G-buffer, per-pixel shading terms -> shared memory
+//   phase A lane = pair   offset, bounds, neighbour gathers, similarity tests; accepted pairs -> work list
+//   phase B lane = accepted pair   pHat of the neighbour's light at this pixel (reservoir.glsl:62-63)
+//   step 3  lane = pixel  M and sumWeights accumulation, selection draws, in neighbour order (reservoir.glsl:61-68)
+//   phase C lane = accepted pair   pHat of the finally selected light at the neighbour's geometry (reservoir.glsl:70-73)
+//   final   lane = pixel  Z, w (reservoir.glsl:74-75), store
+static constexpr int SP_PAIRS = 288;       // >= group size * (k | 1)
+struct SpSmem {
+  float P[3][32], n[3][32], alb[3][32], albedoLum[32], rough[32], metal[32], wo[3][32], fresnelOut[32], smithOut[32], a[32];
+  uint32_t seed0[32], finalLight[32];
+  int px[32], py[32];
+  uint32_t nidx[SP_PAIRS], nM[SP_PAIRS], nLight[SP_PAIRS];   // per pair: neighbour pixel (~0 = rejected), its M, its light
+  float nW[SP_PAIRS], nPHat[SP_PAIRS];                       // its w (phase B turns it into the merge weight), pHat at this pixel
+  uint16_t list[SP_PAIRS];                                   // accepted pairs: pair | pixel << 9
+};
+
+__global__ void __launch_bounds__(128, 6) k_spatial_coop(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes inR, ResPlanes outR,
+                                                         Queues Q, uint32_t iteration, int store_y0, int store_y1, int target_warps) {
+  __shared__ SpSmem sm_all[4];
+  __shared__ uint32_t jmpA[32], jmpC[32];                    // LCG advanced by 2 * i draws
+  SpSmem& sm = sm_all[threadIdx.x >> 5];
+  const FrameParams& F = *Fp;
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  if (threadIdx.x < 32) {
+    uint32_t A = 1u, C = 0u;
+    for (uint32_t i = 0; i < 2u * threadIdx.x; ++i) { A = A * 1664525u; C = C * 1664525u + 1013904223u; }
+    jmpA[threadIdx.x] = A; jmpC[threadIdx.x] = C;
+  }
+  __syncthreads();
+  const uint32_t nhit = Q.counters[Q_HIT];
+  const uint32_t nwarps = gridDim.x * 4u, warp = blockIdx.x * 4u + (threadIdx.x >> 5);
+  uint32_t k = F.spatialNeighbors; if (k > (uint32_t)MAX_NEIGHBORS) k = MAX_NEIGHBORS;
+  const uint32_t kp = k | 1u;                                // odd pair stride: lane = pixel reads are bank-conflict free
+  const uint32_t gmax = (uint32_t)SP_PAIRS / kp < 32u ? (uint32_t)SP_PAIRS / kp : 32u;
+  const uint32_t gsz = group_size_for(nhit, nwarps, (uint32_t)target_warps, gmax);
+  const float radius = F.spatialRadius;
+
+  for (uint32_t g0 = warp * gsz; g0 < nhit; g0 += nwarps * gsz) {
+    const uint32_t npix = nhit - g0 < gsz ? nhit - g0 : gsz;
+    const bool pix = (uint32_t)lane < npix;
+    // ---------------- step 1: lane = pixel
+    uint32_t idx = 0, seed = 0;
+    Res res = newReservoir();
+    if (pix) {
+      idx = Q.hit_pix[g0 + (uint32_t)lane];
+      const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
+      seed = pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_SPATIAL0 + iteration);             // :58-59
+      res = unpackReservoir(inR.info[idx], inR.weight[idx]);
+      const GInfo gi = ginfo_from_planes(cur, idx, F.camPos);
+      const ShadePre pre = shade_pre(gi);
+      sm.P[0][lane] = gi.worldPos.x; sm.P[1][lane] = gi.worldPos.y; sm.P[2][lane] = gi.worldPos.z;
+      sm.n[0][lane] = gi.normal.x; sm.n[1][lane] = gi.normal.y; sm.n[2][lane] = gi.normal.z;
+      sm.alb[0][lane] = gi.albedo[0]; sm.alb[1][lane] = gi.albedo[1]; sm.alb[2][lane] = gi.albedo[2];
+      sm.albedoLum[lane] = gi.albedoLum; sm.rough[lane] = gi.roughness; sm.metal[lane] = gi.metallic;
+      sm.wo[0][lane] = pre.wo.x; sm.wo[1][lane] = pre.wo.y; sm.wo[2][lane] = pre.wo.z;
+      sm.fresnelOut[lane] = pre.fresnelOut; sm.smithOut[lane] = pre.smithOut; sm.a[lane] = pre.a;
+      sm.seed0[lane] = seed; sm.px[lane] = x; sm.py[lane] = y;
+    }
+    __syncwarp();
+    // ---------------- phase A: lane = (pixel, neighbour) pair
+    const uint32_t npairs = npix * k;
+    uint32_t nlist = 0u;
+    for (uint32_t q0 = 0; q0 < npairs; q0 += 32u) {
+      const uint32_t q = q0 + (uint32_t)lane;
+      bool acc = false;
+      uint32_t pair = 0u, p = 0u;
+      if (q < npairs) {
+        p = q / k;
+        const uint32_t i = q - p * k;
+        pair = p * kp + i;
+        uint32_t so = jmpA[i] * sm.seed0[p] + jmpC[i];
+        const float r1 = rnd(so), r2 = rnd(so);
+        const float dx = (r1 * 2.0f - 1.0f) * radius, dy = (r2 * 2.0f - 1.0f) * radius;
+        // Every plane the tests and the merge may need is requested at once, from this pixel's own (cached) slot when the
+        // offset is rejected outright: one L2 round trip per pair instead of three dependent ones.
+        const int ox = int(dx), oy = int(dy);
+        const int nx = sm.px[p] + ox, ny = sm.py[p] + oy;
+        const bool inside = !(dx * dx + dy * dy > radius * radius) && !(ox == 0 && oy == 0) && nx >= 0 && ny >= 0 && nx < (int)F.W && ny < (int)F.H &&
+                            ny >= store_y0 && ny < store_y1;
+        const size_t ni = inside ? (size_t)(ny - store_y0) * F.W + (size_t)nx : (size_t)(sm.py[p] - store_y0) * F.W + (size_t)sm.px[p];
+        const float4 nwp = cur.worldPos[ni], na = cur.albedo[ni], nn = cur.normal[ni], ri = inR.info[ni], rw = inR.weight[ni];
+        uint32_t nidx = 0xFFFFFFFFu;
+        if (inside && !(nwp.w < 0.5f)) {
+          const V3 pd = sub(v3(sm.P[0][p], sm.P[1][p], sm.P[2][p]), v3(nwp.x, nwp.y, nwp.z));
+          const V3 ad = v3(sm.alb[0][p] - na.x, sm.alb[1][p] - na.y, sm.alb[2][p] - na.z);
+          if (dot(pd, pd) < 0.01f && dot(ad, ad) < 0.01f && dot(v3(sm.n[0][p], sm.n[1][p], sm.n[2][p]), v3(nn.x, nn.y, nn.z)) > 0.5f) {
+            const Res nr = unpackReservoir(ri, rw);
+            nidx = (uint32_t)ni;
+            sm.nM[pair] = nr.M; sm.nLight[pair] = nr.lightIndex; sm.nW[pair] = nr.w;
+            acc = true;
+          }
+        }
+        sm.nidx[pair] = nidx;
+      }
+      const unsigned m = __ballot_sync(full, acc);
+      if (acc) sm.list[nlist + (uint32_t)__popc(m & lt_mask)] = (uint16_t)(pair | (p << 9));
+      nlist += (uint32_t)__popc(m);
+    }
+    __syncwarp();
+    // ---------------- phase B: lane = accepted pair, pHat of the neighbour's sample at this pixel
+    for (uint32_t e0 = 0; e0 < nlist; e0 += 32u) {
+      const uint32_t e = e0 + (uint32_t)lane;
+      if (e < nlist) {
+        const uint32_t pr = sm.list[e], pair = pr & 0x1FFu, p = pr >> 9;
+        GInfo g;
+        g.worldPos = v3(sm.P[0][p], sm.P[1][p], sm.P[2][p]); g.normal = v3(sm.n[0][p], sm.n[1][p], sm.n[2][p]);
+        g.albedoLum = sm.albedoLum[p]; g.roughness = sm.rough[p]; g.metallic = sm.metal[p];
+        ShadePre pre;
+        pre.wo = v3(sm.wo[0][p], sm.wo[1][p], sm.wo[2][p]); pre.fresnelOut = sm.fresnelOut[p]; pre.smithOut = sm.smithOut[p];
+        pre.a = sm.a[p]; pre.cosOut = 0.0f;
+        const float pHat = evaluatePHat(L, sm.nLight[pair], g, pre);
+        sm.nPHat[pair] = pHat;
+        sm.nW[pair] = pHat * sm.nW[pair] * float(sm.nM[pair]);                                         // reservoir.glsl:63
+      }
+    }
+    __syncwarp();
+    // ---------------- step 3: lane = pixel, reservoir.glsl:61-68 in neighbour order
+    uint32_t Z = res.M;
+    int nacc = 0;
+    uint32_t selPair = 0xFFFFFFFFu;
+    if (pix) {
+      for (uint32_t i = 0; i < 2u * k; ++i) lcg(seed);                                                 // behind the offset draws
+      for (uint32_t i = 0; i < k; ++i) {
+        const uint32_t pair = (uint32_t)lane * kp + i;
+        if (sm.nidx[pair] == 0xFFFFFFFFu) continue;
+        ++nacc;
+        res.M += sm.nM[pair];
+        const float weight = sm.nW[pair];
+        if (weight > 0.0f) {
+          res.sumWeights += weight;
+          const float replacePossibility = weight / res.sumWeights;
+          if (rnd(seed) < replacePossibility) selPair = pair;
+        }
+      }
+      if (selPair != 0xFFFFFFFFu) {
+        const uint32_t ni = sm.nidx[selPair];
+        const Res nr = unpackReservoir(inR.info[ni], inR.weight[ni]);
+        res.lightIndex = nr.lightIndex; res.lightKind = nr.lightKind; res.pHat = sm.nPHat[selPair]; res.w = nr.w; res.sampleSeed = nr.sampleSeed;
+      }
+      sm.finalLight[lane] = res.lightIndex;
+    }
+    __syncwarp();
+    // ---------------- phase C: lane = accepted pair, the selected light seen from the neighbour (reservoir.glsl:70-73)
+    for (uint32_t e0 = 0; e0 < nlist; e0 += 32u) {
+      const uint32_t e = e0 + (uint32_t)lane;
+      if (e < nlist) {
+        const uint32_t pr = sm.list[e], pair = pr & 0x1FFu, p = pr >> 9;
+        const GInfo ng = ginfo_from_planes(cur, sm.nidx[pair], F.camPos);
+        const float pHat = evaluatePHat(L, sm.finalLight[p], ng);
+        if (!(pHat > 0.0f)) sm.nM[pair] = 0u;
+      }
+    }
+    __syncwarp();
+    // ---------------- final: lane = pixel
+    if (pix) {
+      if (nacc > 0) {
+        for (uint32_t i = 0; i < k; ++i) {
+          const uint32_t pair = (uint32_t)lane * kp + i;
+          if (sm.nidx[pair] != 0xFFFFFFFFu) Z += sm.nM[pair];
+        }
+        if (res.w > 0.0f) res.w = res.sumWeights / (float(Z) * res.pHat);                              // :74-75
+      }
+      float4 a, b; packReservoir(res, a, b);
+      outR.info[idx] = a; outR.weight[idx] = b;
+    }
+    __syncwarp();
   }
 }
 
@@ -669,6 +942,17 @@ __global__ void k_sample_density(const GridDev G, const int* __restrict__ ijk, u
   if (i < n) out[i] = density_at(G, ijk[3 * i], ijk[3 * i + 1], ijk[3 * i + 2]);
 }
 
+// Grid of a grid-stride kernel: exactly one resident wave (a second, partial wave of blocks would run at reduced occupancy
+// for as long as the first).  VRS_WAVE_SCALE multiplies it (for measurements).
+template <class K>
+static int resident_grid(K kernel, int block_threads, int fallback_per_sm) {
+  int d = 0, sms = 148, per_sm = 0;
+  cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block_threads, 0) != cudaSuccess || per_sm < 1) per_sm = fallback_per_sm;
+  const int scale = getenv("VRS_WAVE_SCALE") ? atoi(getenv("VRS_WAVE_SCALE")) : 1;
+  return sms * per_sm * (scale > 0 ? scale : 1);
+}
+
 // ------------------------------------------------------------------------------------------------- launchers
 // `F` is the host copy (launch geometry, which kernels run); `dF` is the same struct in device memory, read by the
 // kernels — so that a captured CUDA graph of the frame stays valid while the per-frame values change.
@@ -687,7 +971,7 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   }();
   static const int refill = (getenv("VRS_REFILL") ? atoi(getenv("VRS_REFILL")) : REFILL_MIN_IDLE) |
                             ((getenv("VRS_CELLS") ? atoi(getenv("VRS_CELLS")) : CELLS_PER_DECISION) << 8) | (target_warps << 16);
-  static const bool ris_thread = getenv("VRS_RIS") && getenv("VRS_RIS")[0] == 't';
+  static const char ris_kind = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'p';   // t(hread) | p(refetch) | c(oop)
   cudaMemsetAsync(Q.counters, 0, 8 * sizeof(uint32_t), st);
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_classify<<<grid, block, 0, st>>>(G, dF, cur, Q, trace, y0, y1, store_y0);
@@ -698,13 +982,17 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   k_hit_compact<<<nblocks, 256, 0, st>>>(Q.flag, npix, Q.counters, Q.hit_pix);
   const bool vis = (F.flags & FLAG_VISIBILITY) != 0, temporal = (F.flags & FLAG_TEMPORAL) != 0;
   const int needs_finish = (vis || temporal) ? 1 : 0;
-  if (ris_thread) k_ris_thread<<<persistent_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
+  static const bool one_wave = !getenv("VRS_NO_ONE_WAVE");
+  static const int g_thread = one_wave ? resident_grid(k_ris_thread, 128, 8) : persistent_blocks, g_prefetch = one_wave ? resident_grid(k_ris_prefetch, 128, 6) : persistent_blocks;
+  static const int g_finish = one_wave ? resident_grid(k_finish, 128, 8) : persistent_blocks;
+  if (ris_kind == 't') k_ris_thread<<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
+  else if (ris_kind == 'p') k_ris_prefetch<<<g_prefetch, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
   else k_ris_coop<<<ris_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, target_warps);
   if (vis) k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill);
   // the previous frame's halo rows (multi-GPU) are only needed by the temporal merge: everything above overlapped their exchange
   if (needs_finish && prev_halo_ready) cudaStreamWaitEvent(st, prev_halo_ready, 0);
   if (needs_finish && peer_wait) k_halo_wait<<<1, 1, 0, st>>>(peer_wait[0], peer_wait[1], peer_wait[2], const_cast<unsigned*>(peer_wait[3]));
-  if (needs_finish) k_finish<<<persistent_blocks, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1);
+  if (needs_finish) k_finish<<<g_finish, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1);
 }
 int initial_pass_launches(int flags) {
   const bool vis = (flags & FLAG_VISIBILITY) != 0, temporal = (flags & FLAG_TEMPORAL) != 0;
@@ -712,7 +1000,20 @@ int initial_pass_launches(int flags) {
 }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, int store_y0, int store_y1, int persistent_blocks) {
-  k_spatial<<<persistent_blocks, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1);
+  static const bool thread_form = !(getenv("VRS_SPATIAL") && getenv("VRS_SPATIAL")[0] == 'c');
+  static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+  static const int target_warps = sms * (getenv("VRS_MIN_WARPS_PER_SM") ? atoi(getenv("VRS_MIN_WARPS_PER_SM")) : MIN_WARPS_PER_SM);
+  static const int coop_blocks = [] {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spatial_coop, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    return sms * per_sm;
+  }();
+  static const int minb = getenv("VRS_SPATIAL_MINB") ? atoi(getenv("VRS_SPATIAL_MINB")) : 8;
+  static const bool one_wave = !getenv("VRS_NO_ONE_WAVE");
+  static const int g8 = one_wave ? resident_grid(k_spatial_thread<8>, 128, 8) : persistent_blocks, g7 = one_wave ? resident_grid(k_spatial_thread<7>, 128, 7) : persistent_blocks;
+  if (thread_form && minb >= 8) k_spatial_thread<8><<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1);
+  else if (thread_form) k_spatial_thread<7><<<g7, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1);
+  else k_spatial_coop<<<coop_blocks, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, target_warps);
 }
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, ResPlanes rs,
                   float4* accum, int y0, int y1, int store_y0) {
