@@ -8,30 +8,30 @@ import common
 pytestmark = pytest.mark.gpu
 
 
-def run_frames(V, O, name, W, H, n_lights, flags, frames, M=32, k=5, iterations=2, orbit_step=6.0, white=False):
-    R, OR, ctr, diag = common.setup_pair(V, O, name, W, H, n_lights, white=white, iterations=iterations)
+def run_frames(V, O, name, W, H, n_lights, flags, frames, M=32, k=5, iterations=2, orbit_step=6.0, white=False, trace=True, eye=1.6):
+    R, OR, ctr, diag = common.setup_pair(V, O, name, W, H, n_lights, white=white, iterations=iterations, trace=trace)
     R.m_restirUniforms.initialLightSampleCount = M
     R.m_restirUniforms.spatialNeighbors = k
     R.m_restirUniforms.flags = flags
-    R.CameraManip.setLookat(common.orbit_eye(ctr, 1.6 * diag, 0.2 * diag, 30.0), ctr)
+    R.CameraManip.setLookat(common.orbit_eye(ctr, eye * diag, 0.2 * diag, 30.0), ctr)
     R.createRestirUniformBuffer()
     out = []
     for f in range(frames):
-        R.CameraManip.setLookat(common.orbit_eye(ctr, 1.6 * diag, 0.2 * diag, 30.0 + orbit_step * f), ctr)
+        R.CameraManip.setLookat(common.orbit_eye(ctr, eye * diag, 0.2 * diag, 30.0 + orbit_step * f), ctr)
         R.renderFrame(clock=f)
         gu, ru, pc = common.oracle_uniforms(O, R)
         pc.initialize = R._last_initialize      # main.cpp:441-443 flips it after the submit; replay the value this frame used
         img_o = OR.render(gu, ru, pc, f).copy()
         img_p = R.readFrame()
         out.append((img_p, img_o, R.readGBuffer(), {k2: v.copy() for k2, v in OR.gbuffer().items()}, R.readReservoirs(),
-                    {k2: v.copy() for k2, v in OR.reservoirs().items()}, R.readTrace(), OR.f.trace.copy()))
+                    {k2: v.copy() for k2, v in OR.reservoirs().items()}, R.readTrace() if trace else None, OR.f.trace.copy()))
     R.destroy()
     return out
 
 
 def check(frames, exact_images=True):
     for i, (img_p, img_o, g_p, g_o, r_p, r_o, t_p, t_o) in enumerate(frames):
-        assert (t_p == t_o).all(), "frame %d: trace (voxel code / collisions / cells / final RNG state) differs at %d px" % (i, (t_p != t_o).any(-1).sum())
+        assert t_p is None or (t_p == t_o).all(), "frame %d: trace (voxel code / collisions / cells / final RNG state) differs at %d px" % (i, (t_p != t_o).any(-1).sum())
         for plane in ("worldPos", "albedo", "normal", "matProps"):
             assert (common.u32(g_p[plane]) == common.u32(g_o[plane])).all(), "frame %d: G-buffer %s differs" % (i, plane)
         assert (common.u32(r_p["info"]) == common.u32(r_o["info"])).all(), "frame %d: reservoir M/lightIndex/kind/seed differ" % i
@@ -90,3 +90,11 @@ def test_device_grid_lookup_matches_host_and_oracle(V, O):
     exp[inside] = dens[loc[inside, 2], loc[inside, 1], loc[inside, 0]]
     assert (got.view(np.uint32) == exp.view(np.uint32)).all()
     R.destroy()
+
+
+@pytest.mark.parametrize("name,eye", [("smoke", 1.6), ("smoke", 3.0), ("smoke", 0.45), ("cube", 1.2)])
+def test_coverage_culling_changes_nothing(V, O, name, eye):
+    """Without the trace buffer the product culls primary rays whose 8x8-pixel tile no occupied cell projects into
+    (k_cover); every pixel, reservoir and the image must still equal the oracle's, which marches every ray."""
+    flags = V.VISIBILITY_REUSE_FLAG | V.TEMPORAL_REUSE_FLAG | V.SPATIAL_REUSE_FLAG
+    check(run_frames(V, O, name, 331, 187, 16, flags, 4, M=8, k=3, iterations=1, orbit_step=17.0, trace=False, eye=eye))

@@ -4,6 +4,7 @@
 // and the call order of src/main.cpp:405-448.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -130,7 +131,7 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
     if (!alloc((void**)&Q.counters, 64) || !alloc((void**)&Q.cand, ctx->npix * 4) || !alloc((void**)&Q.cand_ray, ctx->npix * 32) ||
         !alloc((void**)&Q.flag, ctx->npix + 16) || !alloc((void**)&Q.block_count, ncompact * 4) || !alloc((void**)&Q.hit_pix, ctx->npix * 4) ||
         !alloc((void**)&Q.hit_seed, ctx->npix * 4) || !alloc((void**)&Q.hit_T, ctx->npix * 4) || !alloc((void**)&Q.shadow, ctx->npix * 4) ||
-        !alloc((void**)&Q.shadow_ray, ctx->npix * 32))
+        !alloc((void**)&Q.shadow_ray, ctx->npix * 32) || !alloc((void**)&Q.cover, ((size_t)(ctx->W + 7) / 8) * ((size_t)(ctx->H + 7) / 8) + 16))
       return bail(VRS_ERR_CUDA);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) ctx->persistent_blocks = prop.multiProcessorCount * (getenv("VRS_BLOCKS_PER_SM") ? atoi(getenv("VRS_BLOCKS_PER_SM")) : 12);
@@ -180,7 +181,7 @@ void vrs_destroy(vrs_ctx* ctx) {
   {
     Queues& Q = ctx->queues;
     cudaFree(Q.counters); cudaFree(Q.cand); cudaFree(Q.cand_ray); cudaFree(Q.flag); cudaFree(Q.block_count); cudaFree(Q.hit_pix);
-    cudaFree(Q.hit_seed); cudaFree(Q.hit_T); cudaFree(Q.shadow); cudaFree(Q.shadow_ray);
+    cudaFree(Q.hit_seed); cudaFree(Q.hit_T); cudaFree(Q.shadow); cudaFree(Q.shadow_ray); cudaFree(Q.cover);
   }
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -439,6 +440,23 @@ vrs_status vrs_get_alias_table(const vrs_ctx* ctx, vrs_alias_table_cell* out, ui
 static Planes planes_of(vrs_ctx* ctx, int i) { Planes p; p.worldPos = ctx->g_planes[i][0]; p.albedo = ctx->g_planes[i][1]; p.normal = ctx->g_planes[i][2]; p.mat = ctx->g_planes[i][3]; return p; }
 static ResPlanes res_of(vrs_ctx* ctx, int i) { ResPlanes r; r.info = ctx->r_planes[i][0]; r.weight = ctx->r_planes[i][1]; return r; }
 
+// 4x4 inverse in double precision (Gauss-Jordan with partial pivoting, column-major in and out); false = singular
+static bool invert4d(const double* m, double* out) {
+  double a[4][8];
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) { a[r][c] = m[c * 4 + r]; a[r][4 + c] = r == c ? 1.0 : 0.0; }
+  for (int i = 0; i < 4; ++i) {
+    int piv = i;
+    for (int r = i + 1; r < 4; ++r) if (std::fabs(a[r][i]) > std::fabs(a[piv][i])) piv = r;
+    if (!(std::fabs(a[piv][i]) > 1e-300)) return false;
+    if (piv != i) for (int c = 0; c < 8; ++c) std::swap(a[i][c], a[piv][c]);
+    const double d = 1.0 / a[i][i];
+    for (int c = 0; c < 8; ++c) a[i][c] *= d;
+    for (int r = 0; r < 4; ++r) if (r != i) { const double f = a[r][i]; if (f != 0.0) for (int c = 0; c < 8; ++c) a[r][c] -= f * a[i][c]; }
+  }
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) out[c * 4 + r] = a[r][4 + c];
+  return true;
+}
+
 static vrs_status make_params(vrs_ctx* ctx, const vrs_global_uniforms* gu, const vrs_restir_uniforms* ru, const vrs_push_constant_restir* pc,
                               uint32_t clock, FrameParams& F) {
   if (!ctx->has_grid) return fail(ctx, VRS_ERR_INVALID, "no grid loaded");
@@ -448,7 +466,21 @@ static vrs_status make_params(vrs_ctx* ctx, const vrs_global_uniforms* gu, const
     return fail(ctx, VRS_ERR_INVALID, "RestirUniforms light counts != uploaded lights");
   if (ru->triangleLightCount > 1) return fail(ctx, VRS_ERR_UNSUPPORTED, "triangle lights are outside the volume hot path");
   memset(&F, 0, sizeof(F));
-  if (gu) { memcpy(F.viewInverse, gu->viewInverse, 64); memcpy(F.projInverse, gu->projInverse, 64); }
+  if (gu) {
+    memcpy(F.viewInverse, gu->viewInverse, 64); memcpy(F.projInverse, gu->projInverse, 64);
+    // world -> clip of the primary rays, from the very matrices the rays are built with (coverage culling, k_cover)
+    double vi[16], pi[16], v[16], p[16];
+    for (int i = 0; i < 16; ++i) { vi[i] = gu->viewInverse[i]; pi[i] = gu->projInverse[i]; }
+    if (invert4d(vi, v) && invert4d(pi, p)) {
+      for (int c = 0; c < 4; ++c) for (int r = 0; r < 4; ++r) {          // column-major: (P * V)[r][c] = sum_k P[r][k] V[k][c]
+        double acc = 0.0;
+        for (int k = 0; k < 4; ++k) acc += p[k * 4 + r] * v[c * 4 + k];
+        F.cullVP[c * 4 + r] = (float)acc;
+      }
+      F.cull = 1;
+      for (int i = 0; i < 16; ++i) if (!std::isfinite(F.cullVP[i])) F.cull = 0;
+    }
+  }
   memcpy(F.prevVP, ru->prevFrameProjectionViewMatrix, 64);
   for (int a = 0; a < 3; ++a) F.camPos[a] = ru->currCamPos[a];
   F.W = ctx->W; F.H = ctx->H; F.M = ru->initialLightSampleCount; F.temporalMult = ru->temporalSampleCountMultiplier;
@@ -527,7 +559,7 @@ static vrs_status enqueue_initial(vrs_ctx* ctx, const FrameParams& F, cudaEvent_
                  res_of(ctx, ctx->final_r), res_of(ctx, out), ctx->queues, ctx->trace, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1,
                  ctx->persistent_blocks, prev_halo_ready, peer_wait ? pw : nullptr);
   CK(cudaGetLastError());
-  ctx->src_r = out; ctx->timings.launches += (uint32_t)initial_pass_launches(F.flags);
+  ctx->src_r = out; ctx->timings.launches += (uint32_t)initial_pass_launches(F.flags, F.cull && !ctx->trace && !getenv("VRS_NO_CULL"));
   return VRS_OK;
 }
 static vrs_status enqueue_spatial(vrs_ctx* ctx, uint32_t iteration) {
@@ -616,7 +648,7 @@ vrs_status vrs_render_frame(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
   }
   // The launch sequence depends only on which buffers are current (6 ping-pong phases) and on the structural flags.
   const uint64_t key = (uint64_t)ctx->cur_g | ((uint64_t)ctx->final_r << 1) | ((uint64_t)(F.flags & 0x3f) << 3) | ((uint64_t)ctx->cfg.spatial_iterations << 9) |
-                       ((uint64_t)(ctx->comm ? 1 : 0) << 12) | ((uint64_t)(ctx->peer_mode ? 1 : 0) << 13);
+                       ((uint64_t)(ctx->comm ? 1 : 0) << 12) | ((uint64_t)(ctx->peer_mode ? 1 : 0) << 13) | ((uint64_t)(F.cull ? 1 : 0) << 14);
   auto it = ctx->graphs.find(key);
   if (it == ctx->graphs.end() && ctx->seen[key]++ == 0) {
     // first frame of a phase runs eagerly: NCCL sets up its peer connections on first use, which must not happen under capture

@@ -50,6 +50,8 @@ struct FrameParams {
   uint32_t clock;
   float clear[3];
   int frame, initialize;
+  float cullVP[16];               // world -> clip of the primary rays (inverse of viewInverse / projInverse), for k_cover
+  int cull;                       // 1 = cullVP is valid, screen-space coverage culling may be used
 };
 
 struct Planes {                   // band-local RGBA32F planes (reference layouts)
@@ -62,7 +64,8 @@ struct ResPlanes { float4* info; float4* weight; };
 // anybody reads is worldPos.w = 0, which is what keeps the frame's HBM traffic proportional to the
 // part of the screen the volume covers.
 struct Queues {
-  uint32_t* counters;     // [0] candidates [1] hits [2] shadow rays [3] primary queue head [4] shadow queue head
+  uint32_t* counters;     // [0] candidates [1] hits [2] shadow rays [3] primary queue head [4] shadow queue head [5] coverage mask unusable
+  uint8_t* cover;         // per 8x8-pixel screen tile: 1 = some non-empty cell of the grid may project into it (k_cover)
   uint32_t* cand;         // pixels whose primary ray enters the grid window
   float4* cand_ray;       // 2 x float4 per candidate: clipped primary ray {o.xyz, t0}, {d.xyz, t1}
   uint8_t* flag;          // per pixel: 1 = real collision found by k_primary
@@ -430,7 +433,7 @@ template <int MODE>
 struct Ray {
   float o[3], d[3], tn[3], dt[3];
   float t, t1, tcell, mu_d, mu, tau, T;
-  int c[3];
+  int c[3], sgn[3];
   int cell, axis;
   uint32_t ntent, ncells;
   bool last, hit;
@@ -447,6 +450,7 @@ struct Ray {
       if (ci < 0) ci = 0;
       if (ci > G.cdim[a] - 1) ci = G.cdim[a] - 1;
       c[a] = ci;
+      sgn[a] = d[a] > 0.0f ? 1 : -1;
       if (d[a] == 0.0f) { tn[a] = __int_as_float(0x7f800000); dt[a] = 0.0f; }
       else {
         float inv = 1.0f / d[a];
@@ -455,6 +459,7 @@ struct Ray {
         dt[a] = fabsf(inv) * 8.0f;
       }
     }
+    cell = (c[2] * G.cdim[1] + c[1]) * G.cdim[0] + c[0];
     t = r.t0; t1 = r.t1;
     tau = neglog1m(rnd(seed));
   }
@@ -471,8 +476,7 @@ struct Ray {
     if (tn[2] < tcell) { tcell = tn[2]; axis = 2; }
     last = false;
     if (!(tcell < t1)) { tcell = t1; last = true; }
-    cell = (c[2] * G.cdim[1] + c[1]) * G.cdim[0] + c[0];
-    mu_d = __ldg(&G.dir_max[cell]);
+    mu_d = __ldg(&G.dir_max[cell]);                          // `cell` = (c[2] * cdim[1] + c[1]) * cdim[0] + c[0], kept incrementally
     mu = mu_d > 0.0f ? mu_d * G.density_scale : 0.0f;        // empty cell: seg = 0 below, tau is untouched (x - 0 = x)
   }
 
@@ -480,16 +484,13 @@ struct Ray {
     const float seg = (tcell - t) * mu;
     if (tau < seg) return RAY_COLLIDE;
     tau = tau - seg;
-    t = tcell;                                               // leave the cell along `axis` (branch-free over the axis)
+    t = tcell;
     if (last) return RAY_DONE;
-    c[0] += axis == 0 ? (d[0] > 0.0f ? 1 : -1) : 0;
-    c[1] += axis == 1 ? (d[1] > 0.0f ? 1 : -1) : 0;
-    c[2] += axis == 2 ? (d[2] > 0.0f ? 1 : -1) : 0;
-    if ((unsigned)c[0] >= (unsigned)G.cdim[0] || (unsigned)c[1] >= (unsigned)G.cdim[1] || (unsigned)c[2] >= (unsigned)G.cdim[2]) return RAY_DONE;
-    tn[0] = axis == 0 ? tn[0] + dt[0] : tn[0];
-    tn[1] = axis == 1 ? tn[1] + dt[1] : tn[1];
-    tn[2] = axis == 2 ? tn[2] + dt[2] : tn[2];
-    return RAY_SKIP;
+    bool out;                                                // leave the cell along `axis`
+    if (axis == 0)      { c[0] += sgn[0]; cell += sgn[0];                           tn[0] = tn[0] + dt[0]; out = (unsigned)c[0] >= (unsigned)G.cdim[0]; }
+    else if (axis == 1) { c[1] += sgn[1]; cell += sgn[1] * G.cdim[0];               tn[1] = tn[1] + dt[1]; out = (unsigned)c[1] >= (unsigned)G.cdim[1]; }
+    else                { c[2] += sgn[2]; cell += sgn[2] * (G.cdim[0] * G.cdim[1]); tn[2] = tn[2] + dt[2]; out = (unsigned)c[2] >= (unsigned)G.cdim[2]; }
+    return out ? RAY_DONE : RAY_SKIP;
   }
 
   // false = the ray ended at this collision (primary: real collision found; shadow: opaque)

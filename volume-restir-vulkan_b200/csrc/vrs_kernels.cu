@@ -26,7 +26,8 @@ static constexpr int MAX_NEIGHBORS = 16;
 //   A4 k_shadow     persistent warps: ratio-tracking transmittance toward the selected light (:229-235).
 //   A5 k_finish     one thread per hit: apply the transmittance, temporal merge (:237-284), pack (:286-289).
 // -------------------------------------------------------------------------------------------------
-enum { Q_CAND = 0, Q_HIT = 1, Q_SHADOW = 2, Q_PRIMARY_HEAD = 3, Q_SHADOW_HEAD = 4 };
+enum { Q_CAND = 0, Q_HIT = 1, Q_SHADOW = 2, Q_PRIMARY_HEAD = 3, Q_SHADOW_HEAD = 4, Q_COVER_ALL = 5 };
+static constexpr int COVER_TILE = 8;            // pixels per side of a coverage tile
 static constexpr int REFILL_MIN_IDLE = 16;
 static constexpr int CELLS_PER_DECISION = 2;
 static constexpr int MIN_WARPS_PER_SM = 16;     // small launches are spread over at least this many warps per SM
@@ -43,8 +44,41 @@ __device__ __forceinline__ void primary_ray(const FrameParams& F, int x, int y, 
   org = v3(o4[0], o4[1], o4[2]); dir = v3(d4[0], d4[1], d4[2]);
 }
 
+
+// A-1 k_cover: screen-space bound of the occupied part of the grid.  Every non-empty 8^3 cell of the directory is
+// projected (8 corners through the inverse of the primary-ray matrices, padded by 2 pixels) and the 8x8-pixel tiles its
+// bounding rectangle touches are marked.  A primary ray can only collide inside a non-empty cell, so a pixel in an
+// unmarked tile is a miss without marching: k_classify does not queue it.  Cells that reach behind the eye, or that
+// would cover a large part of the screen (camera inside the volume), switch the mask off for the frame instead.
+__global__ void __launch_bounds__(128) k_cover(const GridDev G, const FrameParams* __restrict__ Fp, Queues Q, int tiles_x, int tiles_y) {
+  const FrameParams& F = *Fp;
+  const int ncell = G.cdim[0] * G.cdim[1] * G.cdim[2];
+  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ci >= ncell) return;
+  if (!(__ldg(&G.dir_max[ci]) > 0.0f)) return;
+  const int c[3] = {ci % G.cdim[0], (ci / G.cdim[0]) % G.cdim[1], ci / (G.cdim[0] * G.cdim[1])};
+  float minx = 3.0e38f, maxx = -3.0e38f, miny = 3.0e38f, maxy = -3.0e38f;
+  for (int k = 0; k < 8; ++k) {
+    float w3[3];
+    for (int a = 0; a < 3; ++a) w3[a] = (float(G.vmin[a] + 8 * (c[a] + ((k >> a) & 1))) - 0.5f) * G.A + G.B[a];   // voxel ijk covers [ijk - 1/2, ijk + 1/2)
+    float q[4];
+    mat_vec(F.cullVP, w3[0], w3[1], w3[2], 1.0f, q);
+    if (!(q[3] > 1e-6f)) { Q.counters[Q_COVER_ALL] = 1u; return; }
+    const float px = (q[0] / q[3] + 1.0f) * 0.5f * float(F.W), py = (q[1] / q[3] + 1.0f) * 0.5f * float(F.H);   // pixel x <-> NDC 2x/W - 1 (:142-145)
+    minx = fminf(minx, px); maxx = fmaxf(maxx, px); miny = fminf(miny, py); maxy = fmaxf(maxy, py);
+  }
+  if (!(minx == minx && maxx == maxx && miny == miny && maxy == maxy)) { Q.counters[Q_COVER_ALL] = 1u; return; }
+  minx = floorf(minx) - 2.0f; miny = floorf(miny) - 2.0f; maxx = ceilf(maxx) + 2.0f; maxy = ceilf(maxy) + 2.0f;
+  if (maxx < 0.0f || maxy < 0.0f || minx > float(F.W - 1) || miny > float(F.H - 1)) return;                       // off screen
+  const int tx0 = (int)fmaxf(minx, 0.0f) / COVER_TILE, ty0 = (int)fmaxf(miny, 0.0f) / COVER_TILE;
+  const int tx1 = (int)fminf(maxx, float(F.W - 1)) / COVER_TILE, ty1 = (int)fminf(maxy, float(F.H - 1)) / COVER_TILE;
+  if ((long long)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 4096) { Q.counters[Q_COVER_ALL] = 1u; return; }
+  for (int ty = ty0; ty <= ty1 && ty < tiles_y; ++ty)
+    for (int tx = tx0; tx <= tx1 && tx < tiles_x; ++tx) Q.cover[(size_t)ty * tiles_x + tx] = 1;
+}
+
 __global__ void __launch_bounds__(256) k_classify(const GridDev G, const FrameParams* __restrict__ Fp, Planes cur, Queues Q,
-                                                  uint32_t* __restrict__ trace, int y0, int y1, int store_y0) {
+                                                  uint32_t* __restrict__ trace, int y0, int y1, int store_y0, int tiles_x) {
   const FrameParams& F = *Fp;
   const int x = blockIdx.x * 32 + threadIdx.x;
   const int y = y0 + blockIdx.y * 8 + threadIdx.y;
@@ -55,6 +89,7 @@ __global__ void __launch_bounds__(256) k_classify(const GridDev G, const FramePa
     idx = (size_t)(y - store_y0) * F.W + x;
     V3 org, dir; primary_ray(F, x, y, org, dir);
     enters = clip_ray(G, org, dir, 0.0001f, 100000.0f, seg);                       // :164-166 ray range
+    if (enters && tiles_x > 0 && Q.counters[Q_COVER_ALL] == 0u && Q.cover[(size_t)(y / COVER_TILE) * tiles_x + x / COVER_TILE] == 0) enters = false;
     cur.worldPos[idx] = make_float4(0.f, 0.f, 0.f, 0.f);                           // miss until k_primary says otherwise
     Q.flag[idx] = 0;
     if (trace) {
@@ -973,8 +1008,18 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
                             ((getenv("VRS_CELLS") ? atoi(getenv("VRS_CELLS")) : CELLS_PER_DECISION) << 8) | (target_warps << 16);
   static const char ris_kind = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'p';   // t(hread) | p(refetch) | c(oop)
   cudaMemsetAsync(Q.counters, 0, 8 * sizeof(uint32_t), st);
+  // screen-space coverage culling (k_cover); the RNG / cell trace of a culled ray would differ, so tracing turns it off
+  static const bool no_cull = getenv("VRS_NO_CULL") != nullptr;
+  int tiles_x = 0;
+  if (F.cull && !trace && !no_cull && Q.cover) {
+    tiles_x = ((int)F.W + COVER_TILE - 1) / COVER_TILE;
+    const int tiles_y = ((int)F.H + COVER_TILE - 1) / COVER_TILE;
+    cudaMemsetAsync(Q.cover, 0, (size_t)tiles_x * tiles_y, st);
+    const int ncell = G.cdim[0] * G.cdim[1] * G.cdim[2];
+    k_cover<<<(ncell + 127) / 128, 128, 0, st>>>(G, dF, Q, tiles_x, tiles_y);
+  }
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
-  k_classify<<<grid, block, 0, st>>>(G, dF, cur, Q, trace, y0, y1, store_y0);
+  k_classify<<<grid, block, 0, st>>>(G, dF, cur, Q, trace, y0, y1, store_y0, tiles_x);
   k_primary<<<persistent_blocks, 128, 0, st>>>(G, dF, cur, Q, trace, store_y0, refill);
   // compaction runs over every stored row (8-byte aligned flag loads); flags outside the band rows stay 0
   const size_t npix = (size_t)(store_y1 - store_y0) * F.W;
@@ -994,9 +1039,9 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   if (needs_finish && peer_wait) k_halo_wait<<<1, 1, 0, st>>>(peer_wait[0], peer_wait[1], peer_wait[2], const_cast<unsigned*>(peer_wait[3]));
   if (needs_finish) k_finish<<<g_finish, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1);
 }
-int initial_pass_launches(int flags) {
+int initial_pass_launches(int flags, bool culling) {
   const bool vis = (flags & FLAG_VISIBILITY) != 0, temporal = (flags & FLAG_TEMPORAL) != 0;
-  return 4 + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
+  return 4 + (culling ? 1 : 0) + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
 }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, int store_y0, int store_y1, int persistent_blocks) {
