@@ -1006,7 +1006,11 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   }();
   static const int refill = (getenv("VRS_REFILL") ? atoi(getenv("VRS_REFILL")) : REFILL_MIN_IDLE) |
                             ((getenv("VRS_CELLS") ? atoi(getenv("VRS_CELLS")) : CELLS_PER_DECISION) << 8) | (target_warps << 16);
-  static const char ris_kind = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'p';   // t(hread) | p(refetch) | c(oop)
+  // RIS stage: t(hread) | p(refetch) | c(oop) | a(uto).  Measured on B200 (profiles/r01_summary.md): with light tables that
+  // stay L1-resident the plain per-thread loop is fastest; once they spill to L2 (thousands of lights) the cooperative
+  // kernel, which keeps the dependent table fetches of several pixels in flight, wins.
+  static const char ris_env = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'a';
+  const char ris_kind = ris_env != 'a' ? ris_env : ((size_t)L.nlights * 32 + (size_t)L.ntable * 16 > (size_t)64 * 1024 ? 'c' : 't');
   cudaMemsetAsync(Q.counters, 0, 8 * sizeof(uint32_t), st);
   // screen-space coverage culling (k_cover); the RNG / cell trace of a culled ray would differ, so tracing turns it off
   static const bool no_cull = getenv("VRS_NO_CULL") != nullptr;
