@@ -234,7 +234,7 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
   // dense directory over the window's cells (the top tree levels flattened once more for the raymarch)
   const size_t ncell = (size_t)G.cdim[0] * G.cdim[1] * G.cdim[2];
   if (ncell > ((size_t)1 << 30)) { free_grid(ctx); return fail(ctx, VRS_ERR_UNSUPPORTED, "grid window exceeds 2^30 cells"); }
-  std::vector<float> dir_max(ncell); std::vector<int32_t> dir_leaf(ncell);
+  std::vector<float> dir(2 * ncell);      // {majorant, leaf bits} per cell (GridDev::dir)
   for (int cz = 0; cz < G.cdim[2]; ++cz)
     for (int cy = 0; cy < G.cdim[1]; ++cy)
       for (int cx = 0; cx < G.cdim[0]; ++cx) {
@@ -248,8 +248,8 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
           if (c >= 0) c = h.i4[(size_t)c * 4096 + ((((x & 127) >> 3) << 8) | (((y & 127) >> 3) << 4) | ((z & 127) >> 3))];
         }
         const size_t ci = ((size_t)cz * G.cdim[1] + cy) * G.cdim[0] + cx;
-        dir_leaf[ci] = c;
-        dir_max[ci] = c < 0 ? tile_density[~c] : leaf_max[c];
+        dir[2 * ci] = c < 0 ? tile_density[~c] : leaf_max[c];
+        memcpy(&dir[2 * ci + 1], &c, 4);
       }
   // One slab for every grid table, so that a single L2 access-policy window can pin the whole grid: the per-pixel
   // buffers stream through L2 every frame (hundreds of MB) and would otherwise evict the few MB every ray keeps re-reading.
@@ -257,8 +257,7 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
   G.nroot = (int)(h.root.size() / 4);
   Part parts[] = {{h.root.data(), h.root.size() * 4, (const void**)&G.root}, {h.i5.data(), h.i5.size() * 4, (const void**)&G.i5},
                   {h.i4.data(), h.i4.size() * 4, (const void**)&G.i4}, {tile_density.data(), tile_density.size() * 4, (const void**)&G.tile_density},
-                  {leaf_max.data(), leaf_max.size() * 4, (const void**)&G.leaf_max}, {dir_max.data(), dir_max.size() * 4, (const void**)&G.dir_max},
-                  {dir_leaf.data(), dir_leaf.size() * 4, (const void**)&G.dir_leaf}, {atlas.data(), atlas.size() * 4, (const void**)&G.atlas}};
+                  {leaf_max.data(), leaf_max.size() * 4, (const void**)&G.leaf_max}, {dir.data(), dir.size() * 4, (const void**)&G.dir}, {atlas.data(), atlas.size() * 4, (const void**)&G.atlas}};
   size_t total = 0;
   for (const Part& p : parts) total += (p.bytes + 255) & ~(size_t)255;
   char* slab = nullptr;

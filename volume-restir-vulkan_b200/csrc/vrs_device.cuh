@@ -26,8 +26,8 @@ struct GridDev {
   const float* atlas;             // [nleaf][512] densities, offset (x<<6)|(y<<3)|z
   // Dense directory over the window's 8^3 cells (the top tree levels flattened once more): the raymarch reads one
   // L1/L2-resident entry per cell instead of walking root -> internal5 -> internal4.
-  const float* dir_max;           // [cdim z][cdim y][cdim x] majorant density of the cell (0 = empty)
-  const int* dir_leaf;            // same shape: leaf index (>= 0) or ~tile (< 0)
+  const float2* dir;              // [cdim z][cdim y][cdim x] {majorant density of the cell (0 = empty), leaf index (>= 0) or ~tile (< 0) as bits}:
+                                  // one 8-byte load per visited cell serves both the majorant test and the later brick lookup
 };
 
 struct LightsDev {
@@ -434,7 +434,7 @@ struct Ray {
   float o[3], d[3], tn[3], dt[3];
   float t, t1, tcell, mu_d, mu, tau, T;
   int c[3], sgn[3];
-  int cell, axis;
+  int cell, axis, leaf;
   uint32_t ntent, ncells;
   bool last, hit;
   int vox[3];
@@ -476,7 +476,8 @@ struct Ray {
     if (tn[2] < tcell) { tcell = tn[2]; axis = 2; }
     last = false;
     if (!(tcell < t1)) { tcell = t1; last = true; }
-    mu_d = __ldg(&G.dir_max[cell]);                          // `cell` = (c[2] * cdim[1] + c[1]) * cdim[0] + c[0], kept incrementally
+    const float2 e = __ldg(&G.dir[cell]);                    // `cell` = (c[2] * cdim[1] + c[1]) * cdim[0] + c[0], kept incrementally
+    mu_d = e.x; leaf = __float_as_int(e.y);
     mu = mu_d > 0.0f ? mu_d * G.density_scale : 0.0f;        // empty cell: seg = 0 below, tau is untouched (x - 0 = x)
   }
 
@@ -502,7 +503,6 @@ struct Ray {
     vx = vx < vlo0 ? vlo0 : (vx > vlo0 + 7 ? vlo0 + 7 : vx);
     vy = vy < vlo1 ? vlo1 : (vy > vlo1 + 7 ? vlo1 + 7 : vy);
     vz = vz < vlo2 ? vlo2 : (vz > vlo2 + 7 ? vlo2 + 7 : vz);
-    const int leaf = __ldg(&G.dir_leaf[cell]);
     float dens = leaf < 0 ? mu_d : __ldg(&G.atlas[(size_t)leaf * 512 + (((vx & 7) << 6) | ((vy & 7) << 3) | (vz & 7))]);
     if (MODE == 0) {
       float u2 = rnd(seed);

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) k_cover(const GridDev G, const FrameParam
   const int ncell = G.cdim[0] * G.cdim[1] * G.cdim[2];
   const int ci = blockIdx.x * blockDim.x + threadIdx.x;
   if (ci >= ncell) return;
-  if (!(__ldg(&G.dir_max[ci]) > 0.0f)) return;
+  if (!(__ldg(&G.dir[ci]).x > 0.0f)) return;
   const int c[3] = {ci % G.cdim[0], (ci / G.cdim[0]) % G.cdim[1], ci / (G.cdim[0] * G.cdim[1])};
   float minx = 3.0e38f, maxx = -3.0e38f, miny = 3.0e38f, maxy = -3.0e38f;
   for (int k = 0; k < 8; ++k) {
