@@ -196,6 +196,9 @@ vrs_status vrs_write_image(vrs_ctx* ctx, const char* path);
 typedef struct { float initial_ms, spatial_ms, shade_ms, exchange_ms, frame_ms; uint32_t launches; } vrs_timings;
 /* CUDA-event times of the last vrs_render_frame on the context stream (valid after vrs_synchronize). */
 vrs_status vrs_get_timings(vrs_ctx* ctx, vrs_timings* out);
+/* Per-pass CUDA events are recorded inside every frame by default; they cost a few microseconds of a sub-millisecond
+   frame.  enabled = 0 leaves them out (vrs_get_timings then fails with VRS_ERR_INVALID until re-enabled and a frame ran). */
+vrs_status vrs_set_pass_timing(vrs_ctx* ctx, int enabled);
 void*      vrs_stream(vrs_ctx* ctx);                                                    /* cudaStream_t */
 
 /* ---- multi-GPU: screen-space bands, grid replicated, halo rows exchanged over NCCL ---------- */

@@ -31,7 +31,7 @@ EXPORTS = [
     "vrs_grid_sample_device", "vrs_set_lights", "vrs_collect_emissive_lights", "vrs_vdb_emissive_lights", "vrs_set_triangle_lights", "vrs_get_alias_table", "vrs_create_alias_table",
     "vrs_generate_point_lights", "vrs_perspectiveVK", "vrs_look_at", "vrs_invert", "vrs_mat4_mul", "vrs_pass_initial",
     "vrs_pass_spatial", "vrs_pass_shade", "vrs_render_frame", "vrs_synchronize", "vrs_read_frame", "vrs_read_gbuffer",
-    "vrs_read_reservoirs", "vrs_read_trace", "vrs_read_display", "vrs_present_async", "vrs_present_wait", "vrs_write_image", "vrs_get_timings", "vrs_stream", "vrs_comm_unique_id",
+    "vrs_read_reservoirs", "vrs_read_trace", "vrs_read_display", "vrs_present_async", "vrs_present_wait", "vrs_write_image", "vrs_get_timings", "vrs_set_pass_timing", "vrs_stream", "vrs_comm_unique_id",
     "vrs_comm_init", "vrs_peer_export", "vrs_peer_connect", "vrs_band_for_rank",
 ]
 
@@ -120,7 +120,7 @@ def lib():
                      "vrs_grid_sample_device", "vrs_set_lights", "vrs_collect_emissive_lights", "vrs_vdb_emissive_lights", "vrs_set_triangle_lights", "vrs_get_alias_table",
                      "vrs_pass_initial", "vrs_pass_spatial", "vrs_pass_shade", "vrs_render_frame", "vrs_synchronize",
                      "vrs_read_frame", "vrs_read_gbuffer", "vrs_read_reservoirs", "vrs_read_trace", "vrs_write_image",
-                     "vrs_get_timings", "vrs_comm_init", "vrs_read_display", "vrs_present_async", "vrs_present_wait"]:
+                     "vrs_get_timings", "vrs_set_pass_timing", "vrs_comm_init", "vrs_read_display", "vrs_present_async", "vrs_present_wait"]:
             getattr(L, name).restype = C.c_int
         L.vrs_load_vdb.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.vrs_load_vrsg.argtypes = [C.c_void_p, C.c_char_p]
@@ -148,6 +148,7 @@ def lib():
         L.vrs_present_async.argtypes = [C.c_void_p, C.c_void_p]
         L.vrs_present_wait.argtypes = [C.c_void_p]
         L.vrs_get_timings.argtypes = [C.c_void_p, C.c_void_p]
+        L.vrs_set_pass_timing.argtypes = [C.c_void_p, C.c_int]
         L.vrs_stream.argtypes = [C.c_void_p]
         L.vrs_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.vrs_peer_export.argtypes = [C.c_void_p, C.c_void_p]
@@ -473,6 +474,9 @@ class Renderer:
 
     def writeImage(self, path):
         self._ck(lib().vrs_write_image(self._ctx, path.encode()))
+
+    def setPassTiming(self, enabled):
+        self._ck(lib().vrs_set_pass_timing(self._ctx, int(bool(enabled))))
 
     def timings(self):
         t = Timings()

@@ -69,6 +69,7 @@ struct vrs_ctx {
   cudaEvent_t ev[8] = {nullptr};
   vrs_timings timings{};
   bool timings_valid = false;
+  bool pass_timing = true;                   // record the per-pass events inside each frame (vrs_set_pass_timing)
   Comm* comm = nullptr;
   // peer-memory exchange (vrs_peer_connect): neighbours' planes opened through CUDA IPC
   struct Peer { bool present = false; float4* g[2][4] = {{nullptr}}; float4* r[3][2] = {{nullptr}}; unsigned* flags = nullptr; int store_y0 = 0, store_y1 = 0, band_y0 = 0, band_y1 = 0; std::vector<void*> opened; };
@@ -548,6 +549,7 @@ static vrs_status exchange(vrs_ctx* ctx, bool gbuf, int g_index, int r_index, bo
 
 // timing events must become event-record nodes when the frame is being captured into a graph
 static cudaError_t mark(vrs_ctx* ctx, int i) {
+  if (!ctx->pass_timing) return cudaSuccess;
   return ctx->capturing ? cudaEventRecordWithFlags(ctx->ev[i], ctx->stream, cudaEventRecordExternal) : cudaEventRecord(ctx->ev[i], ctx->stream);
 }
 
@@ -642,17 +644,17 @@ vrs_status vrs_render_frame(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
   (void)no_graph_comm;
   if (no_graph || ctx->comm) {     // NCCL send/recv under stream capture hangs here (NCCL 2.28.9): NCCL contexts launch eagerly
     if ((s = enqueue_frame(ctx, F))) return s;
-    ctx->timings_valid = true;
+    ctx->timings_valid = ctx->pass_timing;
     return VRS_OK;
   }
   // The launch sequence depends only on which buffers are current (6 ping-pong phases) and on the structural flags.
   const uint64_t key = (uint64_t)ctx->cur_g | ((uint64_t)ctx->final_r << 1) | ((uint64_t)(F.flags & 0x3f) << 3) | ((uint64_t)ctx->cfg.spatial_iterations << 9) |
-                       ((uint64_t)(ctx->comm ? 1 : 0) << 12) | ((uint64_t)(ctx->peer_mode ? 1 : 0) << 13) | ((uint64_t)(F.cull ? 1 : 0) << 14);
+                       ((uint64_t)(ctx->comm ? 1 : 0) << 12) | ((uint64_t)(ctx->peer_mode ? 1 : 0) << 13) | ((uint64_t)(F.cull ? 1 : 0) << 14) | ((uint64_t)(ctx->pass_timing ? 1 : 0) << 15);
   auto it = ctx->graphs.find(key);
   if (it == ctx->graphs.end() && ctx->seen[key]++ == 0) {
     // first frame of a phase runs eagerly: NCCL sets up its peer connections on first use, which must not happen under capture
     if ((s = enqueue_frame(ctx, F))) return s;
-    ctx->timings_valid = true;
+    ctx->timings_valid = ctx->pass_timing;
     return VRS_OK;
   }
   if (it == ctx->graphs.end()) {
@@ -678,7 +680,7 @@ vrs_status vrs_render_frame(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
     ctx->timings.launches = ge.launches;
   }
   CK(cudaGraphLaunch(it->second.exec, ctx->stream));
-  ctx->timings_valid = true;
+  ctx->timings_valid = ctx->pass_timing;
   return VRS_OK;
 }
 
@@ -687,6 +689,13 @@ vrs_status vrs_synchronize(vrs_ctx* ctx) {
   cudaSetDevice(ctx->device);
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaStreamSynchronize(ctx->comm_stream));
+  return VRS_OK;
+}
+
+vrs_status vrs_set_pass_timing(vrs_ctx* ctx, int enabled) {
+  if (!ctx) return VRS_ERR_INVALID;
+  ctx->pass_timing = enabled != 0;
+  if (!ctx->pass_timing) ctx->timings_valid = false;
   return VRS_OK;
 }
 
