@@ -323,7 +323,7 @@ def run_ours(args):
             "mpixels_per_s": round(px * fps / 1e6, 1), "mpixel_samples_per_s": round(px * wl["M"] * fps / 1e6, 1),
             "frame_hbm_gbs": round(frame_bytes * fps / 1e9, 1), "frame_hbm_frac": round(frame_bytes * fps / 1e9 / peak, 4),
             "pass_ms": {k_: round(v, 5) for k_, v in pass_ms.items()},
-            "roofline": {"kernel": "initial pass = k_classify + k_primary + k_hit_compact + k_ris (M=%d) + k_shadow + k_finish (restir.rgen main on a volume)" % wl["M"], "bound": "hbm",
+            "roofline": {"kernel": "initial pass = k_cover + k_classify + k_primary + k_hit_compact + k_ris_* (M=%d) + k_shadow + k_finish (restir.rgen main on a volume)" % wl["M"], "bound": "hbm",
                          "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": int(init_bytes)},
             "e2e": {"value": round(1000.0 / e2e_ms, 3), "unit": "frames/s", "h2d_bytes_per_step": 192 + 320 + 20,

@@ -9,7 +9,7 @@ VRS_NO_GRAPH=1 ncu --metrics $M --clock-control none -c 60 --csv --log-file gpur
   python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_stdout.log 2>&1
 python tools/summarize_launches.py gpurun_out/${tag}_launches.csv
 if [ -n "$k" ]; then
-  VRS_NO_GRAPH=1 ncu --set full --import-source on --clock-control none -k regex:$k --launch-skip 3 -c 1 -f -o gpurun_out/${tag}_full \
+  VRS_NO_GRAPH=1 ncu --set full --import-source on --clock-control none -k regex:"$k" --launch-skip 6 -c 2 -f -o gpurun_out/${tag}_full \
     python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu-baseline >> gpurun_out/${tag}_ncu_stdout.log 2>&1
   ncu -i gpurun_out/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>/dev/null
 fi

@@ -52,29 +52,44 @@ __device__ __forceinline__ void primary_ray(const FrameParams& F, int x, int y, 
 // would cover a large part of the screen (camera inside the volume), switch the mask off for the frame instead.
 __global__ void __launch_bounds__(128) k_cover(const GridDev G, const FrameParams* __restrict__ Fp, Queues Q, int tiles_x, int tiles_y) {
   const FrameParams& F = *Fp;
+  // 8 lanes per cell: lane k projects corner k, the bounding rectangle is reduced with shuffles, the lanes share the tile loop
   const int ncell = G.cdim[0] * G.cdim[1] * G.cdim[2];
-  const int ci = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ci >= ncell) return;
-  if (!(__ldg(&G.dir[ci]).x > 0.0f)) return;
-  const int c[3] = {ci % G.cdim[0], (ci / G.cdim[0]) % G.cdim[1], ci / (G.cdim[0] * G.cdim[1])};
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ci = t >> 3, k = t & 7;
+  const bool live = ci < ncell && __ldg(&G.dir[ci < ncell ? ci : 0]).x > 0.0f;
   float minx = 3.0e38f, maxx = -3.0e38f, miny = 3.0e38f, maxy = -3.0e38f;
-  for (int k = 0; k < 8; ++k) {
+  bool bad = false;
+  if (live) {
+    const int c[3] = {ci % G.cdim[0], (ci / G.cdim[0]) % G.cdim[1], ci / (G.cdim[0] * G.cdim[1])};
     float w3[3];
     for (int a = 0; a < 3; ++a) w3[a] = (float(G.vmin[a] + 8 * (c[a] + ((k >> a) & 1))) - 0.5f) * G.A + G.B[a];   // voxel ijk covers [ijk - 1/2, ijk + 1/2)
     float q[4];
     mat_vec(F.cullVP, w3[0], w3[1], w3[2], 1.0f, q);
-    if (!(q[3] > 1e-6f)) { Q.counters[Q_COVER_ALL] = 1u; return; }
-    const float px = (q[0] / q[3] + 1.0f) * 0.5f * float(F.W), py = (q[1] / q[3] + 1.0f) * 0.5f * float(F.H);   // pixel x <-> NDC 2x/W - 1 (:142-145)
-    minx = fminf(minx, px); maxx = fmaxf(maxx, px); miny = fminf(miny, py); maxy = fmaxf(maxy, py);
+    if (!(q[3] > 1e-6f)) bad = true;
+    else {
+      const float px = (q[0] / q[3] + 1.0f) * 0.5f * float(F.W), py = (q[1] / q[3] + 1.0f) * 0.5f * float(F.H);   // pixel x <-> NDC 2x/W - 1 (:142-145)
+      if (!(px == px && py == py)) bad = true;
+      minx = maxx = px; miny = maxy = py;
+    }
   }
-  if (!(minx == minx && maxx == maxx && miny == miny && maxy == maxy)) { Q.counters[Q_COVER_ALL] = 1u; return; }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {                          // all 8 lanes of a cell share `live`
+    minx = fminf(minx, __shfl_xor_sync(0xffffffffu, minx, o)); maxx = fmaxf(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+    miny = fminf(miny, __shfl_xor_sync(0xffffffffu, miny, o)); maxy = fmaxf(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+    bad = bad || __shfl_xor_sync(0xffffffffu, (int)bad, o) != 0;
+  }
+  if (!live) return;
+  if (bad) { if (k == 0) Q.counters[Q_COVER_ALL] = 1u; return; }
   minx = floorf(minx) - 2.0f; miny = floorf(miny) - 2.0f; maxx = ceilf(maxx) + 2.0f; maxy = ceilf(maxy) + 2.0f;
   if (maxx < 0.0f || maxy < 0.0f || minx > float(F.W - 1) || miny > float(F.H - 1)) return;                       // off screen
   const int tx0 = (int)fmaxf(minx, 0.0f) / COVER_TILE, ty0 = (int)fmaxf(miny, 0.0f) / COVER_TILE;
   const int tx1 = (int)fminf(maxx, float(F.W - 1)) / COVER_TILE, ty1 = (int)fminf(maxy, float(F.H - 1)) / COVER_TILE;
-  if ((long long)(tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 4096) { Q.counters[Q_COVER_ALL] = 1u; return; }
-  for (int ty = ty0; ty <= ty1 && ty < tiles_y; ++ty)
-    for (int tx = tx0; tx <= tx1 && tx < tiles_x; ++tx) Q.cover[(size_t)ty * tiles_x + tx] = 1;
+  const int nx = tx1 - tx0 + 1, ny = ty1 - ty0 + 1;
+  if ((long long)nx * ny > 4096) { if (k == 0) Q.counters[Q_COVER_ALL] = 1u; return; }
+  for (int i = k; i < nx * ny; i += 8) {
+    const int ty = ty0 + i / nx, tx = tx0 + i % nx;
+    if (ty < tiles_y && tx < tiles_x) Q.cover[(size_t)ty * tiles_x + tx] = 1;
+  }
 }
 
 __global__ void __launch_bounds__(256) k_classify(const GridDev G, const FrameParams* __restrict__ Fp, Planes cur, Queues Q,
@@ -1020,7 +1035,7 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
     const int tiles_y = ((int)F.H + COVER_TILE - 1) / COVER_TILE;
     cudaMemsetAsync(Q.cover, 0, (size_t)tiles_x * tiles_y, st);
     const int ncell = G.cdim[0] * G.cdim[1] * G.cdim[2];
-    k_cover<<<(ncell + 127) / 128, 128, 0, st>>>(G, dF, Q, tiles_x, tiles_y);
+    k_cover<<<(ncell * 8 + 127) / 128, 128, 0, st>>>(G, dF, Q, tiles_x, tiles_y);
   }
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_classify<<<grid, block, 0, st>>>(G, dF, cur, Q, trace, y0, y1, store_y0, tiles_x);
