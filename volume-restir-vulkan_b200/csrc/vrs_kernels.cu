@@ -102,9 +102,12 @@ __global__ void __launch_bounds__(256) k_classify(const GridDev G, const FramePa
   RaySeg seg;
   if (x < (int)F.W && y < y1) {
     idx = (size_t)(y - store_y0) * F.W + x;
-    V3 org, dir; primary_ray(F, x, y, org, dir);
-    enters = clip_ray(G, org, dir, 0.0001f, 100000.0f, seg);                       // :164-166 ray range
-    if (enters && tiles_x > 0 && Q.counters[Q_COVER_ALL] == 0u && Q.cover[(size_t)(y / COVER_TILE) * tiles_x + x / COVER_TILE] == 0) enters = false;
+    // a pixel in a tile no occupied cell projects into is a miss whatever its ray does: skip the ray set-up as well
+    const bool covered = !(tiles_x > 0 && Q.counters[Q_COVER_ALL] == 0u && Q.cover[(size_t)(y / COVER_TILE) * tiles_x + x / COVER_TILE] == 0);
+    if (covered) {
+      V3 org, dir; primary_ray(F, x, y, org, dir);
+      enters = clip_ray(G, org, dir, 0.0001f, 100000.0f, seg);                     // :164-166 ray range
+    }
     cur.worldPos[idx] = make_float4(0.f, 0.f, 0.f, 0.f);                           // miss until k_primary says otherwise
     Q.flag[idx] = 0;
     if (trace) {
