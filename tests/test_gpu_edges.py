@@ -148,3 +148,18 @@ def test_cpp_host_driver_matches_python_host(V, O, tmp_path):
     assert cpp.shape == py.shape
     assert common.rel_mse(cpp, py) < 1e-4
     R.destroy()
+
+
+@pytest.mark.parametrize("env", [{"VRS_RIS": "t"}, {"VRS_RIS": "p"}, {"VRS_RIS": "c"}, {"VRS_SPATIAL": "c"}, {"VRS_RIS_SMALL": "1"},
+                                 {"VRS_NO_GRAPH": "1", "VRS_NO_CULL": "1"}])
+def test_every_kernel_form_matches_the_oracle(env):
+    """The RIS stage has three forms (serial per thread, prefetching, warp-cooperative) and spatial reuse two; the
+    launcher picks one from the light-table size and the hit count.  Each form, forced through its environment switch
+    in a fresh process, must reproduce the oracle bit for bit (__graft_entry__.smoke compares frame and traces)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ, **env)
+    r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "bit-exact" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

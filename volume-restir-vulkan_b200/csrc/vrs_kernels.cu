@@ -30,6 +30,7 @@ enum { Q_CAND = 0, Q_HIT = 1, Q_SHADOW = 2, Q_PRIMARY_HEAD = 3, Q_SHADOW_HEAD = 
 static constexpr int COVER_TILE = 8;            // pixels per side of a coverage tile
 static constexpr int REFILL_MIN_IDLE = 16;
 static constexpr int CELLS_PER_DECISION = 2;
+static constexpr uint32_t RIS_SMALL_LAUNCH = 100000u;   // hit pixels below which the cooperative RIS kernel is used even with small light tables
 static constexpr int MIN_WARPS_PER_SM = 16;     // small launches are spread over at least this many warps per SM
 static constexpr int COMPACT_BLOCK = 2048;      // pixels per compaction block (256 threads x 8 flags)
 
@@ -202,9 +203,10 @@ __global__ void __launch_bounds__(256) k_hit_compact(const uint8_t* __restrict__
 // Reference form of the RIS stage: one thread per hit pixel runs the M-candidate loop serially (kept selectable with
 // VRS_RIS=thread for A/B measurements; k_ris_coop below is the default and produces the same bits).
 __global__ void __launch_bounds__(128) k_ris_thread(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
-                                             Queues Q, uint32_t* __restrict__ trace, int store_y0, int needs_finish) {
+                                             Queues Q, uint32_t* __restrict__ trace, int store_y0, int needs_finish, uint32_t min_hits) {
   const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
+  if (nhit < min_hits) return;                               // small launches are left to k_ris_coop (launch_initial)
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
     const uint32_t idx = Q.hit_pix[s];
     const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
@@ -380,7 +382,8 @@ struct RisSmem {
 };
 
 __global__ void __launch_bounds__(128, 6) k_ris_coop(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
-                                                  Queues Q, uint32_t* __restrict__ trace, int store_y0, int needs_finish, int target_warps) {
+                                                  Queues Q, uint32_t* __restrict__ trace, int store_y0, int needs_finish, int target_warps, uint32_t max_hits) {
+  if (Q.counters[Q_HIT] >= max_hits) return;                 // large launches with L1-resident light tables go to k_ris_thread
   __shared__ RisSmem sm_all[4];
   RisSmem& sm = sm_all[threadIdx.x >> 5];
   const FrameParams& F = *Fp;
@@ -1028,7 +1031,8 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   // stay L1-resident the plain per-thread loop is fastest; once they spill to L2 (thousands of lights) the cooperative
   // kernel, which keeps the dependent table fetches of several pixels in flight, wins.
   static const char ris_env = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'a';
-  const char ris_kind = ris_env != 'a' ? ris_env : ((size_t)L.nlights * 32 + (size_t)L.ntable * 16 > (size_t)64 * 1024 ? 'c' : 't');
+  static const uint32_t small_launch = getenv("VRS_RIS_SMALL") ? (uint32_t)atoi(getenv("VRS_RIS_SMALL")) : RIS_SMALL_LAUNCH;
+  const bool big_tables = (size_t)L.nlights * 32 + (size_t)L.ntable * 16 > (size_t)64 * 1024;
   cudaMemsetAsync(Q.counters, 0, 8 * sizeof(uint32_t), st);
   // screen-space coverage culling (k_cover); the RNG / cell trace of a culled ray would differ, so tracing turns it off
   static const bool no_cull = getenv("VRS_NO_CULL") != nullptr;
@@ -1052,9 +1056,13 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   static const bool one_wave = !getenv("VRS_NO_ONE_WAVE");
   static const int g_thread = one_wave ? resident_grid(k_ris_thread, 128, 8) : persistent_blocks, g_prefetch = one_wave ? resident_grid(k_ris_prefetch, 128, 6) : persistent_blocks;
   static const int g_finish = one_wave ? resident_grid(k_finish, 128, 8) : persistent_blocks;
-  if (ris_kind == 't') k_ris_thread<<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
-  else if (ris_kind == 'p') k_ris_prefetch<<<g_prefetch, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
-  else k_ris_coop<<<ris_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, target_warps);
+  if (ris_env == 't') k_ris_thread<<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, 0u);
+  else if (ris_env == 'p') k_ris_prefetch<<<g_prefetch, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
+  else if (ris_env == 'c' || big_tables) k_ris_coop<<<ris_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, target_warps, 0xFFFFFFFFu);
+  else {   // auto, small tables: the hit count (known only on the device) picks the form; the other launch returns at once
+    k_ris_coop<<<ris_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, target_warps, small_launch);
+    k_ris_thread<<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
+  }
   if (vis) k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill);
   // the previous frame's halo rows (multi-GPU) are only needed by the temporal merge: everything above overlapped their exchange
   if (needs_finish && prev_halo_ready) cudaStreamWaitEvent(st, prev_halo_ready, 0);
@@ -1063,7 +1071,7 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
 }
 int initial_pass_launches(int flags, bool culling) {
   const bool vis = (flags & FLAG_VISIBILITY) != 0, temporal = (flags & FLAG_TEMPORAL) != 0;
-  return 4 + (culling ? 1 : 0) + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
+  return 4 /* classify, primary, compact, one RIS form doing the work */ + (culling ? 1 : 0) + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
 }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, int store_y0, int store_y1, int persistent_blocks) {
