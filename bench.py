@@ -123,9 +123,9 @@ def build_scene_inputs(V, wl, R):
 
 
 def balanced_bands(V, wl, path, world, device):
-    """Screen-space bands of equal estimated cost instead of equal height: a quarter-resolution probe frame (rendered by
-    every rank on its own GPU, bit-identical everywhere) gives the per-row count of volume-hitting pixels; cost(row) =
-    hits + 2.5 % of the pixels.  Bands keep at least halo_rows rows (vrs_comm_init requires it)."""
+    """Per-row cost model for screen-space bands of equal estimated cost instead of equal height: a quarter-resolution
+    probe frame (rendered by every rank on its own GPU, bit-identical everywhere) gives the per-row count of
+    volume-hitting pixels; cost(row) = hits + 2.5 % of the pixels."""
     W, H, halo = wl["W"], wl["H"], 32
     q = 4
     w4, h4 = max(W // q, 16), max(H // q, 16)
@@ -144,6 +144,12 @@ def balanced_bands(V, wl, path, world, device):
     cost = np.repeat(hits / 4.0, q)[:H] * q + 0.025 * W         # per full-resolution row (ncu: ~1.6 ns per hit, ~0.04 ns per pixel)
     if len(cost) < H:
         cost = np.concatenate([cost, np.full(H - len(cost), cost[-1])])
+    return cost
+
+
+def split_rows(cost, world, halo=32):
+    """Band edges that give every rank the same share of the per-row cost (bands keep at least `halo` rows)."""
+    H = len(cost)
     cum = np.concatenate([[0.0], np.cumsum(cost)])
     edges = [0]
     for r in range(1, world):
@@ -155,6 +161,43 @@ def balanced_bands(V, wl, path, world, device):
     for r in range(world - 1, 0, -1):
         edges[r] = min(edges[r], edges[r + 1] - halo)
     return [(edges[r], edges[r + 1]) for r in range(world)]
+
+
+def calibrated_bands(V, wl, path, world, rank, device, dist, lights_ctr_diag=None, rounds=3, frames=12):
+    """Start from the hit-count model, then correct it with measurements: every rank renders its band (no exchange, timing
+    only) for a few frames, the per-band times are all-gathered and turned into a per-band correction of the row costs.
+    Which rows a rank renders never changes a pixel (tests/test_gpu_multi.py); only the load balance does."""
+    import torch
+    cost = balanced_bands(V, wl, path, world, device)
+    bands = split_rows(cost, world)
+    for _ in range(rounds):
+        band = bands[rank]
+        R = V.Renderer(wl["W"], wl["H"], spatial_iterations=wl["iters"], band=band, halo_rows=32, device=device)
+        R.loadVDB(path)
+        lights, ctr, diag = build_scene_inputs(V, wl, R)
+        R.createRestirLights(lights)
+        u = R.m_restirUniforms
+        u.initialLightSampleCount, u.spatialNeighbors, u.flags = wl["M"], wl["k"], wl["flags"]
+        R.CameraManip.setLookat(orbit_eye(ctr, 1.25 * diag, 0.0, 0.0), ctr)
+        R.createRestirUniformBuffer()
+        tot = 0.0
+        for f in range(frames):
+            R.CameraManip.setLookat(orbit_eye(ctr, 1.25 * diag, 0.0, 30.0 * f), ctr)     # spread over the orbit
+            R.renderFrame(clock=f)
+            if f >= 2:
+                tot += R.timings().frame_ms
+        R.destroy()
+        t = torch.tensor([tot / (frames - 2)], device="cuda", dtype=torch.float64)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        times = np.array([float(x[0]) for x in allt])
+        model = np.array([cost[b[0]:b[1]].sum() for b in bands])
+        corr = times / np.maximum(model, 1e-30)
+        corr = corr / corr.mean()
+        for (y0, y1), c in zip(bands, corr):
+            cost[y0:y1] *= 0.5 * (1.0 + c)                                               # damped
+        bands = split_rows(cost, world)
+    return bands
 
 
 def run_ours(args):
@@ -176,7 +219,7 @@ def run_ours(args):
     path = asset_path(V, wl["asset"])
     if dist is not None:
         dist.barrier()       # the stand-in asset (if any) is on disk for every rank
-    bands = balanced_bands(V, wl, path, world, local) if world > 1 else [(0, H)]
+    bands = calibrated_bands(V, wl, path, world, rank, local, dist) if world > 1 else [(0, H)]
     band = bands[rank] if world > 1 else None
     R = V.Renderer(W, H, spatial_iterations=wl["iters"], band=band, halo_rows=32, device=local)
     R.loadVDB(path)
@@ -318,7 +361,7 @@ def run_ours(args):
             "metric": "ReSTIR frames/s", "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_desc(wl),
             "config": {"workload": wl["desc"], "name": args.workload, "resolution": [W, H], "M": wl["M"], "lights": wl["lights"], "flags": wl["flags"],
-                       "spatial_iterations": wl["iters"], "partition": ("cost-balanced bands x%d %s, halo 32 rows" % (world, [b[1] - b[0] for b in bands])) if world > 1 else "single GPU",
+                       "spatial_iterations": wl["iters"], "partition": ("cost-balanced bands (hit-count model corrected by 3 timed calibration rounds) x%d %s, halo 32 rows" % (world, [b[1] - b[0] for b in bands])) if world > 1 else "single GPU",
                        "l2": "per-frame working set %.0f MB > 126 MB L2 (inputs larger than L2, no flush)" % (px * 240 / 1e6)},
             "mpixels_per_s": round(px * fps / 1e6, 1), "mpixel_samples_per_s": round(px * wl["M"] * fps / 1e6, 1),
             "frame_hbm_gbs": round(frame_bytes * fps / 1e9, 1), "frame_hbm_frac": round(frame_bytes * fps / 1e9 / peak, 4),

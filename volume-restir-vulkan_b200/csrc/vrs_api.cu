@@ -563,12 +563,17 @@ static vrs_status enqueue_initial(vrs_ctx* ctx, const FrameParams& F, cudaEvent_
   ctx->src_r = out; ctx->timings.launches += (uint32_t)initial_pass_launches(F.flags, F.cull && !ctx->trace && !getenv("VRS_NO_CULL"));
   return VRS_OK;
 }
-static vrs_status enqueue_spatial(vrs_ctx* ctx, uint32_t iteration) {
+// part 0: every row; 1: rows whose neighbourhood lies inside the band (no halo needed); 2: the rest.  The reservoir
+// ping-pong advances after part 0 or 2.
+static vrs_status enqueue_spatial(vrs_ctx* ctx, uint32_t iteration, int part = 0) {
   int dst = (ctx->src_r + 1) % 3;
+  const int halo = ctx->cfg.halo_rows;
+  const int ylo = ctx->peer_up.present ? ctx->band_y0 + halo : ctx->band_y0, yhi = ctx->peer_down.present ? ctx->band_y1 - halo : ctx->band_y1;
   launch_spatial(ctx->stream, ctx->lights, ctx->d_params, planes_of(ctx, ctx->cur_g), res_of(ctx, ctx->src_r), res_of(ctx, dst), ctx->queues,
-                 iteration, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks);
+                 iteration, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks, part, ylo, yhi);
   CK(cudaGetLastError());
-  ctx->src_r = dst; ctx->timings.launches += 1;
+  if (part != 1) ctx->src_r = dst;
+  ctx->timings.launches += 1;
   return VRS_OK;
 }
 static vrs_status enqueue_shade(vrs_ctx* ctx, const FrameParams& F) {
@@ -619,12 +624,25 @@ static vrs_status enqueue_frame(vrs_ctx* ctx, const FrameParams& F) {
   }
   if ((s = enqueue_initial(ctx, F, halo_in_flight && !ctx->peer_mode ? ctx->ev_halo_done : nullptr, halo_in_flight && ctx->peer_mode))) return s;   // main.cpp:405-409
   CK(mark(ctx, 1));
-  if (multi && spatial && (s = exchange(ctx, true, ctx->cur_g, ctx->src_r, true))) return s;
+  // Optional (VRS_SPLIT_SPATIAL=1, peer-memory mode): split every spatial iteration by rows - the rows whose neighbourhood
+  // lies inside the band run while the halo rows are in flight, the wait for the neighbours' flags comes after them, then
+  // the rows next to the band edges.  Bit-identical (tests/test_gpu_multi.py ran with it), but measured slower on 2 B200
+  // (4K, 1.43 ms vs 1.36 ms per frame): the second pass over the hit list and the thin boundary launch cost more than the
+  // wait they hide, so it is off by default.
+  static const bool no_split = !(getenv("VRS_SPLIT_SPATIAL") && getenv("VRS_SPLIT_SPATIAL")[0] == '1');
+  const bool split = multi && spatial && ctx->peer_mode && !no_split && spatial_supports_row_split() && F.spatialRadius <= (float)ctx->cfg.halo_rows;
+  if (multi && spatial && (s = exchange(ctx, true, ctx->cur_g, ctx->src_r, !split))) return s;
   CK(mark(ctx, 2));
   if (spatial) {
     for (uint32_t it = 0; it < ctx->cfg.spatial_iterations; ++it) {                                   // main.cpp:410-413
-      if ((s = enqueue_spatial(ctx, it))) return s;
-      if (multi && it + 1 < ctx->cfg.spatial_iterations && (s = exchange(ctx, false, 0, ctx->src_r, true))) return s;
+      if (split) {
+        if ((s = enqueue_spatial(ctx, it, 1))) return s;
+        launch_halo_wait(ctx->stream, ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4);
+        CK(cudaGetLastError());
+        ctx->timings.launches += 1;
+        if ((s = enqueue_spatial(ctx, it, 2))) return s;
+      } else if ((s = enqueue_spatial(ctx, it))) return s;
+      if (multi && it + 1 < ctx->cfg.spatial_iterations && (s = exchange(ctx, false, 0, ctx->src_r, !split))) return s;
     }
   }
   CK(mark(ctx, 3));

@@ -653,12 +653,15 @@ __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FramePa
 // -------------------------------------------------------------------------------------------------
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) k_spatial_thread(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes inR, ResPlanes outR,
-                                                 Queues Q, uint32_t iteration, int store_y0, int store_y1) {
+                                                 Queues Q, uint32_t iteration, int store_y0, int store_y1, int part, int ylo, int yhi) {
   const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
     const uint32_t idx = Q.hit_pix[s];
     const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
+    // multi-GPU: part 1 = only rows [ylo, yhi) whose neighbourhood lies inside the band (runs while the halo rows are
+    // still in flight), part 2 = only the rows outside it (after the halo wait); part 0 = every row
+    if (part != 0 && ((y >= ylo && y < yhi) != (part == 1))) continue;
     uint32_t seed = pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_SPATIAL0 + iteration);   // :58-59
     Res res = unpackReservoir(inR.info[idx], inR.weight[idx]);
     GInfo gi = ginfo_from_planes(cur, idx, F.camPos);
@@ -1069,12 +1072,13 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   if (needs_finish && peer_wait) k_halo_wait<<<1, 1, 0, st>>>(peer_wait[0], peer_wait[1], peer_wait[2], const_cast<unsigned*>(peer_wait[3]));
   if (needs_finish) k_finish<<<g_finish, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1);
 }
+bool spatial_supports_row_split() { return !(getenv("VRS_SPATIAL") && getenv("VRS_SPATIAL")[0] == 'c'); }
 int initial_pass_launches(int flags, bool culling) {
   const bool vis = (flags & FLAG_VISIBILITY) != 0, temporal = (flags & FLAG_TEMPORAL) != 0;
   return 4 /* classify, primary, compact, one RIS form doing the work */ + (culling ? 1 : 0) + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
 }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
-                    uint32_t iteration, int store_y0, int store_y1, int persistent_blocks) {
+                    uint32_t iteration, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi) {
   static const bool thread_form = !(getenv("VRS_SPATIAL") && getenv("VRS_SPATIAL")[0] == 'c');
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   static const int target_warps = sms * (getenv("VRS_MIN_WARPS_PER_SM") ? atoi(getenv("VRS_MIN_WARPS_PER_SM")) : MIN_WARPS_PER_SM);
@@ -1086,9 +1090,9 @@ void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, P
   static const int minb = getenv("VRS_SPATIAL_MINB") ? atoi(getenv("VRS_SPATIAL_MINB")) : 8;
   static const bool one_wave = !getenv("VRS_NO_ONE_WAVE");
   static const int g8 = one_wave ? resident_grid(k_spatial_thread<8>, 128, 8) : persistent_blocks, g7 = one_wave ? resident_grid(k_spatial_thread<7>, 128, 7) : persistent_blocks;
-  if (thread_form && minb >= 8) k_spatial_thread<8><<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1);
-  else if (thread_form) k_spatial_thread<7><<<g7, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1);
-  else k_spatial_coop<<<coop_blocks, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, target_warps);
+  if (thread_form && minb >= 8) k_spatial_thread<8><<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
+  else if (thread_form) k_spatial_thread<7><<<g7, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
+  else if (part != 2) k_spatial_coop<<<coop_blocks, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, target_warps);   // (no row split: part 1 does all)
 }
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, ResPlanes rs,
                   float4* accum, int y0, int y1, int store_y0) {
