@@ -165,3 +165,23 @@ def test_band_split(V):
         bands = [V.band_for_rank(h, r, n) for r in range(n)]
         assert bands[0][0] == 0 and bands[-1][1] == h
         assert all(bands[i][1] == bands[i + 1][0] for i in range(n - 1))
+
+
+def test_bench_row_split_balances_cost_and_keeps_halo():
+    """bench.py's band splitter: equal shares of the per-row cost, every band at least as tall as the halo."""
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    H = 1080
+    y = np.arange(H)
+    cost = 1.0 + 50.0 * np.exp(-((y - 600.0) / 120.0) ** 2)          # a bump of expensive rows
+    for world in (2, 4, 8):
+        bands = bench.split_rows(cost.copy(), world)
+        assert bands[0][0] == 0 and bands[-1][1] == H and all(b[1] == n[0] for b, n in zip(bands, bands[1:]))
+        assert all(b[1] - b[0] >= 32 for b in bands)
+        shares = np.array([cost[b[0]:b[1]].sum() for b in bands])
+        assert shares.max() / shares.mean() < 1.15
+    flat = bench.split_rows(np.zeros(H) + 1e-9, 8)                    # degenerate cost: still a valid partition
+    assert flat[0][0] == 0 and flat[-1][1] == H and all(b[1] - b[0] >= 32 for b in flat)
