@@ -85,9 +85,55 @@ def _read_metamap(s):
 COMPRESS_ZIP, COMPRESS_ACTIVE_MASK, COMPRESS_BLOSC = 1, 2, 4
 
 
+def _blosc_decode(chunk, nbytes_expected):
+    """Blosc 1.x chunk (io::bloscFromStream -> blosc_decompress_ctx), restated: 16-byte header, block starts, per block
+    `typesize` split streams (or one), byte unshuffle.  LZ4 streams go through pyarrow's lz4_raw codec, so this reader shares
+    no decompression code with the product's C++ one."""
+    import pyarrow as pa
+    flags, typesize = chunk[2], chunk[3] or 1
+    nbytes, blocksize, cbytes = struct.unpack_from("<III", chunk, 4)
+    if nbytes != nbytes_expected or cbytes > len(chunk):
+        raise ValueError("vdb: Blosc chunk header inconsistent with the buffer")
+    if flags & 0x2:
+        return bytes(chunk[16:16 + nbytes])
+    codec = flags >> 5
+    if flags & 0x4 or codec not in (1, 3):
+        raise NotImplementedError("vdb: Blosc chunk with bit shuffle or a codec other than LZ4 / zlib")
+    shuffle, dont_split = bool(flags & 1) and typesize > 1, bool(flags & 0x10)
+    nblocks = (nbytes + blocksize - 1) // blocksize if nbytes else 0
+    out = bytearray()
+    for j in range(nblocks):
+        bsize = min(blocksize, nbytes - j * blocksize)
+        leftover = bsize != blocksize
+        nsplits = typesize if (not dont_split and typesize <= 16 and bsize // typesize >= 128 and not leftover) else 1
+        neblock = bsize // nsplits
+        p = struct.unpack_from("<I", chunk, 16 + 4 * j)[0]
+        block = bytearray()
+        for _ in range(nsplits):
+            cb = struct.unpack_from("<I", chunk, p)[0]
+            p += 4
+            part = bytes(chunk[p:p + cb])
+            p += cb
+            if cb == neblock:
+                block += part
+            elif codec == 1:
+                block += pa.decompress(part, decompressed_size=neblock, codec="lz4_raw", asbytes=True)
+            else:
+                block += zlib.decompress(part)
+        if shuffle:
+            nelem = bsize // typesize
+            planes = np.frombuffer(bytes(block[:nelem * typesize]), np.uint8).reshape(typesize, nelem)
+            block = bytearray(planes.T.tobytes()) + block[nelem * typesize:]
+        out += block
+    return bytes(out)
+
+
 def _read_raw_block(s, nbytes, compression):
     if compression & COMPRESS_BLOSC:
-        raise NotImplementedError("vdb: Blosc-compressed buffers are not supported")
+        zipped = s.i64()
+        if zipped <= 0:
+            return s.read(-zipped)
+        return _blosc_decode(s.read(zipped), nbytes)
     if compression & COMPRESS_ZIP:
         zipped = s.i64()
         if zipped <= 0:

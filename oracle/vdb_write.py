@@ -8,7 +8,7 @@ import zlib
 
 import numpy as np
 
-COMPRESS_ZIP, COMPRESS_ACTIVE_MASK = 1, 2
+COMPRESS_ZIP, COMPRESS_ACTIVE_MASK, COMPRESS_BLOSC = 1, 2, 4
 
 
 def _s(x):
@@ -39,7 +39,46 @@ def _mask_bytes(bits):
     return np.packbits(np.asarray(bits, bool), bitorder="little").tobytes()
 
 
+BLOSC_MODE = {"mode": "openvdb"}     # how _blosc_chunk lays the next chunks out (tests switch it)
+
+
+def _blosc_chunk(raw, mode):
+    """A Blosc 1.x chunk of `raw`.  Modes: "openvdb" = what io::bloscToStream produces (LZ4, byte shuffle, typesize 4,
+    blocksize = the buffer rounded down to the typesize, split streams); "nosplit" (flag 0x10); "blocks" (several
+    2 KB blocks + a leftover block); "zlib" (codec 3); "memcpy" (stored chunk).  LZ4 streams come from pyarrow's codec."""
+    import pyarrow as pa
+    typesize, n = 4, len(raw)
+    if mode == "memcpy":
+        return struct.pack("<BBBBIII", 2, 1, 0x1 | 0x2, typesize, n, n, n + 16) + raw
+    codec = 3 if mode == "zlib" else 1
+    flags = 0x1 | (codec << 5) | (0x10 if mode == "nosplit" else 0)
+    blocksize = 2048 if mode == "blocks" else max(n // typesize * typesize, typesize)
+    nblocks = (n + blocksize - 1) // blocksize
+    body, starts = b"", []
+    for j in range(nblocks):
+        blk = raw[j * blocksize:(j + 1) * blocksize]
+        bsize, leftover = len(blk), len(blk) != blocksize
+        nelem = bsize // typesize
+        shuf = np.frombuffer(blk[:nelem * typesize], np.uint8).reshape(nelem, typesize).T.tobytes() + blk[nelem * typesize:]
+        nsplits = typesize if (mode != "nosplit" and bsize // typesize >= 128 and not leftover) else 1
+        neblock = bsize // nsplits
+        starts.append(16 + 4 * nblocks + len(body))
+        for k in range(nsplits):
+            part = shuf[k * neblock:(k + 1) * neblock]
+            z = zlib.compress(part, 6) if codec == 3 else pa.compress(part, codec="lz4_raw", asbytes=True)
+            if len(z) >= len(part):
+                z = part                                   # stored split stream: cbytes == its raw size
+            body += struct.pack("<I", len(z)) + z
+    head = struct.pack("<BBBBIII", 2, 1, flags, typesize, n, blocksize, 16 + 4 * nblocks + len(body))
+    return head + b"".join(struct.pack("<I", x) for x in starts) + body
+
+
 def _block(raw, compression):
+    if compression & COMPRESS_BLOSC:                       # io::bloscToStream
+        if len(raw) <= 48 or BLOSC_MODE["mode"] == "raw":  # BLOSC_MINIMUM_BYTES: stored with a negative size
+            return struct.pack("<q", -len(raw)) + raw
+        c = _blosc_chunk(raw, BLOSC_MODE["mode"])
+        return struct.pack("<q", len(c)) + c
     if compression & COMPRESS_ZIP:
         z = zlib.compress(raw, 6)
         if len(z) < len(raw):

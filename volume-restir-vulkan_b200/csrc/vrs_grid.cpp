@@ -3,7 +3,8 @@
 // :741-904 getMeshValuesScalar, :1179-1200 loadBBox; src/loaders/VDBLoader.cpp:5-70) — the reference links
 // OpenVDB >= 8 (README.md:36, CMakeLists.txt:61), which this image does not have, so the published on-disk
 // format is parsed directly: file versions 222-224, Tree_float_5_4_3[_HalfFloat], node-mask compression,
-// optional ZIP blocks (zlib).  Blosc blocks are rejected with VRS_ERR_FORMAT.
+// optional ZIP blocks (zlib) or Blosc chunks (c-blosc 1.x container: LZ4 / zlib codecs, byte shuffle, split blocks;
+// decoded here, no libblosc).  Other Blosc codecs (BloscLZ, Snappy, Zstd, bit shuffle) are rejected with VRS_ERR_FORMAT.
 #include "vrs_grid.h"
 
 #include <zlib.h>
@@ -146,11 +147,89 @@ void skip_metamap(Reader& r, std::map<std::string, std::string>* strings) {
   }
 }
 
+// ---- Blosc 1.x chunk decoder (what openvdb::io::bloscFromStream hands to blosc_decompress_ctx).  OpenVDB compresses with
+// blosc_compress_ctx(clevel 9, byte shuffle, typesize sizeof(float), "lz4", blocksize = the whole buffer), but everything is
+// read from the 16-byte chunk header, so any LZ4- or zlib-coded chunk decodes:
+//   [0] format version [1] codec version [2] flags: 1 byte shuffle, 2 stored (memcpy), 4 bit shuffle, 0x10 blocks not
+//   split, bits 5-7 codec (0 BloscLZ, 1 LZ4/LZ4HC, 2 Snappy, 3 zlib, 4 Zstd) [3] typesize | u32 nbytes | u32 blocksize |
+//   u32 cbytes | i32 bstarts[nblocks] | per block: per split stream i32 cbytes (== its raw size: stored) + bytes.
+static bool lz4_block_decode(const uint8_t* s, size_t n, uint8_t* d, size_t m) {
+  size_t i = 0, o = 0;
+  while (i < n) {
+    const unsigned tok = s[i++];
+    size_t lit = tok >> 4;
+    if (lit == 15) { uint8_t b; do { if (i >= n) return false; b = s[i++]; lit += b; } while (b == 255); }
+    if (i + lit > n || o + lit > m) return false;
+    memcpy(d + o, s + i, lit); i += lit; o += lit;
+    if (i >= n) break;                                   // the last sequence ends after its literals
+    if (i + 2 > n) return false;
+    const size_t off = (size_t)s[i] | ((size_t)s[i + 1] << 8); i += 2;
+    if (off == 0 || off > o) return false;
+    size_t ml = tok & 15;
+    if (ml == 15) { uint8_t b; do { if (i >= n) return false; b = s[i++]; ml += b; } while (b == 255); }
+    ml += 4;
+    if (o + ml > m) return false;
+    for (size_t k = 0; k < ml; ++k) d[o + k] = d[o + k - off];   // may overlap its own output
+    o += ml;
+  }
+  return o == m;
+}
+static bool blosc_chunk_decode(const uint8_t* src, size_t srclen, uint8_t* dst, size_t dstlen, std::string& err) {
+  auto u32 = [&](size_t p) { uint32_t v; memcpy(&v, src + p, 4); return v; };
+  if (srclen < 16) { err = "Blosc chunk shorter than its header"; return false; }
+  const unsigned flags = src[2], typesize = src[3] ? src[3] : 1;
+  const size_t nbytes = u32(4), blocksize = u32(8), cbytes = u32(12);
+  if (nbytes != dstlen || cbytes > srclen || (nbytes && blocksize == 0)) { err = "Blosc chunk header inconsistent with the buffer"; return false; }
+  if (flags & 0x2) {                                     // stored
+    if (16 + nbytes > srclen) { err = "Blosc chunk truncated"; return false; }
+    memcpy(dst, src + 16, nbytes); return true;
+  }
+  if (flags & 0x4) { err = "Blosc bit-shuffled chunks are not supported"; return false; }
+  const unsigned codec = flags >> 5;
+  if (codec != 1 && codec != 3) { err = "Blosc codec other than LZ4 / zlib is not supported (OpenVDB writes LZ4)"; return false; }
+  const bool shuffle = (flags & 0x1) && typesize > 1, dont_split = (flags & 0x10) != 0;
+  const size_t nblocks = nbytes ? (nbytes + blocksize - 1) / blocksize : 0;
+  if (16 + 4 * nblocks > srclen) { err = "Blosc chunk truncated"; return false; }
+  std::vector<uint8_t> tmp(blocksize);
+  for (size_t j = 0; j < nblocks; ++j) {
+    const size_t bsize = (j + 1) * blocksize <= nbytes ? blocksize : nbytes - j * blocksize;
+    const bool leftover = bsize != blocksize;
+    const size_t nsplits = (!dont_split && typesize <= 16 && bsize / typesize >= 128 && !leftover) ? typesize : 1;
+    const size_t neblock = bsize / nsplits;
+    size_t p = u32(16 + 4 * j);
+    uint8_t* out = shuffle ? tmp.data() : dst + j * blocksize;
+    for (size_t k = 0; k < nsplits; ++k) {
+      if (p + 4 > srclen) { err = "Blosc chunk truncated"; return false; }
+      const size_t cb = u32(p); p += 4;
+      if (p + cb > srclen) { err = "Blosc chunk truncated"; return false; }
+      if (cb == neblock) memcpy(out + k * neblock, src + p, neblock);
+      else if (codec == 1) { if (!lz4_block_decode(src + p, cb, out + k * neblock, neblock)) { err = "Blosc chunk: LZ4 stream corrupt"; return false; } }
+      else { uLongf dl = (uLongf)neblock; if (uncompress(out + k * neblock, &dl, src + p, (uLong)cb) != Z_OK || dl != neblock) { err = "Blosc chunk: zlib stream corrupt"; return false; } }
+      p += cb;
+    }
+    if (shuffle) {                                       // byte planes -> elements; a tail shorter than one element is copied
+      uint8_t* d = dst + j * blocksize;
+      const size_t nelem = bsize / typesize;
+      for (size_t b = 0; b < typesize; ++b) for (size_t e = 0; e < nelem; ++e) d[e * typesize + b] = tmp[b * nelem + e];
+      memcpy(d + nelem * typesize, tmp.data() + nelem * typesize, bsize - nelem * typesize);
+    }
+  }
+  return true;
+}
+
 // io::readData: one block of `count` values of `item` bytes, optionally zipped
 bool read_block(Ctx& c, size_t count, size_t item, std::vector<uint8_t>& out) {
   out.resize(count * item);
   uint32_t comp = c.g->compression;
-  if (comp & COMPRESS_BLOSC) { c.err = "Blosc-compressed VDB buffers are not supported"; return false; }
+  if (comp & COMPRESS_BLOSC) {                           // io::bloscFromStream: i64 size (<= 0: stored raw), chunk
+    int64_t zipped = c.r.get<int64_t>();
+    if (zipped <= 0) { c.r.raw(out.data(), (size_t)(-zipped) < out.size() ? (size_t)(-zipped) : out.size()); return c.r.ok; }
+    c.r.need((size_t)zipped);
+    if (!c.r.ok) return false;
+    if (!blosc_chunk_decode(c.r.d + c.r.p, (size_t)zipped, out.data(), out.size(), c.err)) return false;
+    c.r.p += (size_t)zipped;
+    return true;
+  }
   if (comp & COMPRESS_ZIP) {
     int64_t zipped = c.r.get<int64_t>();
     if (zipped <= 0) { c.r.raw(out.data(), (size_t)(-zipped) < out.size() ? (size_t)(-zipped) : out.size()); return c.r.ok; }
