@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(256) k_hit_compact(const uint8_t* __restrict__
 
 // Reference form of the RIS stage: one thread per hit pixel runs the M-candidate loop serially (kept selectable with
 // VRS_RIS=thread for A/B measurements; k_ris_coop below is the default and produces the same bits).
-__global__ void __launch_bounds__(128) k_ris_thread(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_ris_thread(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
                                              Queues Q, uint32_t* __restrict__ trace, int store_y0, int needs_finish, uint32_t min_hits) {
   const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
@@ -237,13 +238,26 @@ __global__ void __launch_bounds__(128) k_ris_thread(const GridDev G, const Light
     Res res = newReservoir();
     if (dot(gi.normal, gi.normal) != 0.0f) {                                                           // :205
       const ShadePre pre = shade_pre(gi);
+      uint32_t selM = 0u; float selSumW = 0.0f;
       for (uint32_t c = 0; c < F.M; ++c) {                                                             // :206-226
-        gi.sampleSeed = seed;                                                                          // :213
+        const uint32_t sampleSeed = seed;                                                              // :213
         float r1 = rnd(seed), r2 = rnd(seed);                                                          // :116, GLSL left-to-right
         uint32_t sel; float pdf;
         aliasTableSample(L, r1, r2, sel, pdf);
-        addSampleToReservoir(L, res, sel, 0, pdf, gi, pre, seed);                                      // :224-225
+        // addSampleToReservoir + updateReservoir (reservoir.glsl:45-54, 30-43).  The w the reference forms for every
+        // candidate, (sumW + weight) / (M * pHat), only survives for the selected one: remember its sumW and M and do
+        // that division once after the loop (same operands, same result).
+        const float pHat = evaluatePHat(L, sel, gi, pre);
+        const float weight = pHat / pdf;
+        res.M += 1;
+        res.sumWeights += weight;
+        const float replacePossibility = weight / res.sumWeights;
+        if (rnd(seed) < replacePossibility) {
+          res.lightIndex = sel; res.lightKind = 0; res.pHat = pHat; res.sampleSeed = sampleSeed;
+          selM = res.M; selSumW = res.sumWeights;
+        }
       }
+      if (selM != 0u) res.w = selSumW / (float(selM) * res.pHat);                                      // reservoir.glsl:51
     }
     if ((F.flags & FLAG_FINALIZE_W) != 0 && res.w > 0.0f) res.w = res.sumWeights / (float(res.M) * res.pHat);
     float4 a, b; packReservoir(res, a, b);
@@ -1057,14 +1071,16 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   const bool vis = (F.flags & FLAG_VISIBILITY) != 0, temporal = (F.flags & FLAG_TEMPORAL) != 0;
   const int needs_finish = (vis || temporal) ? 1 : 0;
   static const bool one_wave = !getenv("VRS_NO_ONE_WAVE");
-  static const int g_thread = one_wave ? resident_grid(k_ris_thread, 128, 8) : persistent_blocks, g_prefetch = one_wave ? resident_grid(k_ris_prefetch, 128, 6) : persistent_blocks;
+  static const int ris_minb = getenv("VRS_RIS_MINB") ? atoi(getenv("VRS_RIS_MINB")) : 8;
+  static const int g_thread = one_wave ? (ris_minb >= 8 ? resident_grid(k_ris_thread<8>, 128, 8) : resident_grid(k_ris_thread<7>, 128, 7)) : persistent_blocks, g_prefetch = one_wave ? resident_grid(k_ris_prefetch, 128, 6) : persistent_blocks;
   static const int g_finish = one_wave ? resident_grid(k_finish, 128, 8) : persistent_blocks;
-  if (ris_env == 't') k_ris_thread<<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, 0u);
+  if (ris_env == 't') { if (ris_minb >= 8) k_ris_thread<8><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, 0u); else k_ris_thread<7><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, 0u); }
   else if (ris_env == 'p') k_ris_prefetch<<<g_prefetch, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
   else if (ris_env == 'c' || big_tables) k_ris_coop<<<ris_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, target_warps, 0xFFFFFFFFu);
   else {   // auto, small tables: the hit count (known only on the device) picks the form; the other launch returns at once
     k_ris_coop<<<ris_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, target_warps, small_launch);
-    k_ris_thread<<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
+    if (ris_minb >= 8) k_ris_thread<8><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
+    else k_ris_thread<7><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
   }
   if (vis) k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill);
   // the previous frame's halo rows (multi-GPU) are only needed by the temporal merge: everything above overlapped their exchange
