@@ -200,6 +200,25 @@ def calibrated_bands(V, wl, path, world, rank, device, dist, lights_ctr_diag=Non
     return bands
 
 
+def issue_roofline(tj, fps, clocks, workload, world):
+    """The frame is instruction-issue bound, not HBM bound: besides the contract's HBM roofline, report how
+    much of the SMs' issue capacity the frame uses.  Warp instructions per frame come from the committed ncu launch list
+    of the default workload (profiles/traffic.json), the frame rate and the SM clock are measured live.  None when the
+    inputs do not apply (other workload, several GPUs, no clock sample)."""
+    try:
+        if workload != "smoke_1080p_temporal" or world != 1 or not clocks or not clocks.get("sm_mhz"):
+            return None
+        winst = sum(float(k_["warp_inst_M"]) for k_ in tj.get("per_kernel", {}).values()) * 1e6
+        if winst <= 0:
+            return None
+        peak_issue = 148 * 4 * float(clocks["sm_mhz"]) * 1e6            # 4 warp schedulers per SM, one instruction per clock each
+        return {"warp_instructions_per_frame": int(winst), "achieved_ginst_s": round(winst * fps / 1e9, 1),
+                "peak_ginst_s": round(peak_issue / 1e9, 1), "frac": round(winst * fps / peak_issue, 4),
+                "source": "profiles/traffic.json (ncu smsp__inst_executed.sum per kernel) x live frames/s; peak = 148 SMs x 4 schedulers x measured SM clock"}
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import vrs_pkg
@@ -354,9 +373,12 @@ def run_ours(args):
         frame_bytes = px * (BYTES_PER_PX["initial"] + (BYTES_PER_PX["temporal"] if temporal else 0) + BYTES_PER_PX["shade"] +
                             (BYTES_PER_PX["spatial_iter"] * wl["iters"] if wl["flags"] & 4 else 0))
         traffic = None
+        issue = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("k_initial_dram_bytes_per_launch")
+            tj = json.load(open(tp))
+            traffic = tj.get("k_initial_dram_bytes_per_launch")
+            issue = issue_roofline(tj, fps, clocks, args.workload, world)
         line = {
             "metric": "ReSTIR frames/s", "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_desc(wl),
@@ -375,6 +397,7 @@ def run_ours(args):
                     "rgba32f_sync_readback_ms_per_step": round(e2e_f32_ms, 4)},
             "gpu_launches": int(launches * args.steps), "clocks": clocks, "wall_s": round(t_wall, 3),
             "per_rank_initial_ms": per_rank_initial if world > 1 else None,
+            "issue_roofline": issue,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(args.workload, frames=args.cpu_frames)

@@ -185,3 +185,22 @@ def test_bench_row_split_balances_cost_and_keeps_halo():
         assert shares.max() / shares.mean() < 1.15
     flat = bench.split_rows(np.zeros(H) + 1e-9, 8)                    # degenerate cost: still a valid partition
     assert flat[0][0] == 0 and flat[-1][1] == H and all(b[1] - b[0] >= 32 for b in flat)
+
+
+def test_bench_issue_roofline_helper():
+    """bench.py's extra "issue_roofline" object: warp instructions per frame (committed ncu launch list) x live frames/s
+    over 148 SMs x 4 schedulers x SM clock; None whenever its inputs do not apply, never an exception."""
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    tj = json.load(open(os.path.join(root, "profiles", "traffic.json")))
+    r = bench.issue_roofline(tj, 2000.0, {"sm_mhz": 1965.0}, "smoke_1080p_temporal", 1)
+    want = sum(k["warp_inst_M"] for k in tj["per_kernel"].values()) * 1e6 * 2000.0 / (148 * 4 * 1965.0e6)
+    assert r is not None and abs(r["frac"] - want) < 1e-3 and 0.0 < r["frac"] < 1.0
+    assert bench.issue_roofline(tj, 2000.0, None, "smoke_1080p_temporal", 1) is None
+    assert bench.issue_roofline(tj, 2000.0, {"sm_mhz": 1965.0}, "bunny_4k_full", 1) is None
+    assert bench.issue_roofline(tj, 2000.0, {"sm_mhz": 1965.0}, "smoke_1080p_temporal", 8) is None
+    assert bench.issue_roofline({"per_kernel": {"k": {}}}, 2000.0, {"sm_mhz": 1965.0}, "smoke_1080p_temporal", 1) is None

@@ -1089,9 +1089,13 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   if (needs_finish) k_finish<<<g_finish, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1);
 }
 bool spatial_supports_row_split() { return !(getenv("VRS_SPATIAL") && getenv("VRS_SPATIAL")[0] == 'c'); }
-int initial_pass_launches(int flags, bool culling) {
+int initial_pass_launches(int flags, bool culling, const LightsDev& L) {
   const bool vis = (flags & FLAG_VISIBILITY) != 0, temporal = (flags & FLAG_TEMPORAL) != 0;
-  return 4 /* classify, primary, compact, one RIS form doing the work */ + (culling ? 1 : 0) + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
+  // auto mode with small light tables launches both RIS forms (the device-side hit count decides which one works)
+  const char ris_env = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'a';
+  const bool big_tables = (size_t)L.nlights * 32 + (size_t)L.ntable * 16 > (size_t)64 * 1024;
+  const int ris = (ris_env == 'a' && !big_tables) ? 2 : 1;
+  return 3 /* classify, primary, compact */ + ris + (culling ? 1 : 0) + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
 }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi) {

@@ -15,7 +15,7 @@ struct HaloPush;
 void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, Planes prev,
                     ResPlanes prevR, ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1,
                     int persistent_blocks, cudaEvent_t prev_halo_ready, const unsigned* const* peer_wait);
-int initial_pass_launches(int flags, bool culling);
+int initial_pass_launches(int flags, bool culling, const LightsDev& L);
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi);
 bool spatial_supports_row_split();
