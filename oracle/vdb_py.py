@@ -335,14 +335,24 @@ def read_vdb(path, grid_name=None):
         map_type = s.string()
         if map_type == "UniformScaleMap" or map_type == "ScaleMap":
             v = [s.vec3d() for _ in range(5)]
-            g.voxel_size = v[0][0]
+            scale = v[0]
             g.translation = (0.0, 0.0, 0.0)
         elif map_type == "UniformScaleTranslateMap" or map_type == "ScaleTranslateMap":
             v = [s.vec3d() for _ in range(6)]
             g.translation = v[0]
-            g.voxel_size = v[1][0]
+            scale = v[1]
+        elif map_type == "AffineMap":                       # Mat4d, row-major, row-vector convention (translation = last row)
+            m = np.array(struct.unpack("<16d", s.read(128))).reshape(4, 4)
+            scale = (m[0, 0], m[1, 1], m[2, 2])
+            off = m[:3, :3] - np.diag(scale)
+            if np.abs(off).max() > 1e-9 * abs(scale[0]) or np.abs(m[:3, 3]).max() > 0 or abs(m[3, 3] - 1.0) > 1e-12:
+                raise NotImplementedError("vdb: AffineMap with rotation / shear / projection")
+            g.translation = tuple(m[3, :3])
         else:
             raise NotImplementedError("vdb: map type %s" % map_type)
+        if not (scale[0] > 0 and abs(scale[1] - scale[0]) <= 1e-9 * scale[0] and abs(scale[2] - scale[0]) <= 1e-9 * scale[0]):
+            raise NotImplementedError("vdb: non-uniform voxel size %r" % (scale,))
+        g.voxel_size = scale[0]
         # ---- topology (Tree::readTopology / RootNode::readTopology)
         _buffer_count = s.i32()
         g.background = struct.unpack("<f", s.read(4))[0]

@@ -132,9 +132,13 @@ class Grid:
     tiles [(origin, log2dim in {3,7,12}, value, active)]."""
 
     def __init__(self, name, background=0.0, half=False, compression=COMPRESS_ACTIVE_MASK, voxel_size=0.5, translation=None,
-                 grid_class="fog volume"):
+                 grid_class="fog volume", map_type=None, affine=None):
+        """`map_type` overrides the transform written ("ScaleMap", "ScaleTranslateMap", "AffineMap", or any name for error
+        tests); `affine` is the 4x4 row-major matrix of an AffineMap (row-vector convention: translation in the last row),
+        built from voxel_size / translation when omitted; `voxel_size` may be a 3-tuple for the non-uniform Scale maps."""
         self.name, self.background, self.half, self.compression = name, np.float32(background), half, compression
         self.voxel_size, self.translation, self.grid_class = voxel_size, translation, grid_class
+        self.map_type, self.affine = map_type, affine
         self.leaves, self.tiles = {}, []
 
     def set_leaf(self, origin, values, mask):
@@ -155,15 +159,23 @@ def _grid_bytes(g):
     """-> (topology+header bytes builder) ; returns (pre, topo, buffers)"""
     pre = struct.pack("<I", g.compression)
     pre += _meta({"class": ("string", g.grid_class), "name": ("string", g.name)})
-    vs = g.voxel_size
-    if g.translation is None:
-        pre += _s("UniformScaleMap")
-        vecs = [(vs,) * 3, (vs,) * 3, (1 / vs,) * 3, (1 / vs ** 2,) * 3, (0.5 / vs,) * 3]
+    vs3 = tuple(g.voxel_size) if isinstance(g.voxel_size, (tuple, list)) else (g.voxel_size,) * 3
+    scale_vecs = [vs3, vs3, tuple(1 / v for v in vs3), tuple(1 / v ** 2 for v in vs3), tuple(0.5 / v for v in vs3)]
+    if g.map_type == "AffineMap":                           # AffineMap::write: Mat4d, 16 doubles, row-major
+        m = g.affine
+        if m is None:
+            t = g.translation or (0.0, 0.0, 0.0)
+            m = [[vs3[0], 0, 0, 0], [0, vs3[1], 0, 0], [0, 0, vs3[2], 0], [t[0], t[1], t[2], 1.0]]
+        pre += _s("AffineMap") + struct.pack("<16d", *[float(x) for row in m for x in row])
     else:
-        pre += _s("UniformScaleTranslateMap")
-        vecs = [tuple(g.translation), (vs,) * 3, (vs,) * 3, (1 / vs,) * 3, (1 / vs ** 2,) * 3, (0.5 / vs,) * 3]
-    for v in vecs:
-        pre += struct.pack("<3d", *v)
+        if g.translation is None:
+            pre += _s(g.map_type or "UniformScaleMap")
+            vecs = scale_vecs
+        else:
+            pre += _s(g.map_type or "UniformScaleTranslateMap")
+            vecs = [tuple(g.translation)] + scale_vecs
+        for v in vecs:
+            pre += struct.pack("<3d", *v)
     bg = g.background
     # ---- organise the tree
     roots = {}

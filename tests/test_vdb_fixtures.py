@@ -155,6 +155,43 @@ def test_blosc_chunk_errors(V, tmp_path):
         V.convert_vdb(trunc, str(tmp_path / "trunc.vrsg"))
 
 
+def test_transform_maps(V, tmp_path):
+    """Every way OpenVDB serialises a uniform scale (+ translation): Uniform/ScaleMap, Uniform/ScaleTranslateMap and the
+    general AffineMap (what Houdini exports); non-uniform scale, rotation and frustum maps fail loudly in both readers."""
+    import grid_py
+    import vdb_py
+    import vdb_write as W
+
+    def grid(**kw):
+        g = W.Grid("density", background=0.0, **kw)
+        g.set_leaf((8, -8, 0), np.linspace(0.5, 1.5, 512), np.ones(512, bool))
+        return g
+
+    ok = [dict(voxel_size=0.25), dict(voxel_size=0.25, map_type="ScaleMap"), dict(voxel_size=0.125, translation=(1.0, -2.0, 3.5)),
+          dict(voxel_size=0.125, translation=(1.0, -2.0, 3.5), map_type="ScaleTranslateMap"),
+          dict(voxel_size=0.2, translation=(-4.0, 0.5, 9.0), map_type="AffineMap"), dict(voxel_size=0.2, map_type="AffineMap")]
+    for n, kw in enumerate(ok):
+        path, out = str(tmp_path / ("m%d.vdb" % n)), str(tmp_path / ("m%d.vrsg" % n))
+        W.write_vdb(path, [grid(**kw)])
+        pg = vdb_py.read_vdb(path)
+        V.convert_vdb(path, out)
+        sg = grid_py.read_vrsg(out)
+        want_t = kw.get("translation") or (0.0, 0.0, 0.0)
+        for g_ in (pg, sg):
+            assert abs(g_.voxel_size - kw["voxel_size"]) < 1e-12 and np.allclose(g_.translation, want_t), (kw, g_.voxel_size, g_.translation)
+    rot = [[0.0, 0.2, 0, 0], [-0.2, 0.0, 0, 0], [0, 0, 0.2, 0], [0, 0, 0, 1.0]]
+    bad = [dict(voxel_size=(0.25, 0.5, 0.25), map_type="ScaleMap"), dict(voxel_size=(0.25, 0.25, 0.3), translation=(0.0, 0.0, 1.0), map_type="ScaleTranslateMap"),
+           dict(voxel_size=0.2, map_type="AffineMap", affine=rot), dict(voxel_size=0.2, map_type="NonlinearFrustumMap")]
+    for n, kw in enumerate(bad):
+        path = str(tmp_path / ("b%d.vdb" % n))
+        W.write_vdb(path, [grid(**kw)])
+        with pytest.raises(V.VrsError) as e:
+            V.convert_vdb(path, str(tmp_path / "b.vrsg"))
+        assert e.value.status in (4, 5) and ("not supported" in str(e.value)), str(e.value)
+        with pytest.raises(NotImplementedError):
+            vdb_py.read_vdb(path)
+
+
 def test_grid_selection_by_name_and_errors(V, tmp_path):
     import grid_py
     import vdb_write as W

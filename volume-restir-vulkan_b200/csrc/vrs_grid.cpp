@@ -366,15 +366,29 @@ bool read_vdb(const std::string& path, const char* grid_name, HostGrid& out, std
     skip_metamap(r, &meta);
     out.level_set = meta.count("class") && meta["class"] == "level set";
     std::string map_type = r.str();
-    double v[6][3];
+    // The kernels place voxels with world = A * ijk + B (one scalar A): uniform scale (+ translation) maps, in any of the
+    // forms OpenVDB writes them; anything else (non-uniform scale, rotation, shear, frustum) fails loudly.
+    double v[6][3], scale[3] = {0, 0, 0};
     if (map_type == "UniformScaleMap" || map_type == "ScaleMap") {
       for (int k = 0; k < 5; ++k) r.raw(v[k], 24);
-      out.voxel_size = v[0][0];
+      for (int a = 0; a < 3; ++a) scale[a] = v[0][a];
     } else if (map_type == "UniformScaleTranslateMap" || map_type == "ScaleTranslateMap") {
       for (int k = 0; k < 6; ++k) r.raw(v[k], 24);
-      for (int a = 0; a < 3; ++a) out.translation[a] = v[0][a];
-      out.voxel_size = v[1][0];
+      for (int a = 0; a < 3; ++a) { out.translation[a] = v[0][a]; scale[a] = v[1][a]; }
+    } else if (map_type == "AffineMap") {                  // Mat4d, row-major, row-vector convention: translation in the last row
+      double m[16]; r.raw(m, 128);
+      for (int a = 0; a < 3; ++a) { scale[a] = m[a * 4 + a]; out.translation[a] = m[12 + a]; }
+      double off = 0.0;
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) if (i != j && std::fabs(m[i * 4 + j]) > off) off = std::fabs(m[i * 4 + j]);
+      if (off > 1e-9 * std::fabs(scale[0]) || m[3] != 0.0 || m[7] != 0.0 || m[11] != 0.0 || std::fabs(m[15] - 1.0) > 1e-12) {
+        err = "AffineMap with rotation / shear / projection is not supported (uniform scale + translation only)"; return false;
+      }
     } else { err = "transform map " + map_type + " is not supported"; return false; }
+    if (!r.ok) { err = "truncated VDB transform"; return false; }
+    if (!(scale[0] > 0.0) || std::fabs(scale[1] - scale[0]) > 1e-9 * scale[0] || std::fabs(scale[2] - scale[0]) > 1e-9 * scale[0]) {
+      err = "non-uniform voxel size is not supported"; return false;
+    }
+    out.voxel_size = scale[0];
     // Tree::readTopology / RootNode::readTopology
     r.get<int32_t>();                                    // buffer count
     out.background = r.get<float>();
