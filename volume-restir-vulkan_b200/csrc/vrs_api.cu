@@ -560,7 +560,7 @@ static vrs_status enqueue_initial(vrs_ctx* ctx, const FrameParams& F, cudaEvent_
                  res_of(ctx, ctx->final_r), res_of(ctx, out), ctx->queues, ctx->trace, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1,
                  ctx->persistent_blocks, prev_halo_ready, peer_wait ? pw : nullptr);
   CK(cudaGetLastError());
-  ctx->src_r = out; ctx->timings.launches += (uint32_t)initial_pass_launches(F.flags, F.cull && !ctx->trace && !getenv("VRS_NO_CULL"), ctx->lights);
+  ctx->src_r = out; ctx->timings.launches += (uint32_t)initial_pass_launches(F.flags, F.cull && !ctx->trace && !getenv("VRS_NO_CULL") && (long long)ctx->grid.cdim[0] * ctx->grid.cdim[1] * ctx->grid.cdim[2] <= (1ll << 27), ctx->lights);
   return VRS_OK;
 }
 // part 0: every row; 1: rows whose neighbourhood lies inside the band (no halo needed); 2: the rest.  The reservoir

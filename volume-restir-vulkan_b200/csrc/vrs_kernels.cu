@@ -1054,12 +1054,12 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   // screen-space coverage culling (k_cover); the RNG / cell trace of a culled ray would differ, so tracing turns it off
   static const bool no_cull = getenv("VRS_NO_CULL") != nullptr;
   int tiles_x = 0;
-  if (F.cull && !trace && !no_cull && Q.cover) {
+  const long long ncell = (long long)G.cdim[0] * G.cdim[1] * G.cdim[2];
+  if (F.cull && !trace && !no_cull && Q.cover && ncell <= (1ll << 27)) {          // (8 threads per cell in a 32-bit grid index)
     tiles_x = ((int)F.W + COVER_TILE - 1) / COVER_TILE;
     const int tiles_y = ((int)F.H + COVER_TILE - 1) / COVER_TILE;
     cudaMemsetAsync(Q.cover, 0, (size_t)tiles_x * tiles_y, st);
-    const int ncell = G.cdim[0] * G.cdim[1] * G.cdim[2];
-    k_cover<<<(ncell * 8 + 127) / 128, 128, 0, st>>>(G, dF, Q, tiles_x, tiles_y);
+    k_cover<<<(unsigned)((ncell * 8 + 127) / 128), 128, 0, st>>>(G, dF, Q, tiles_x, tiles_y);
   }
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_classify<<<grid, block, 0, st>>>(G, dF, cur, Q, trace, y0, y1, store_y0, tiles_x);
