@@ -200,6 +200,64 @@ __global__ void __launch_bounds__(256) k_hit_compact(const uint8_t* __restrict__
   while (mm) { const int k = __ffs(mm) - 1; mm &= mm - 1; hit_pix[off++] = (uint32_t)(base + k); }
 }
 
+// ---- A3, the parts every form of the RIS stage shares: what a hit pixel needs before its candidate loop, and what happens to
+// the finished reservoir.
+// ris_hit_setup: world position of the collision k_primary left in the pixel's worldPos slot as {t, voxel code, RNG state, 1},
+// gradient normal (6 density lookups), voxel material, the G-buffer stores of restir.rgen:193-197, GeometryInfo (:174-186).
+__device__ __forceinline__ void ris_hit_setup(const GridDev& G, const FrameParams& F, const Planes& cur, const Queues& Q, uint32_t s, int store_y0,
+                                              uint32_t& idx, uint32_t& vcode, uint32_t& seed, GInfo& gi) {
+  idx = Q.hit_pix[s];
+  const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
+  const float4 scratch = cur.worldPos[idx];
+  seed = __float_as_uint(scratch.z);
+  V3 org, dir; primary_ray(F, x, y, org, dir);
+  const V3 P = add(org, muls(dir, scratch.x));
+  vcode = __float_as_uint(scratch.y);
+  const int i = (int)(vcode % (uint32_t)G.vdim[0]) + G.vmin[0];
+  const int j = (int)((vcode / (uint32_t)G.vdim[0]) % (uint32_t)G.vdim[1]) + G.vmin[1];
+  const int k = (int)(vcode / ((uint32_t)G.vdim[0] * (uint32_t)G.vdim[1])) + G.vmin[2];
+  const float dens = density_at(G, i, j, k);
+  V3 grad = v3(density_at(G, i + 1, j, k) - density_at(G, i - 1, j, k), density_at(G, i, j + 1, k) - density_at(G, i, j - 1, k),
+               density_at(G, i, j, k + 1) - density_at(G, i, j, k - 1));
+  const float gg = dot(grad, grad);
+  V3 n;
+  if (gg > 0.0f) { float l = sqrtf(gg); n = v3(-grad.x / l, -grad.y / l, -grad.z / l); }
+  else n = v3(-dir.x, -dir.y, -dir.z);
+  const float4 al = voxel_albedo(dens);
+  cur.worldPos[idx] = make_float4(P.x, P.y, P.z, 1.0f); cur.albedo[idx] = al;                          // :193-197
+  cur.normal[idx] = make_float4(n.x, n.y, n.z, 1.0f); cur.mat[idx] = make_float4(G.roughness, G.metallic, 1.0f, 1.0f);
+  gi.albedo[0] = al.x; gi.albedo[1] = al.y; gi.albedo[2] = al.z; gi.albedo[3] = al.w;
+  gi.normal = n; gi.worldPos = P; gi.metallic = G.metallic; gi.roughness = G.roughness;
+  gi.albedoLum = luminance_common(al.x, al.y, al.z);                                                   // :182
+  gi.camPos = v3(F.camPos[0], F.camPos[1], F.camPos[2]);                                               // :183
+  gi.sampleSeed = 0;
+}
+// ris_hit_store: optional FINALIZE_W, pack (:286-289), the state k_shadow / k_finish continue from, and the shadow ray of
+// ratio_track() toward the selected light (:229-235), clipped and queued for k_shadow.
+__device__ __forceinline__ void ris_hit_store(const GridDev& G, const LightsDev& L, const FrameParams& F, const ResPlanes& outR, const Queues& Q,
+                                              uint32_t* __restrict__ trace, int needs_finish, uint32_t s, uint32_t idx, uint32_t vcode, uint32_t seed,
+                                              V3 P, Res res) {
+  if ((F.flags & FLAG_FINALIZE_W) != 0 && res.w > 0.0f) res.w = res.sumWeights / (float(res.M) * res.pHat);
+  float4 a, b; packReservoir(res, a, b);
+  outR.info[idx] = a; outR.weight[idx] = b;
+  Q.hit_seed[s] = seed; Q.hit_T[s] = 1.0f;
+  if (trace) { trace[(size_t)idx * 4 + 0] = vcode; if (!needs_finish) trace[(size_t)idx * 4 + 3] = seed; }
+  if ((F.flags & FLAG_VISIBILITY) != 0 && res.w > 0.0f) {
+    const float4 lp = __ldg(&L.lights[2 * res.lightIndex]);
+    V3 sd = sub(v3(lp.x, lp.y, lp.z), P);
+    const float dist = sqrtf(dot(sd, sd));
+    RaySeg seg;
+    bool march = dist > 0.0f;
+    if (march) { sd = divs(sd, dist); march = clip_ray(G, P, sd, 0.0f, dist, seg); }
+    if (march) {                          // otherwise T = 1 and the RNG state is untouched
+      const uint32_t q = warp_append(&Q.counters[Q_SHADOW]);
+      Q.shadow[q] = s;
+      Q.shadow_ray[2 * q] = make_float4(seg.o[0], seg.o[1], seg.o[2], seg.t0);
+      Q.shadow_ray[2 * q + 1] = make_float4(seg.d[0], seg.d[1], seg.d[2], seg.t1);
+    }
+  }
+}
+
 // Reference form of the RIS stage: one thread per hit pixel runs the M-candidate loop serially (kept selectable with
 // VRS_RIS=thread for A/B measurements; k_ris_coop below is the default and produces the same bits).
 template <int MINB>
@@ -209,32 +267,9 @@ __global__ void __launch_bounds__(128, MINB) k_ris_thread(const GridDev G, const
   const uint32_t nhit = Q.counters[Q_HIT];
   if (nhit < min_hits) return;                               // small launches are left to k_ris_coop (launch_initial)
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
-    const uint32_t idx = Q.hit_pix[s];
-    const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
-    const float4 scratch = cur.worldPos[idx];                                      // {t, voxel code, RNG state, 1} from k_primary
-    uint32_t seed = __float_as_uint(scratch.z);
-    V3 org, dir; primary_ray(F, x, y, org, dir);
-    const V3 P = add(org, muls(dir, scratch.x));
-    const uint32_t vcode = __float_as_uint(scratch.y);
-    const int i = (int)(vcode % (uint32_t)G.vdim[0]) + G.vmin[0];
-    const int j = (int)((vcode / (uint32_t)G.vdim[0]) % (uint32_t)G.vdim[1]) + G.vmin[1];
-    const int k = (int)(vcode / ((uint32_t)G.vdim[0] * (uint32_t)G.vdim[1])) + G.vmin[2];
-    const float dens = density_at(G, i, j, k);
-    V3 grad = v3(density_at(G, i + 1, j, k) - density_at(G, i - 1, j, k), density_at(G, i, j + 1, k) - density_at(G, i, j - 1, k),
-                 density_at(G, i, j, k + 1) - density_at(G, i, j, k - 1));
-    const float gg = dot(grad, grad);
-    V3 n;
-    if (gg > 0.0f) { float l = sqrtf(gg); n = v3(-grad.x / l, -grad.y / l, -grad.z / l); }
-    else n = v3(-dir.x, -dir.y, -dir.z);
-    const float4 al = voxel_albedo(dens);
-    cur.worldPos[idx] = make_float4(P.x, P.y, P.z, 1.0f); cur.albedo[idx] = al;                        // :193-197
-    cur.normal[idx] = make_float4(n.x, n.y, n.z, 1.0f); cur.mat[idx] = make_float4(G.roughness, G.metallic, 1.0f, 1.0f);
-    GInfo gi;
-    gi.albedo[0] = al.x; gi.albedo[1] = al.y; gi.albedo[2] = al.z; gi.albedo[3] = al.w;
-    gi.normal = n; gi.worldPos = P; gi.metallic = G.metallic; gi.roughness = G.roughness;
-    gi.albedoLum = luminance_common(al.x, al.y, al.z);                                                 // :182
-    gi.camPos = v3(F.camPos[0], F.camPos[1], F.camPos[2]);                                             // :183
-    gi.sampleSeed = 0;
+    uint32_t idx, vcode, seed; GInfo gi;
+    ris_hit_setup(G, F, cur, Q, s, store_y0, idx, vcode, seed, gi);
+    const V3 P = gi.worldPos;
     Res res = newReservoir();
     if (dot(gi.normal, gi.normal) != 0.0f) {                                                           // :205
       const ShadePre pre = shade_pre(gi);
@@ -259,25 +294,7 @@ __global__ void __launch_bounds__(128, MINB) k_ris_thread(const GridDev G, const
       }
       if (selM != 0u) res.w = selSumW / (float(selM) * res.pHat);                                      // reservoir.glsl:51
     }
-    if ((F.flags & FLAG_FINALIZE_W) != 0 && res.w > 0.0f) res.w = res.sumWeights / (float(res.M) * res.pHat);
-    float4 a, b; packReservoir(res, a, b);
-    outR.info[idx] = a; outR.weight[idx] = b;
-    Q.hit_seed[s] = seed; Q.hit_T[s] = 1.0f;
-    if (trace) { trace[(size_t)idx * 4 + 0] = vcode; if (!needs_finish) trace[(size_t)idx * 4 + 3] = seed; }
-    if ((F.flags & FLAG_VISIBILITY) != 0 && res.w > 0.0f) {                                              // shadow ray of ratio_track()
-      const float4 lp = __ldg(&L.lights[2 * res.lightIndex]);
-      V3 sd = sub(v3(lp.x, lp.y, lp.z), P);
-      const float dist = sqrtf(dot(sd, sd));
-      RaySeg seg;
-      bool march = dist > 0.0f;
-      if (march) { sd = divs(sd, dist); march = clip_ray(G, P, sd, 0.0f, dist, seg); }
-      if (march) {                        // otherwise T = 1 and the RNG state is untouched
-        const uint32_t q = warp_append(&Q.counters[Q_SHADOW]);
-        Q.shadow[q] = s;
-        Q.shadow_ray[2 * q] = make_float4(seg.o[0], seg.o[1], seg.o[2], seg.t0);
-        Q.shadow_ray[2 * q + 1] = make_float4(seg.d[0], seg.d[1], seg.d[2], seg.t1);
-      }
-    }
+    ris_hit_store(G, L, F, outR, Q, trace, needs_finish, s, idx, vcode, seed, P, res);
   }
 }
 
@@ -288,32 +305,9 @@ __global__ void __launch_bounds__(128, 6) k_ris_prefetch(const GridDev G, const 
   const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
-    const uint32_t idx = Q.hit_pix[s];
-    const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
-    const float4 scratch = cur.worldPos[idx];                                      // {t, voxel code, RNG state, 1} from k_primary
-    uint32_t seed = __float_as_uint(scratch.z);
-    V3 org, dir; primary_ray(F, x, y, org, dir);
-    const V3 P = add(org, muls(dir, scratch.x));
-    const uint32_t vcode = __float_as_uint(scratch.y);
-    const int i = (int)(vcode % (uint32_t)G.vdim[0]) + G.vmin[0];
-    const int j = (int)((vcode / (uint32_t)G.vdim[0]) % (uint32_t)G.vdim[1]) + G.vmin[1];
-    const int k = (int)(vcode / ((uint32_t)G.vdim[0] * (uint32_t)G.vdim[1])) + G.vmin[2];
-    const float dens = density_at(G, i, j, k);
-    V3 grad = v3(density_at(G, i + 1, j, k) - density_at(G, i - 1, j, k), density_at(G, i, j + 1, k) - density_at(G, i, j - 1, k),
-                 density_at(G, i, j, k + 1) - density_at(G, i, j, k - 1));
-    const float gg = dot(grad, grad);
-    V3 n;
-    if (gg > 0.0f) { float l = sqrtf(gg); n = v3(-grad.x / l, -grad.y / l, -grad.z / l); }
-    else n = v3(-dir.x, -dir.y, -dir.z);
-    const float4 al = voxel_albedo(dens);
-    cur.worldPos[idx] = make_float4(P.x, P.y, P.z, 1.0f); cur.albedo[idx] = al;                        // :193-197
-    cur.normal[idx] = make_float4(n.x, n.y, n.z, 1.0f); cur.mat[idx] = make_float4(G.roughness, G.metallic, 1.0f, 1.0f);
-    GInfo gi;
-    gi.albedo[0] = al.x; gi.albedo[1] = al.y; gi.albedo[2] = al.z; gi.albedo[3] = al.w;
-    gi.normal = n; gi.worldPos = P; gi.metallic = G.metallic; gi.roughness = G.roughness;
-    gi.albedoLum = luminance_common(al.x, al.y, al.z);                                                 // :182
-    gi.camPos = v3(F.camPos[0], F.camPos[1], F.camPos[2]);                                             // :183
-    gi.sampleSeed = 0;
+    uint32_t idx, vcode, seed; GInfo gi;
+    ris_hit_setup(G, F, cur, Q, s, store_y0, idx, vcode, seed, gi);
+    const V3 P = gi.worldPos;
     Res res = newReservoir();
     if (dot(gi.normal, gi.normal) != 0.0f) {                                                           // :205
       const ShadePre pre = shade_pre(gi);
@@ -352,25 +346,7 @@ __global__ void __launch_bounds__(128, 6) k_ris_prefetch(const GridDev G, const 
       }
       if (selM != 0u) res.w = selSumW / (float(selM) * res.pHat);                                      // reservoir.glsl:51
     }
-    if ((F.flags & FLAG_FINALIZE_W) != 0 && res.w > 0.0f) res.w = res.sumWeights / (float(res.M) * res.pHat);
-    float4 a, b; packReservoir(res, a, b);
-    outR.info[idx] = a; outR.weight[idx] = b;
-    Q.hit_seed[s] = seed; Q.hit_T[s] = 1.0f;
-    if (trace) { trace[(size_t)idx * 4 + 0] = vcode; if (!needs_finish) trace[(size_t)idx * 4 + 3] = seed; }
-    if ((F.flags & FLAG_VISIBILITY) != 0 && res.w > 0.0f) {                                              // shadow ray of ratio_track()
-      const float4 lp = __ldg(&L.lights[2 * res.lightIndex]);
-      V3 sd = sub(v3(lp.x, lp.y, lp.z), P);
-      const float dist = sqrtf(dot(sd, sd));
-      RaySeg seg;
-      bool march = dist > 0.0f;
-      if (march) { sd = divs(sd, dist); march = clip_ray(G, P, sd, 0.0f, dist, seg); }
-      if (march) {                        // otherwise T = 1 and the RNG state is untouched
-        const uint32_t q = warp_append(&Q.counters[Q_SHADOW]);
-        Q.shadow[q] = s;
-        Q.shadow_ray[2 * q] = make_float4(seg.o[0], seg.o[1], seg.o[2], seg.t0);
-        Q.shadow_ray[2 * q + 1] = make_float4(seg.d[0], seg.d[1], seg.d[2], seg.t1);
-      }
-    }
+    ris_hit_store(G, L, F, outR, Q, trace, needs_finish, s, idx, vcode, seed, P, res);
   }
 }
 
@@ -421,36 +397,16 @@ __global__ void __launch_bounds__(128, 6) k_ris_coop(const GridDev G, const Ligh
     uint32_t idx = 0, vcode = 0, seed = 0;
     bool valid = false;
     if (pix) {
-      idx = Q.hit_pix[s];
-      const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
-      const float4 scratch = cur.worldPos[idx];                                    // {t, voxel code, RNG state, 1} from k_primary
-      seed = __float_as_uint(scratch.z);
-      V3 org, dir; primary_ray(F, x, y, org, dir);
-      const V3 P = add(org, muls(dir, scratch.x));
-      vcode = __float_as_uint(scratch.y);
-      const int i = (int)(vcode % (uint32_t)G.vdim[0]) + G.vmin[0];
-      const int j = (int)((vcode / (uint32_t)G.vdim[0]) % (uint32_t)G.vdim[1]) + G.vmin[1];
-      const int k = (int)(vcode / ((uint32_t)G.vdim[0] * (uint32_t)G.vdim[1])) + G.vmin[2];
-      const float dens = density_at(G, i, j, k);
-      V3 grad = v3(density_at(G, i + 1, j, k) - density_at(G, i - 1, j, k), density_at(G, i, j + 1, k) - density_at(G, i, j - 1, k),
-                   density_at(G, i, j, k + 1) - density_at(G, i, j, k - 1));
-      const float gg = dot(grad, grad);
-      V3 n;
-      if (gg > 0.0f) { float l = sqrtf(gg); n = v3(-grad.x / l, -grad.y / l, -grad.z / l); }
-      else n = v3(-dir.x, -dir.y, -dir.z);
-      const float4 al = voxel_albedo(dens);
-      cur.worldPos[idx] = make_float4(P.x, P.y, P.z, 1.0f); cur.albedo[idx] = al;                      // :193-197
-      cur.normal[idx] = make_float4(n.x, n.y, n.z, 1.0f); cur.mat[idx] = make_float4(G.roughness, G.metallic, 1.0f, 1.0f);
       GInfo gi;
-      gi.normal = n; gi.worldPos = P; gi.metallic = G.metallic; gi.roughness = G.roughness;
-      gi.camPos = v3(F.camPos[0], F.camPos[1], F.camPos[2]);                                           // :183
+      ris_hit_setup(G, F, cur, Q, s, store_y0, idx, vcode, seed, gi);
+      const V3 P = gi.worldPos, n = gi.normal;
       valid = dot(gi.normal, gi.normal) != 0.0f;                                                       // :205
       const ShadePre pre = shade_pre(gi);
       sm.P[0][lane] = P.x; sm.P[1][lane] = P.y; sm.P[2][lane] = P.z;
       sm.n[0][lane] = n.x; sm.n[1][lane] = n.y; sm.n[2][lane] = n.z;
       sm.wo[0][lane] = pre.wo.x; sm.wo[1][lane] = pre.wo.y; sm.wo[2][lane] = pre.wo.z;
       sm.fresnelOut[lane] = pre.fresnelOut; sm.smithOut[lane] = pre.smithOut;
-      sm.albedoLum[lane] = luminance_common(al.x, al.y, al.z);                                         // :182
+      sm.albedoLum[lane] = gi.albedoLum;
       sm.seed0[lane] = seed;
     }
     const unsigned vmask = __ballot_sync(full, valid);
@@ -568,25 +524,7 @@ __global__ void __launch_bounds__(128, 6) k_ris_coop(const GridDev G, const Ligh
           res.w = sel_sumW / (float(selc + 1u) * pHat);                                                // reservoir.glsl:51
         }
       }
-      if ((F.flags & FLAG_FINALIZE_W) != 0 && res.w > 0.0f) res.w = res.sumWeights / (float(res.M) * res.pHat);
-      float4 a, b; packReservoir(res, a, b);
-      outR.info[idx] = a; outR.weight[idx] = b;
-      Q.hit_seed[s] = seed; Q.hit_T[s] = 1.0f;
-      if (trace) { trace[(size_t)idx * 4 + 0] = vcode; if (!needs_finish) trace[(size_t)idx * 4 + 3] = seed; }
-      if ((F.flags & FLAG_VISIBILITY) != 0 && res.w > 0.0f) {                                            // shadow ray of ratio_track()
-        const float4 lp = __ldg(&L.lights[2 * res.lightIndex]);
-        V3 sd = sub(v3(lp.x, lp.y, lp.z), P);
-        const float dist = sqrtf(dot(sd, sd));
-        RaySeg seg;
-        bool march = dist > 0.0f;
-        if (march) { sd = divs(sd, dist); march = clip_ray(G, P, sd, 0.0f, dist, seg); }
-        if (march) {                        // otherwise T = 1 and the RNG state is untouched
-          const uint32_t q = warp_append(&Q.counters[Q_SHADOW]);
-          Q.shadow[q] = s;
-          Q.shadow_ray[2 * q] = make_float4(seg.o[0], seg.o[1], seg.o[2], seg.t0);
-          Q.shadow_ray[2 * q + 1] = make_float4(seg.d[0], seg.d[1], seg.d[2], seg.t1);
-        }
-      }
+      ris_hit_store(G, L, F, outR, Q, trace, needs_finish, s, idx, vcode, seed, P, res);
     }
     __syncwarp();
   }
