@@ -215,3 +215,23 @@ def test_neglog1m_accuracy(O):
     assert got[0] == 0.0
     rel = np.abs(got[1:] - exp[1:]) / exp[1:]
     assert rel.max() < 4e-7, rel.max()
+
+
+def test_oracle_frames_match_committed_digests(O):
+    """The oracle's full-frame outputs (G-buffer, reservoirs, RNG / voxel / cell trace, accumulated image) for four small
+    configurations must equal the SHA-256 digests committed in tests/golden/oracle_frame_digests.json
+    (tools/gen_frame_digests.py): a change of the volumetric specification is a deliberate regeneration, never a drift."""
+    import json
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import gen_frame_digests as G
+    want = json.load(open(G.OUT))
+    got = G.compute()
+    assert set(got) == set(want)
+    for case in want:
+        for frame in want[case]:
+            for key, val in want[case][frame].items():
+                assert got[case][frame][key] == val, (case, frame, key)
+        assert want[case]["frame0"]["hit_pixels"] > 100          # the volume is in view: the digests cover real work
