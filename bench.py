@@ -36,6 +36,9 @@ WORKLOADS = {
                                  desc="configs[2] on a procedural stand-in for explosion.vdb (~8M voxels): 1920x1080, <=1001 emissive-voxel lights, full spatiotemporal k=5 x2"),
     "bunny_4k_full": dict(asset="proc:bunny_cloud:288", W=3840, H=2160, lights=10000, M=32, flags=1 | 2 | 4, k=5, iters=2,
                           desc="configs[3] on a procedural stand-in for bunny_cloud.vdb (~1.2M voxels): 3840x2160, 10k lights, full spatiotemporal k=5 x2"),
+    # configs[4] (meant for --gpus 8; 33 Mpixel: 8 GB of planes + 2.8 GB of queues when run on one GPU)
+    "composite_8k_full": dict(asset="proc:fire_torus:384", W=7680, H=4320, lights=100000, M=32, flags=1 | 2 | 4, k=5, iters=2,
+                              desc="configs[4] on a procedural stand-in for the fire.vdb + torus_knot_helix.vdb composite (one merged grid): 7680x4320, 100k lights, full spatiotemporal k=5 x2"),
 }
 
 

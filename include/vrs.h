@@ -112,7 +112,8 @@ vrs_status vrs_load_vrsg(vrs_ctx* ctx, const char* path);
 /* Host-only conversion `.vdb` -> `.vrsg` (no device needed; ctx may be NULL). */
 vrs_status vrs_convert_vdb(const char* vdb_path, const char* grid_name, const char* vrsg_path);
 /* Deterministic procedural stand-ins for the assets missing from the reference checkout
- * (.MISSING_LARGE_BLOBS:1-4): kind 0 = "bunny_cloud", 1 = "explosion", 2 = "fire", 3 = "torus_knot_helix". */
+ * (.MISSING_LARGE_BLOBS:1-4): kind 0 = "bunny_cloud", 1 = "explosion", 2 = "fire", 3 = "torus_knot_helix",
+ * 4 = "fire_torus" (the fire + torus_knot_helix composite of BASELINE.json configs[4], merged into one grid). */
 vrs_status vrs_make_procedural_grid(vrs_ctx* ctx, int kind, uint32_t resolution);
 /* Host-only: generate the same stand-in and write it as a `.vrsg` snapshot (no device needed). */
 vrs_status vrs_write_procedural_vrsg(int kind, uint32_t resolution, const char* vrsg_path);

@@ -231,13 +231,19 @@ def test_procedural_standins_are_deterministic(V, tmp_path):
     V.write_procedural_vrsg("torus_knot_helix", 64, a)
     V.write_procedural_vrsg("torus_knot_helix", 64, b)
     assert open(a, "rb").read() == open(b, "rb").read()
-    for kind in ("bunny_cloud", "explosion", "fire"):
+    for kind in ("bunny_cloud", "explosion", "fire", "fire_torus"):
         V.write_procedural_vrsg(kind, 64, a)
         g = grid_py.read_vrsg(a)
         assert len(g.leaf_origin) > 10 and 0.0 < float(g.leaf_value.max()) < 10.0 and not g.level_set
         assert (g.leaf_value[~g.leaf_mask] == 0).all()
+    # the composite of configs[4] holds both of its parts: the knot's ring low in the grid and the plume rising above it
+    dense, vmin, vdim = grid_py.dense_raw(grid_py.read_vrsg(a))                     # [z][y][x]
+    occupied_rows = np.nonzero((dense > 0).any(axis=(0, 2)))[0] + vmin[1]
+    assert occupied_rows.min() < 16 and occupied_rows.max() > 44
     with pytest.raises(V.VrsError):
         V.write_procedural_vrsg(0, 30, a)
+    with pytest.raises(V.VrsError):
+        V.write_procedural_vrsg(5, 64, a)
 
 
 def test_emissive_voxel_lights_from_temperature_grid(V, tmp_path):

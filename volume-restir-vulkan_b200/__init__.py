@@ -214,7 +214,7 @@ def convert_vdb(vdb_path, vrsg_path, grid_name=None):
         raise VrsError(s, lib().vrs_last_error(None).decode())
 
 
-PROCEDURAL_KINDS = {"bunny_cloud": 0, "explosion": 1, "fire": 2, "torus_knot_helix": 3}
+PROCEDURAL_KINDS = {"bunny_cloud": 0, "explosion": 1, "fire": 2, "torus_knot_helix": 3, "fire_torus": 4}
 
 
 def write_procedural_vrsg(kind, resolution, path):

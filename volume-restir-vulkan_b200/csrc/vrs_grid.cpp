@@ -554,6 +554,13 @@ inline float smooth01(float x) { x = x < 0 ? 0 : (x > 1 ? 1 : x); return x * x *
 
 // density in [0, ~3] at normalised coordinates p in [0,1]^3
 float procedural_density(int kind, float px, float py, float pz) {
+  if (kind == 4) {          // "fire_torus": the composite of configs[4] - the fire plume standing inside the torus knot
+    const float fx = 0.5f + (px - 0.5f) * 1.6f, fy = (py - 0.18f) * 1.35f, fz = 0.5f + (pz - 0.5f) * 1.6f;   // plume: narrower, taller
+    const float fire = (fx < 0.f || fx > 1.f || fy < 0.f || fy > 1.f || fz < 0.f || fz > 1.f) ? 0.0f : procedural_density(2, fx, fy, fz);
+    const float ty = 0.5f + (py - 0.30f) * 1.25f;                                                            // knot: lowered around its base
+    const float knot = (ty < 0.f || ty > 1.f) ? 0.0f : procedural_density(3, px, ty, pz);
+    return std::max(fire, knot);
+  }
   float x = px - 0.5f, y = py - 0.5f, z = pz - 0.5f;
   if (kind == 0) {          // "bunny_cloud": three soft ellipsoids eroded by fbm
     auto blob = [](float x, float y, float z, float cx, float cy, float cz, float rx, float ry, float rz) {
@@ -594,8 +601,8 @@ float procedural_density(int kind, float px, float py, float pz) {
 }  // namespace
 
 bool make_procedural(int kind, uint32_t res, HostGrid& g, std::string& err) {
-  if (kind < 0 || kind > 3 || res < 32 || res > 2048 || (res % 8) != 0) { err = "procedural grid: kind 0..3, resolution multiple of 8 in [32,2048]"; return false; }
-  static const char* names[4] = {"bunny_cloud", "explosion", "fire", "torus_knot_helix"};
+  if (kind < 0 || kind > 4 || res < 32 || res > 2048 || (res % 8) != 0) { err = "procedural grid: kind 0..4, resolution multiple of 8 in [32,2048]"; return false; }
+  static const char* names[5] = {"bunny_cloud", "explosion", "fire", "torus_knot_helix", "fire_torus"};
   g = HostGrid();
   g.name = names[kind]; g.grid_type = "Tree_float_5_4_3"; g.half = false; g.level_set = false; g.background = 0.0f;
   g.voxel_size = 100.0 / res;                       // 100 index-world units across, ~5 world units after the 0.05 scale
