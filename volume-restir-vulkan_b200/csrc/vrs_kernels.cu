@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(128, 6) k_ris_coop(const GridDev G, const Ligh
       //   stage 2 picks the light of pixel pA and requests it                (consumed one iteration later)
       //   stage 3 culls the candidates of pixel pL behind the surface and appends the others to the phase-B list
       int pA = -1, pL = -1;
-      uint32_t colA = 0u, selL = 0u; float r2A = 0.0f, pdfL = 0.0f, lewL = 0.0f;
+      uint32_t colA = 0u; float r2A = 0.0f, pdfL = 0.0f, lewL = 0.0f;
       float4 cellA = make_float4(0.f, 0.f, 0.f, 0.f), lpL = make_float4(0.f, 0.f, 0.f, 0.f);
       for (;;) {
         int pN2 = pA; uint32_t selN = 0u; float pdfN = 0.0f, lewN = 0.0f; float4 lpN = lpL;
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(128, 6) k_ris_coop(const GridDev G, const Ligh
           __syncwarp();
         }
         if (flush) break;
-        pL = pN2; selL = selN; pdfL = pdfN; lpL = lpN; lewL = lewN;
+        pL = pN2; pdfL = pdfN; lpL = lpN; lewL = lewN;
         pA = pN1; colA = colN; r2A = r2N; cellA = cellN;
       }
       // ---------------- step 3: lane = pixel, the serial part of updateReservoir (reservoir.glsl:30-43) for this chunk
