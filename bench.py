@@ -4,9 +4,10 @@
   python bench.py --gpus N --steps K --warmup W            # our CUDA path through the C ABI (libvrs.so)
   python bench.py --impl reference ...                     # the reference math on the box's host cores (oracle port)
 
-A "step" is one frame of BASELINE.json configs[1]: smoke.vdb, 1920x1080, 64 point lights, RIS M=32 + temporal
-reuse, camera on a 6 deg/frame orbit.  N > 1 (torchrun) splits the screen into horizontal bands, grid replicated,
-halo rows exchanged over NCCL (strong scaling: total work fixed).
+A "step" is one frame of the workload.  The default is BASELINE.json configs[3] (the north-star target): bunny_cloud
+stand-in at 3840x2160, 10k point lights, RIS M=32, visibility + temporal + spatial reuse (k=5, 2 iterations), camera on a
+6 deg/frame orbit.  configs[1] (smoke.vdb 1080p temporal) is `--workload smoke_1080p_temporal`.  N > 1 (torchrun) splits
+the screen into horizontal bands, grid replicated, halo rows exchanged over NVLink (strong scaling: total work fixed).
 """
 import argparse
 import ctypes as C
@@ -40,6 +41,13 @@ WORKLOADS = {
     "composite_8k_full": dict(asset="proc:fire_torus:384", W=7680, H=4320, lights=100000, M=32, flags=1 | 2 | 4, k=5, iters=2,
                               desc="configs[4] on a procedural stand-in for the fire.vdb + torus_knot_helix.vdb composite (one merged grid): 7680x4320, 100k lights, full spatiotemporal k=5 x2"),
 }
+DEFAULT_WORKLOAD = "bunny_4k_full"
+ORBIT_DEG, ORBIT_RADIUS = 6.0, 1.25          # camera orbit of every workload: degrees per frame, radius in bbox half-diagonals
+UNBIASED_FLAGS = 2 | 4 | 16 | 32             # temporal + spatial + FINAL_VISIBILITY + FINALIZE_W (tests/test_unbiased.py)
+
+# SURVEY.md §8d algorithmic (compulsory) bytes per pixel per frame, by pass and by the kernel that moves them
+BYTES_PER_PX = {"initial": 96, "temporal": 96, "spatial_iter": 128, "shade": 128}
+KERNEL_BYTES_PER_PX = {"k_ris": 96, "k_finish": 96, "k_spatial": 128, "k_shade": 128}
 
 
 def data_desc(wl):
@@ -48,8 +56,16 @@ def data_desc(wl):
     return "synthetic camera orbit + generated lights over the reference's %s.vdb grid (assets/%s.vrsg)" % (wl["asset"], wl["asset"])
 
 
+def config_of(wl, name):
+    """Identical for both arms (the driver compares the dicts)."""
+    return {"workload": wl["desc"], "name": name, "resolution": [wl["W"], wl["H"]], "M": wl["M"], "lights": wl["lights"], "flags": wl["flags"],
+            "spatial_neighbors": wl["k"], "spatial_iterations": wl["iters"], "orbit_deg_per_frame": ORBIT_DEG,
+            "l2": "per-frame working set %.0f MB > 126 MB L2 (inputs larger than L2, no flush)" % (wl["W"] * wl["H"] * 240 / 1e6)}
+
+
 def asset_path(V, name):
-    """assets/<name>.vrsg, or a procedural stand-in generated (host-only, deterministic) into the scratch directory."""
+    """assets/<name>.vrsg, or a procedural stand-in generated (host-only, deterministic) into the scratch directory.
+    V = the loaded product module, or None to generate in a child process (the reference arm never maps libvrs.so)."""
     if not name.startswith("proc:"):
         return os.path.join(ROOT, "assets", name + ".vrsg")
     _, kind, res = name.split(":")
@@ -58,10 +74,13 @@ def asset_path(V, name):
     path = os.path.join(d, "%s_%s.vrsg" % (kind, res))
     if not os.path.exists(path):
         tmp = path + ".%d.tmp" % os.getpid()
-        V.write_procedural_vrsg(kind, int(res), tmp)
+        if V is not None:
+            V.write_procedural_vrsg(kind, int(res), tmp)
+        else:
+            subprocess.check_call([sys.executable, "-c", "import sys; sys.path.insert(0, %r); import vrs_pkg; vrs_pkg.load().write_procedural_vrsg(%r, %d, %r)"
+                                   % (ROOT, kind, int(res), tmp)])
         os.replace(tmp, path)
     return path
-BYTES_PER_PX = {"initial": 96, "temporal": 96, "spatial_iter": 128, "shade": 128}   # SURVEY.md §8d / BASELINE.md §4
 
 
 def measured_peak():
@@ -112,24 +131,52 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_scene_inputs(V, wl, R):
-    gi = R.gridInfo()
-    lo, hi = list(gi.world_bbox_min), list(gi.world_bbox_max)
+def scene_lights(gen_lights, wl, lo, hi, emissive):
+    """Lights of a workload from the grid's world bbox: generatePointLights semantics inside the box, or the emissive-voxel
+    rule (callable `emissive`).  Returns (lights, bbox centre, bbox half-diagonal)."""
     ctr = [(a + b) * 0.5 for a, b in zip(lo, hi)]
     ext = [(b - a) * 0.5 for a, b in zip(lo, hi)]
-    if wl["lights"] < 0:      # emissive-voxel lights (Renderer.cpp:1615-1637); "hot" = raw value above 85 % of the maximum
-        lights = R.collectEmissiveLights(0.85 * gi.max_density, -wl["lights"])
+    if wl["lights"] < 0:
+        lights = emissive(-wl["lights"])
     else:
-        lights = V.generate_point_lights([c - e for c, e in zip(ctr, ext)], [c + e for c, e in zip(ctr, ext)], False, wl["lights"])
-    diag = math.sqrt(sum(e * e for e in ext))
-    return lights, ctr, diag
+        lights = gen_lights([c - e for c, e in zip(ctr, ext)], [c + e for c, e in zip(ctr, ext)], False, wl["lights"])
+    return lights, ctr, math.sqrt(sum(e * e for e in ext))
+
+
+def build_scene_inputs(V, wl, R):
+    gi = R.gridInfo()
+    # emissive-voxel lights (Renderer.cpp:1615-1637); "hot" = raw value above 85 % of the maximum
+    return scene_lights(V.generate_point_lights, wl, list(gi.world_bbox_min), list(gi.world_bbox_max),
+                        lambda n: R.collectEmissiveLights(0.85 * gi.max_density, n))
+
+
+def temporal_halo_rows(V, wl, lo, hi, ctr, diag, frames=60, minimum=32):
+    """Rows a band must keep above / below itself so that the temporal reprojection of any point of the grid's bounding box
+    stays inside them on this camera orbit: max |row(prevVP p) - row(curVP p)| over a lattice of the box, plus a margin.
+    (The library counts violations: vrs_get_counters().temporal_out_of_halo must stay 0.)"""
+    W, H = wl["W"], wl["H"]
+    ax = [np.linspace(lo[a], hi[a], 9) for a in range(3)]
+    P = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3)
+    P4 = np.concatenate([P, np.ones((len(P), 1))], 1)
+    aspect = float(np.float32(W) / np.float32(H))
+    proj = V.perspectiveVK(60.0, aspect, 0.1, 1000.0).reshape(4, 4).T.astype(np.float64)
+    rows, worst = None, 0.0
+    for f in range(frames + 1):
+        view = V.look_at(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, ORBIT_DEG * f), ctr).reshape(4, 4).T.astype(np.float64)
+        q = P4 @ (proj @ view).T
+        y = (q[:, 1] / q[:, 3] + 1.0) * 0.5 * H
+        if rows is not None:
+            worst = max(worst, float(np.abs(y - rows).max()))
+        rows = y
+    need = int(math.ceil(worst * 1.1)) + 4
+    return max(minimum, (need + 7) // 8 * 8)
 
 
 def balanced_bands(V, wl, path, world, device):
     """Per-row cost model for screen-space bands of equal estimated cost instead of equal height: a quarter-resolution
     probe frame (rendered by every rank on its own GPU, bit-identical everywhere) gives the per-row count of
     volume-hitting pixels; cost(row) = hits + 2.5 % of the pixels."""
-    W, H, halo = wl["W"], wl["H"], 32
+    W, H = wl["W"], wl["H"]
     q = 4
     w4, h4 = max(W // q, 16), max(H // q, 16)
     P = V.Renderer(w4, h4, spatial_iterations=0, device=device)
@@ -139,7 +186,7 @@ def balanced_bands(V, wl, path, world, device):
     P.m_restirUniforms.initialLightSampleCount, P.m_restirUniforms.flags = 1, 0
     hits = np.zeros(h4, np.float64)
     for ang in (0.0, 90.0, 180.0, 270.0):
-        P.CameraManip.setLookat(orbit_eye(ctr, 1.25 * diag, 0.0, ang), ctr)
+        P.CameraManip.setLookat(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, ang), ctr)
         P.createRestirUniformBuffer()
         P.renderFrame(clock=int(ang))
         hits += P.readGBuffer()["worldPos"][..., 3].sum(1)
@@ -150,8 +197,8 @@ def balanced_bands(V, wl, path, world, device):
     return cost
 
 
-def split_rows(cost, world, halo=32):
-    """Band edges that give every rank the same share of the per-row cost (bands keep at least `halo` rows)."""
+def split_rows(cost, world, min_rows=32):
+    """Band edges that give every rank the same share of the per-row cost (bands keep at least `min_rows` rows = the halo)."""
     H = len(cost)
     cum = np.concatenate([[0.0], np.cumsum(cost)])
     edges = [0]
@@ -160,32 +207,32 @@ def split_rows(cost, world, halo=32):
         edges.append(y)
     edges.append(H)
     for r in range(1, world):                                     # enforce the minimum band height front to back, then back to front
-        edges[r] = max(edges[r], edges[r - 1] + halo)
+        edges[r] = max(edges[r], edges[r - 1] + min_rows)
     for r in range(world - 1, 0, -1):
-        edges[r] = min(edges[r], edges[r + 1] - halo)
+        edges[r] = min(edges[r], edges[r + 1] - min_rows)
     return [(edges[r], edges[r + 1]) for r in range(world)]
 
 
-def calibrated_bands(V, wl, path, world, rank, device, dist, lights_ctr_diag=None, rounds=3, frames=12):
+def calibrated_bands(V, wl, path, world, rank, device, dist, halo, rounds=3, frames=12):
     """Start from the hit-count model, then correct it with measurements: every rank renders its band (no exchange, timing
     only) for a few frames, the per-band times are all-gathered and turned into a per-band correction of the row costs.
     Which rows a rank renders never changes a pixel (tests/test_gpu_multi.py); only the load balance does."""
     import torch
     cost = balanced_bands(V, wl, path, world, device)
-    bands = split_rows(cost, world)
+    bands = split_rows(cost, world, halo)
     for _ in range(rounds):
         band = bands[rank]
-        R = V.Renderer(wl["W"], wl["H"], spatial_iterations=wl["iters"], band=band, halo_rows=32, device=device)
+        R = V.Renderer(wl["W"], wl["H"], spatial_iterations=wl["iters"], band=band, halo_rows=halo, device=device)
         R.loadVDB(path)
         lights, ctr, diag = build_scene_inputs(V, wl, R)
         R.createRestirLights(lights)
         u = R.m_restirUniforms
         u.initialLightSampleCount, u.spatialNeighbors, u.flags = wl["M"], wl["k"], wl["flags"]
-        R.CameraManip.setLookat(orbit_eye(ctr, 1.25 * diag, 0.0, 0.0), ctr)
+        R.CameraManip.setLookat(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, 0.0), ctr)
         R.createRestirUniformBuffer()
         tot = 0.0
         for f in range(frames):
-            R.CameraManip.setLookat(orbit_eye(ctr, 1.25 * diag, 0.0, 30.0 * f), ctr)     # spread over the orbit
+            R.CameraManip.setLookat(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, 30.0 * f), ctr)     # spread over the orbit
             R.renderFrame(clock=f)
             if f >= 2:
                 tot += R.timings().frame_ms
@@ -199,19 +246,30 @@ def calibrated_bands(V, wl, path, world, rank, device, dist, lights_ctr_diag=Non
         corr = corr / corr.mean()
         for (y0, y1), c in zip(bands, corr):
             cost[y0:y1] *= 0.5 * (1.0 + c)                                               # damped
-        bands = split_rows(cost, world)
+        bands = split_rows(cost, world, halo)
     return bands
 
 
-def issue_roofline(tj, fps, clocks, workload, world):
-    """The frame is instruction-issue bound, not HBM bound (DESIGN.md §4): besides the contract's HBM roofline, report how
-    much of the SMs' issue capacity the frame uses.  Warp instructions per frame come from the committed ncu launch list
-    of the default workload (profiles/traffic.json), the frame rate and the SM clock are measured live.  None when the
-    inputs do not apply (other workload, several GPUs, no clock sample)."""
+def load_traffic(workload):
+    """ncu-measured DRAM bytes and warp instructions per kernel launch for this workload (profiles/traffic.json), or {}."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tp):
+        return {}
     try:
-        if workload != "smoke_1080p_temporal" or world != 1 or not clocks or not clocks.get("sm_mhz"):
+        return json.load(open(tp)).get("workloads", {}).get(workload, {})
+    except Exception:
+        return {}
+
+
+def issue_roofline(traffic, fps, clocks, world):
+    """The frame is instruction-issue bound, not HBM bound (DESIGN.md §4): besides the contract's HBM roofline, report how
+    much of the SMs' issue capacity the frame uses.  Warp instructions per frame come from the committed ncu launch list of
+    this workload (profiles/traffic.json), the frame rate and the SM clock are measured live.  None when the inputs do not
+    apply (no capture for the workload, several GPUs, no clock sample)."""
+    try:
+        if not traffic or world != 1 or not clocks or not clocks.get("sm_mhz"):
             return None
-        winst = sum(float(k_["warp_inst_M"]) for k_ in tj.get("per_kernel", {}).values()) * 1e6
+        winst = sum(float(k_["warp_inst_M"]) * float(k_.get("launches_per_frame", 1)) for k_ in traffic.values()) * 1e6
         if winst <= 0:
             return None
         peak_issue = 148 * 4 * float(clocks["sm_mhz"]) * 1e6            # 4 warp schedulers per SM, one instruction per clock each
@@ -238,12 +296,22 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W, H = wl["W"], wl["H"]
-    path = asset_path(V, wl["asset"])
+    path = asset_path(V, wl["asset"]) if rank == 0 or world == 1 else None
     if dist is not None:
         dist.barrier()       # the stand-in asset (if any) is on disk for every rank
-    bands = calibrated_bands(V, wl, path, world, rank, local, dist) if world > 1 else [(0, H)]
+        path = asset_path(V, wl["asset"])
+    halo = 32
+    if world > 1:
+        P = V.Renderer(16, 16, spatial_iterations=0, device=local)
+        P.loadVDB(path)
+        gi = P.gridInfo()
+        lo, hi = list(gi.world_bbox_min), list(gi.world_bbox_max)
+        _, ctr0, diag0 = scene_lights(lambda *a: None, dict(wl, lights=1), lo, hi, None)
+        P.destroy()
+        halo = temporal_halo_rows(V, wl, lo, hi, ctr0, diag0) if wl["flags"] & 2 else 32
+    bands = calibrated_bands(V, wl, path, world, rank, local, dist, halo) if world > 1 else [(0, H)]
     band = bands[rank] if world > 1 else None
-    R = V.Renderer(W, H, spatial_iterations=wl["iters"], band=band, halo_rows=32, device=local)
+    R = V.Renderer(W, H, spatial_iterations=wl["iters"], band=band, halo_rows=halo, device=local)
     R.loadVDB(path)
     lights, ctr, diag = build_scene_inputs(V, wl, R)
     wl = dict(wl, lights=len(lights))
@@ -259,24 +327,29 @@ def run_ours(args):
             R.peerConnect(rank, world, blobs)
     u = R.m_restirUniforms
     u.initialLightSampleCount, u.spatialNeighbors, u.flags = wl["M"], wl["k"], wl["flags"]
-    radius = 1.25 * diag
+    radius = ORBIT_RADIUS * diag
     R.CameraManip.setLookat(orbit_eye(ctr, radius, 0.0, 0.0), ctr)
     R.createRestirUniformBuffer()
 
     stream = torch.cuda.ExternalStream(R.stream())
     L = V.lib()
-    # Host inputs of every frame (camera uniforms, push constants) are produced up front by the Renderer methods that mirror
-    # the reference's updateUniformBuffer / updateRestirUniformBuffer / updateFrame; a step then is the one C-ABI call.
-    n_frames = args.warmup + args.steps + 22 + 2 + min(max(3, args.steps), 200) + 12
+    # Host inputs of every frame (camera uniforms, push constants) are produced by the Renderer methods that mirror the
+    # reference's updateUniformBuffer / updateRestirUniformBuffer / updateFrame, a block of frames ahead of their use (outside
+    # the timed regions); a step then is the one C-ABI call.
     inputs = []
-    for f in range(n_frames):
-        R.CameraManip.setLookat(orbit_eye(ctr, radius, 0.0, 6.0 * f), ctr)
-        R.updateUniformBuffer(); R.updateRestirUniformBuffer(); R.updateFrame()
-        inputs.append((V.GlobalUniforms.from_buffer_copy(R.m_globalUniforms), V.RestirUniforms.from_buffer_copy(R.m_restirUniforms),
-                       V.PushConstantRestir.from_buffer_copy(R.m_pcRestirPost)))
-        if R.m_pcRestirPost.frame > 10:
-            R.m_pcRestirPost.initialize = 0
     frame_no = [0]
+    flags_now = [wl["flags"]]
+
+    def extend_inputs(n):
+        while len(inputs) < frame_no[0] + n:
+            f = len(inputs)
+            R.CameraManip.setLookat(orbit_eye(ctr, radius, 0.0, ORBIT_DEG * f), ctr)
+            R.m_restirUniforms.flags = flags_now[0]
+            R.updateUniformBuffer(); R.updateRestirUniformBuffer(); R.updateFrame()
+            inputs.append((V.GlobalUniforms.from_buffer_copy(R.m_globalUniforms), V.RestirUniforms.from_buffer_copy(R.m_restirUniforms),
+                           V.PushConstantRestir.from_buffer_copy(R.m_pcRestirPost)))
+            if R.m_pcRestirPost.frame > 10:
+                R.m_pcRestirPost.initialize = 0
 
     def step():
         gu, ru, pc = inputs[frame_no[0]]
@@ -292,31 +365,54 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput: K frames, CUDA events on the launching stream (the per-pass events inside the
-    # frame are left out of the timed loops and switched on for the probe frames further down)
+    def timed_block(n):
+        """n frames bracketed by CUDA events on the launching stream; returns ms per frame (this rank)."""
+        extend_inputs(n)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(n):
+            step()
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1) / n
+
+    def max_over_ranks(v):
+        if dist is None:
+            return v
+        t = torch.tensor([v], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- device-resident throughput: K frames per repetition, CUDA events on the launching stream, max over ranks per
+    # repetition; repetitions until the timed region adds up to >= 0.5 s; the median repetition is reported.
     R.setPassTiming(False)
+    extend_inputs(args.warmup)
     for _ in range(args.warmup):
         step()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    reps = []
+    while True:
+        reps.append(max_over_ranks(timed_block(args.steps)))
+        if sum(reps) * args.steps >= 500.0 or len(reps) >= 25:
+            break
+    t_wall = time.perf_counter() - t_wall0
+    ms_step = float(np.median(reps))
+    clocks = sampler.stop() if rank == 0 else None
+    cnt = R.counters()
+    hits_band, ooh = cnt.hits, cnt.temporal_out_of_halo
+
+    # ---- per-pass event times of a few more frames (events recorded inside vrs_render_frame)
     pass_ms = {"initial": 0.0, "spatial": 0.0, "shade": 0.0, "exchange": 0.0}
     launches = 0
-    t_wall0 = time.perf_counter()
-    e0.record(stream)
-    for _ in range(args.steps):
-        step()
-    e1.record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
-    # per-pass event times of a few more frames (the events are recorded inside vrs_render_frame)
-    barrier()
     R.setPassTiming(True)
-    probe = min(args.steps, 20)
+    probe = 20
+    extend_inputs(probe + 2)
+    barrier()
     for i in range(probe + 2):
         step()
         t = R.timings()
@@ -329,81 +425,139 @@ def run_ours(args):
     R.setPassTiming(False)
     barrier()
 
+    # ---- per-kernel event times (frames launched kernel by kernel, one event after each kernel on the context stream)
+    kernel_ms = {}
+    if world == 1:
+        R.setKernelTiming(True)
+        extend_inputs(14)
+        for i in range(14):
+            step()
+            if i >= 2:
+                for name, ms in R.kernelTimes():
+                    kernel_ms[name] = kernel_ms.get(name, 0.0) + ms / 12.0
+        R.setKernelTiming(False)
+        barrier()
+
     # ---- end to end through the public API: host uniforms in, host frame buffer out, every step.
     # The result a caller of the reference gets per frame is the presented 8-bit image (restir_post.frag:104 ->
     # swapchain); here it is presented headlessly into pinned host memory, the copy of frame i overlapping frame i+1.
     pinned = [torch.empty((R.rows, W, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
     host_frames = [t.numpy() for t in pinned]
+    e2e_steps = max(3, min(args.steps, 200))
+    extend_inputs(e2e_steps + 2)
     for i in range(2):
         step(); R.presentAsync(host_frames[i & 1])
     R.presentWait()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(3, min(args.steps, 200))
     for i in range(e2e_steps):
         step()
         R.presentAsync(host_frames[i & 1])
     R.presentWait()
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_ms = max_over_ranks(1000.0 * (time.perf_counter() - t0) / e2e_steps)
     # the same with the full RGBA32F accumulation buffer read back synchronously (debug / parity read path)
     pinned_f = torch.empty((R.rows, W, 4), dtype=torch.float32, pin_memory=True)
     hf = pinned_f.numpy()
+    extend_inputs(5)
     t0 = time.perf_counter()
-    for _ in range(10):
+    for _ in range(5):
         step(); R.readFrame(hf)
     barrier()
-    e2e_f32_ms = 1000.0 * (time.perf_counter() - t0) / 10
+    e2e_f32_ms = 1000.0 * (time.perf_counter() - t0) / 5
 
-    ms_step = ms_total / args.steps
-    e2e_ms = 1000.0 * e2e_s / e2e_steps
+    # ---- the unbiased configuration (FINALIZE_W + FINAL_VISIBILITY instead of the reference's selection-time w and
+    # reused visibility): same frame, second ratio-tracking ray in the shade pass
+    unbiased_ms = None
+    if not args.no_unbiased:
+        ub_flags = UNBIASED_FLAGS if wl["flags"] & 4 else (UNBIASED_FLAGS & ~4)
+        flags_now[0] = ub_flags
+        del inputs[frame_no[0]:]
+        extend_inputs(4)
+        for _ in range(4):
+            step()
+        n_u = max(10, min(args.steps, 100))
+        unbiased_ms = max_over_ranks(timed_block(n_u))
+        flags_now[0] = wl["flags"]
+        del inputs[frame_no[0]:]
+
     if dist is not None:
-        tt = torch.tensor([ms_step, e2e_ms, pass_ms["initial"], pass_ms["spatial"], pass_ms["shade"], pass_ms["exchange"]], device="cuda", dtype=torch.float64)
+        tt = torch.tensor([pass_ms["initial"], pass_ms["spatial"], pass_ms["shade"], pass_ms["exchange"], float(hits_band), float(ooh)], device="cuda", dtype=torch.float64)
         per_rank = [torch.zeros_like(tt) for _ in range(world)]
         dist.all_gather(per_rank, tt)
-        per_rank_initial = [round(float(t_[2]), 4) for t_ in per_rank]
+        per_rank_initial = [round(float(t_[0]), 4) for t_ in per_rank]
+        hits_total = sum(float(t_[4]) for t_ in per_rank)
+        ooh = int(sum(float(t_[5]) for t_ in per_rank))
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_step, e2e_ms = float(tt[0]), float(tt[1])
-        pass_ms = {"initial": float(tt[2]), "spatial": float(tt[3]), "shade": float(tt[4]), "exchange": float(tt[5])}
+        pass_ms = {"initial": float(tt[0]), "spatial": float(tt[1]), "shade": float(tt[2]), "exchange": float(tt[3])}
+    else:
+        hits_total = float(hits_band)
     if rank == 0:
         fps = 1000.0 / ms_step
         px = W * H
         peak, peak_src = measured_peak()
-        rows_frac = (R.rows / H)
         temporal = bool(wl["flags"] & 2)
-        init_bytes = px * rows_frac * (BYTES_PER_PX["initial"] + (BYTES_PER_PX["temporal"] if temporal else 0))
-        ach = init_bytes / (pass_ms["initial"] * 1e-3) / 1e9 if pass_ms["initial"] > 0 else 0.0
         frame_bytes = px * (BYTES_PER_PX["initial"] + (BYTES_PER_PX["temporal"] if temporal else 0) + BYTES_PER_PX["shade"] +
                             (BYTES_PER_PX["spatial_iter"] * wl["iters"] if wl["flags"] & 4 else 0))
-        traffic = None
-        issue = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            tj = json.load(open(tp))
-            traffic = tj.get("k_initial_dram_bytes_per_launch")
-            issue = issue_roofline(tj, fps, clocks, args.workload, world)
+        init_bytes = px * (R.rows / H) * (BYTES_PER_PX["initial"] + (BYTES_PER_PX["temporal"] if temporal else 0))
+        init_ach = init_bytes / (pass_ms["initial"] * 1e-3) / 1e9 if pass_ms["initial"] > 0 else 0.0
+        traffic = load_traffic(args.workload)
+        # dominant kernel by live event time; algorithmic bytes per launch = SURVEY §8d bytes/px of the part of the pass that
+        # kernel moves x pixels.  At N > 1 the per-kernel probe is skipped: the initial pass as a whole is used.
+        per_kernel = {}
+        for name, ms in kernel_ms.items():
+            e = {"ms": round(ms, 5)}
+            if name in KERNEL_BYTES_PER_PX and ms > 0:
+                nl = wl["iters"] if name == "k_spatial" else 1
+                e["launches_per_frame"] = nl
+                e["algorithmic_gbs"] = round(KERNEL_BYTES_PER_PX[name] * px * nl / (ms * 1e-3) / 1e9, 1)
+            tk = traffic.get(name)
+            if tk and ms > 0:
+                e["dram_bytes_per_launch"] = tk.get("dram_bytes_per_launch")
+                e["dram_gbs"] = round(tk["dram_bytes_per_launch"] * tk.get("launches_per_frame", 1) / (ms * 1e-3) / 1e9, 1)
+            per_kernel[name] = e
+        if kernel_ms:
+            dom = max((n_ for n_ in kernel_ms if n_ in KERNEL_BYTES_PER_PX), key=lambda n_: kernel_ms[n_])
+            nl = wl["iters"] if dom == "k_spatial" else 1
+            dom_ms = kernel_ms[dom] / nl
+            dom_bytes = KERNEL_BYTES_PER_PX[dom] * px
+            roof = {"kernel": dom + (" (RIS stage of the initial pass: G-buffer 64 B + reservoir 32 B written per pixel, M=%d candidates each)" % wl["M"] if dom == "k_ris" else ""),
+                    "bound": "hbm", "achieved": round(dom_bytes / (dom_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(dom_bytes / (dom_ms * 1e-3) / 1e9 / peak, 4),
+                    "traffic": (traffic.get(dom) or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": int(dom_bytes), "launch_ms": round(dom_ms, 5),
+                    "note": "instruction-issue bound, not HBM bound (DESIGN.md §4): see per_kernel for the streaming kernels and profiles/ for issue-slot utilisation"}
+        else:
+            roof = {"kernel": "initial pass (all kernels of restir.rgen main on a volume)", "bound": "hbm", "achieved": round(init_ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(init_ach / peak, 4), "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(init_bytes)}
+        hit_fraction = hits_total / px
         line = {
             "metric": "ReSTIR frames/s", "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_desc(wl),
-            "config": {"workload": wl["desc"], "name": args.workload, "resolution": [W, H], "M": wl["M"], "lights": wl["lights"], "flags": wl["flags"],
-                       "spatial_iterations": wl["iters"], "partition": ("cost-balanced bands (hit-count model corrected by 3 timed calibration rounds) x%d %s, halo 32 rows" % (world, [b[1] - b[0] for b in bands])) if world > 1 else "single GPU",
-                       "l2": "per-frame working set %.0f MB > 126 MB L2 (inputs larger than L2, no flush)" % (px * 240 / 1e6)},
+            "config": config_of(wl, args.workload),
+            "partition": ("cost-balanced bands (hit-count model corrected by 3 timed calibration rounds) x%d %s, halo %d rows (sized from the orbit's reprojection distance)"
+                          % (world, [b[1] - b[0] for b in bands], halo)) if world > 1 else "single GPU",
+            "repetitions_ms_per_step": [round(r_, 5) for r_ in reps], "timed_region_s": round(sum(reps) * args.steps / 1e3, 3),
             "mpixels_per_s": round(px * fps / 1e6, 1), "mpixel_samples_per_s": round(px * wl["M"] * fps / 1e6, 1),
+            "hit_fraction": round(hit_fraction, 4), "hit_pixel_samples_per_s_M": round(hits_total * wl["M"] * fps / 1e6, 1),
             "frame_hbm_gbs": round(frame_bytes * fps / 1e9, 1), "frame_hbm_frac": round(frame_bytes * fps / 1e9 / peak, 4),
             "pass_ms": {k_: round(v, 5) for k_, v in pass_ms.items()},
-            "roofline": {"kernel": "initial pass = k_cover + k_classify + k_primary + k_hit_compact + k_ris_* (M=%d) + k_shadow + k_finish (restir.rgen main on a volume)" % wl["M"], "bound": "hbm",
-                         "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": int(init_bytes)},
+            "initial_pass_roofline": {"achieved": round(init_ach, 1), "frac": round(init_ach / peak, 4), "algorithmic_bytes_per_launch": int(init_bytes)},
+            "roofline": roof, "per_kernel": per_kernel,
             "e2e": {"value": round(1000.0 / e2e_ms, 3), "unit": "frames/s", "h2d_bytes_per_step": 192 + 320 + 20,
                     "d2h_bytes_per_step": int(R.rows * W * 4), "ms_per_step": round(e2e_ms, 4),
                     "result": "presented RGBA8 frame (vrs_present_async, double-buffered, pinned host memory)",
                     "rgba32f_sync_readback_ms_per_step": round(e2e_f32_ms, 4)},
-            "gpu_launches": int(launches * args.steps), "clocks": clocks, "wall_s": round(t_wall, 3),
+            "unbiased": None if unbiased_ms is None else {"value": round(1000.0 / unbiased_ms, 3), "unit": "frames/s", "ms_per_step": round(unbiased_ms, 5),
+                                                          "flags": ub_flags,
+                                                          "what": "same workload with FINALIZE_W + FINAL_VISIBILITY (the configuration tests/test_unbiased.py proves unbiased)"},
+            "temporal_out_of_halo": int(ooh),
+            "gpu_launches": int(launches * args.steps * len(reps)), "clocks": clocks, "wall_s": round(t_wall, 3),
             "per_rank_initial_ms": per_rank_initial if world > 1 else None,
-            "issue_roofline": issue,
+            "issue_roofline": issue_roofline(traffic, fps, clocks, world),
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args.workload, frames=args.cpu_frames)
+            line["cpu_baseline"] = cpu_baseline(args.workload, seconds=args.cpu_seconds)
         print(json.dumps(line), flush=True)
     R.destroy()
     if dist is not None:
@@ -412,25 +566,24 @@ def run_ours(args):
 
 
 def oracle_setup(workload):
-    """The oracle's own scene for a workload (reads assets/*.vrsg with its own numpy reader)."""
+    """The oracle's own scene for a workload: its own numpy .vrsg reader, its own light generator, no libvrs.so in this
+    process (procedural stand-in assets are generated by a child process)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import grid_py
     import oracle as O
     import vdb_py
     O.build()
-    import vrs_pkg
-    V = vrs_pkg.load()     # host-only helper (light generation) — no device use
+    O.set_num_threads(os.cpu_count() or 1)          # launchers pin OMP_NUM_THREADS=1 (torch.distributed.run): use the box
     wl = WORKLOADS[workload]
-    g = grid_py.read_vrsg(asset_path(V, wl["asset"]))
+    g = grid_py.read_vrsg(asset_path(None, wl["asset"]))
     raw, vmin, _ = grid_py.dense_raw(g)
     dens = vdb_py.density_from_raw(raw, g.level_set, g.background)
     probe = O.OracleScene(dens, vmin, g.voxel_size, g.translation, np.ones((1, 8), np.float32))
     lo, hi = probe.world_bbox()
-    ctr = [(a + b) * 0.5 for a, b in zip(lo, hi)]
-    ext = [(b - a) * 0.5 for a, b in zip(lo, hi)]
-    if wl["lights"] < 0:      # emissive-voxel lights, Renderer.cpp:1615-1637 (first voxels in tree order above the threshold)
+
+    def emissive(n):      # emissive-voxel lights, Renderer.cpp:1615-1637 (first voxels in tree order above the threshold)
         thr = np.float32(0.85) * np.float32(g.leaf_value.max())
-        sel = np.argwhere(g.leaf_mask & (g.leaf_value > thr))[:-wl["lights"]]
+        sel = np.argwhere(g.leaf_mask & (g.leaf_value > thr))[:n]
         off = sel[:, 1]
         ijk = g.leaf_origin[sel[:, 0]] + np.stack([off >> 6, (off >> 3) & 7, off & 7], 1)
         lights = np.zeros((len(ijk), 8), np.float32)
@@ -439,60 +592,90 @@ def oracle_setup(workload):
         lights[:, 3] = 1.0
         lights[:, 4:7] = [0.6, 0.2, 0.1]
         lights[:, 7] = np.float32(0.2126) * np.float32(0.6) + np.float32(0.7152) * np.float32(0.2) + np.float32(0.0722) * np.float32(0.1)
-    else:
-        lights = V.generate_point_lights([c - e for c, e in zip(ctr, ext)], [c + e for c, e in zip(ctr, ext)], False, wl["lights"])
+        return lights
+
+    lights, ctr, diag = scene_lights(O.generate_point_lights, wl, lo, hi, emissive)
     wl = dict(wl, lights=len(lights))
     scene = O.OracleScene(dens, vmin, g.voxel_size, g.translation, lights)
-    diag = math.sqrt(sum(e * e for e in ext))
     return O, wl, scene, ctr, diag
 
 
-def oracle_frames(O, wl, scene, ctr, diag, frames, first=0, renderer=None):
+def oracle_frames(O, wl, scene, ctr, diag, frames, first=0, renderer=None, y_rows=None):
+    """Render `frames` frames of the workload's orbit on the oracle; y_rows = (y0, y1) restricts every pass to a band of
+    rows (a bounded sample of the frame: the per-row work is what the full frame does for those rows)."""
     W, H = wl["W"], wl["H"]
     OR = renderer or O.OracleRenderer(scene, W, H, spatial_iterations=wl["iters"])
-    radius = 1.25 * diag
-    prev = None
+    radius = ORBIT_RADIUS * diag
+    prev = O.Camera(orbit_eye(ctr, radius, 0.0, ORBIT_DEG * (first - 1)), ctr) if first > 0 else None
     times = []
     for f in range(first, first + frames):
-        cam = O.Camera(orbit_eye(ctr, radius, 0.0, 6.0 * f), ctr)
+        cam = O.Camera(orbit_eye(ctr, radius, 0.0, ORBIT_DEG * f), ctr)
         gu = O.global_uniforms(cam, W, H)
         ru = O.restir_uniforms(cam, prev, W, H, wl["lights"], M=wl["M"], flags=wl["flags"], k=wl["k"])
         pc = O.PushConstant(0, 0, 0, 0, 1)
         t0 = time.perf_counter()
-        OR.render(gu, ru, pc, f)
+        if y_rows is None:
+            OR.render(gu, ru, pc, f)
+        else:
+            OR.render(gu, ru, pc, f, y0=y_rows[0], y1=y_rows[1])
         times.append(time.perf_counter() - t0)
         prev = cam
     return OR, times
 
 
-def cpu_baseline(workload, frames=20):
+def reference_arm(workload, steps, warmup, budget_s):
+    """The reference math on the host cores.  Each step is one full frame of the workload when the whole run fits the time
+    budget; otherwise every step renders the same centred band of rows (all passes, all M candidates, all reuse) and the
+    frame rate is scaled by the band's share of the frame's hit pixels — the rows differ in cost only through how many of
+    their pixels hit the volume (stated in `sample`)."""
     O, wl, scene, ctr, diag = oracle_setup(workload)
-    OR, _ = oracle_frames(O, wl, scene, ctr, diag, 1)
-    _, times = oracle_frames(O, wl, scene, ctr, diag, frames, first=1, renderer=OR)
-    fps = len(times) / sum(times)
-    return {"value": round(fps, 4), "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
-            "sample": "%d full %dx%d frames of the same workload through oracle/liboracle.so (OpenMP over rows, -O2 -ffp-contract=off)" % (frames, wl["W"], wl["H"])}
+    W, H = wl["W"], wl["H"]
+    OR, t_first = oracle_frames(O, wl, scene, ctr, diag, 1)
+    hit_rows = OR.gbuffer()["worldPos"][..., 3].sum(1).astype(np.float64) + 0.025 * W       # same per-row cost model as the band balancer
+    est_frame = t_first[0]
+    full = est_frame * (steps + warmup) <= budget_s
+    if full:
+        rows, share = None, 1.0
+    else:
+        want = max(budget_s / (steps + warmup) / est_frame, 0.02)                           # share of the frame's cost per step
+        cum = np.cumsum(hit_rows) / hit_rows.sum()
+        mid = int(np.searchsorted(cum, 0.5))
+        y0 = y1 = mid
+        while (cum[min(y1, H - 1)] - (cum[y0 - 1] if y0 > 0 else 0.0)) < want and (y0 > 0 or y1 < H):
+            y0, y1 = max(0, y0 - 4), min(H, y1 + 4)
+        rows = (y0, max(y1, y0 + 8))
+        share = float(hit_rows[rows[0]:rows[1]].sum() / hit_rows.sum())
+    if warmup > 1:
+        oracle_frames(O, wl, scene, ctr, diag, warmup - 1, first=1, renderer=OR, y_rows=rows)
+    _, times = oracle_frames(O, wl, scene, ctr, diag, steps, first=max(1, warmup), renderer=OR, y_rows=rows)
+    ms = 1000.0 * sum(times) / len(times) / share
+    sample = ("each step = one full %dx%d frame of the workload" % (W, H)) if full else \
+             ("each step = rows %d..%d of the %dx%d frame (all passes), %.1f %% of the frame's cost by the hit-pixel row model; frame time = band time / that share"
+              % (rows[0], rows[1], W, H, 100.0 * share))
+    return O, wl, ms, sample
+
+
+def cpu_baseline(workload, seconds=15.0):
+    O, wl, ms, sample = reference_arm(workload, steps=4, warmup=1, budget_s=seconds)
+    return {"value": round(1000.0 / ms, 4), "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
+            "sample": sample + "; oracle/liboracle.so (the reference shader math restated in C++, OpenMP over rows, -O2 -ffp-contract=off)"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    O, wl, scene, ctr, diag = oracle_setup(args.workload)
-    OR, _ = oracle_frames(O, wl, scene, ctr, diag, max(1, args.warmup))
-    _, times = oracle_frames(O, wl, scene, ctr, diag, args.steps, first=args.warmup, renderer=OR)
-    ms = 1000.0 * sum(times) / len(times)
+    O, wl, ms, sample = reference_arm(args.workload, steps=args.steps, warmup=max(1, args.warmup), budget_s=args.reference_seconds)
     fps = 1000.0 / ms
     W, H = wl["W"], wl["H"]
     line = {
         "impl": "reference", "metric": "ReSTIR frames/s", "value": round(fps, 4), "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": data_desc(wl),
-        "config": {"workload": wl["desc"], "name": args.workload, "resolution": [W, H], "M": wl["M"], "lights": wl["lights"], "flags": wl["flags"],
-                   "spatial_iterations": wl["iters"]},
+        "config": config_of(wl, args.workload),
         "cpu_baseline": {"value": round(fps, 4), "unit": "frames/s", "cores": O.num_threads(), "kind": "port",
-                         "sample": "each step = one full %dx%d frame of the workload on the host cores (oracle/liboracle.so: the reference shader math "
-                                   "restated in C++, OpenMP over rows; the reference's own Vulkan-RT binary cannot run here)" % (W, H)},
+                         "sample": sample + " on the host cores (oracle/liboracle.so: the reference shader math restated in C++, OpenMP over rows; "
+                                            "the reference's own Vulkan-RT binary cannot run here)"},
         "e2e": {"value": round(fps, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mpixel_samples_per_s": round(W * H * wl["M"] * fps / 1e6, 2),
     }
@@ -502,13 +685,15 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="smoke_1080p_temporal", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="multi-GPU halo exchange: NVLink peer-memory kernel or NCCL send/recv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=20)
+    ap.add_argument("--no-unbiased", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="time budget of the cpu_baseline leg")
+    ap.add_argument("--reference-seconds", type=float, default=150.0, help="time budget of --impl reference (all steps)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -18,7 +18,7 @@
 extern "C" {
 #endif
 
-#define VRS_ABI_VERSION 1
+#define VRS_ABI_VERSION 2
 
 typedef enum {
   VRS_OK = 0,
@@ -27,7 +27,7 @@ typedef enum {
   VRS_ERR_IO = 3,           /* file could not be read / written */
   VRS_ERR_FORMAT = 4,       /* unsupported or corrupt .vdb / .vrsg content */
   VRS_ERR_UNSUPPORTED = 5,  /* feature outside the hot path (e.g. triangle lights) */
-  VRS_ERR_COMM = 6,         /* NCCL error */
+  VRS_ERR_COMM = 6,         /* NCCL error, or a halo exchange that timed out / left the stored rows (see vrs_get_counters) */
   VRS_ERR_NO_DEVICE = 7
 } vrs_status;
 
@@ -100,6 +100,11 @@ void       vrs_default_config(vrs_config* cfg, uint32_t width, uint32_t height);
 void       vrs_default_restir_uniforms(vrs_restir_uniforms* u, uint32_t width, uint32_t height);
 vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out);
 void       vrs_destroy(vrs_ctx* ctx);                                  /* RestirPass::destroy restirPass.h:35 */
+/* RestirPass::createRenderPass(VkExtent2D) / SpatialReusePass::createRenderPass (src/passes/restirPass.cpp:79-81,
+ * spatialReusePass.cpp:41-43), Renderer::onResize (src/Renderer.cpp:1022-1026) and the createGBuffers / createRestirBuffer it implies: new per-pixel buffers
+ * for width x height (whole image, no band), grid and lights stay staged, the temporal history is dropped.
+ * Not available on a context that is part of a multi-GPU group (VRS_ERR_INVALID): re-create the group instead. */
+vrs_status vrs_resize(vrs_ctx* ctx, uint32_t width, uint32_t height);
 const char* vrs_last_error(const vrs_ctx* ctx);                        /* ctx may be NULL: last create error */
 int        vrs_abi_version(void);
 
@@ -201,6 +206,17 @@ vrs_status vrs_get_timings(vrs_ctx* ctx, vrs_timings* out);
    frame.  enabled = 0 leaves them out (vrs_get_timings then fails with VRS_ERR_INVALID until re-enabled and a frame ran). */
 vrs_status vrs_set_pass_timing(vrs_ctx* ctx, int enabled);
 void*      vrs_stream(vrs_ctx* ctx);                                                    /* cudaStream_t */
+/* Work counters of the last frame (valid after vrs_synchronize) and the cumulative health counters of the halo exchange:
+ * temporal_out_of_halo = hit pixels whose temporal reprojection fell on a row of the image this context does not store
+ * (halo_rows too small for the camera motion: those merges were skipped, the frame differs from a single-GPU frame);
+ * comm_timeouts = halo waits that gave up (a neighbour never published its rows). */
+typedef struct { uint32_t candidates, hits, shadow_rays, temporal_out_of_halo, comm_timeouts; } vrs_counters;
+vrs_status vrs_get_counters(vrs_ctx* ctx, vrs_counters* out);
+/* Per-kernel CUDA-event times of the last frame.  While enabled, frames are launched kernel by kernel (no CUDA graph)
+ * with an event after every kernel on the context stream; meant for a short probe next to the timed loops. */
+typedef struct { char name[40]; float ms; } vrs_kernel_time;
+vrs_status vrs_set_kernel_timing(vrs_ctx* ctx, int enabled);
+vrs_status vrs_get_kernel_times(vrs_ctx* ctx, vrs_kernel_time* out, uint32_t capacity, uint32_t* count);
 
 /* ---- multi-GPU: screen-space bands, grid replicated, halo rows exchanged over NCCL ---------- */
 /* 128-byte ncclUniqueId produced on rank 0 and broadcast by the launcher (torch.distributed / MPI / file). */
@@ -214,6 +230,10 @@ vrs_status vrs_comm_init(vrs_ctx* ctx, const uint8_t id128[128], int rank, int n
 #define VRS_PEER_BLOB_BYTES 1152
 vrs_status vrs_peer_export(vrs_ctx* ctx, uint8_t blob[VRS_PEER_BLOB_BYTES]);
 vrs_status vrs_peer_connect(vrs_ctx* ctx, int rank, int nranks, const uint8_t* all_blobs /* nranks x VRS_PEER_BLOB_BYTES */);
+/* The same wiring between contexts of ONE process (any mix of devices with peer access, or several bands on one device):
+ * `up` / `down` are the contexts that render the bands above / below this one (NULL at the image edges).  Frames of the
+ * connected contexts must all be enqueued before any of them is synchronized (each waits for its neighbours' rows). */
+vrs_status vrs_peer_connect_local(vrs_ctx* ctx, vrs_ctx* up, vrs_ctx* down);
 /* Even band split of `height` rows over nranks (helper for launchers). */
 void       vrs_band_for_rank(uint32_t height, int rank, int nranks, uint32_t* y0, uint32_t* y1);
 

@@ -297,9 +297,11 @@ class OracleRenderer:
         self.final_res = 0   # index into f.res of the last frame's final reservoirs
 
     def render(self, gu, ru, pc, clock, y0=0, y1=None, exchange=None):
-        """`exchange(planes)` (multi-rank band mode) is called at the points where libvrs exchanges halo rows:
-        after the initial pass (G-buffer + reservoirs), between spatial iterations (reservoirs) and after the frame
-        (what the next frame's temporal reuse reads) — the schedule of vrs_render_frame."""
+        """`exchange(planes, kind)` (multi-rank band mode) is called at the points where libvrs exchanges halo rows:
+        kind "spatial" after the initial pass (G-buffer + reservoirs) and between spatial iterations (reservoirs) — only the
+        ceil(spatialRadius) rows spatial reuse can reach travel; kind "temporal" after the frame (libvrs: at the start of the
+        next one) with the previous G-buffer + final reservoirs over ALL halo rows, which the temporal reprojection may reach
+        — the schedule of vrs_render_frame."""
         L, f, s = lib(), self.f, self.scene.c
         y1 = self.H if y1 is None else y1
         cur_g, prev_g = f.g[self.cur], f.g[1 - self.cur]
@@ -311,7 +313,7 @@ class OracleRenderer:
         g_planes = [cur_g[k] for k in ("worldPos", "albedo", "normal", "matProps")]
         r_planes = lambda i: [f.res[i]["info"], f.res[i]["weight"]]
         if exchange and spatial:
-            exchange(g_planes + r_planes(src))
+            exchange(g_planes + r_planes(src), "spatial")
         if spatial:
             for it in range(self.iters):
                 dst = (src + 1) % 3
@@ -319,11 +321,11 @@ class OracleRenderer:
                                    Frame.rbuf(f.res[src]), Frame.rbuf(f.res[dst]))
                 src = dst
                 if exchange and it + 1 < self.iters:
-                    exchange(r_planes(src))
+                    exchange(r_planes(src), "spatial")
         L.orc_pass_shade(C.byref(s), C.byref(ru), C.byref(pc), C.c_uint32(clock), y0, y1, Frame.gbuf(cur_g),
                          Frame.rbuf(f.res[src]), _p(f.accum))
         if exchange and (ru.flags & FLAG_TEMPORAL):
-            exchange((g_planes if not spatial else []) + r_planes(src))
+            exchange(g_planes + r_planes(src), "temporal")
         self.final_res = src
         self.last_g = self.cur
         self.cur = 1 - self.cur
@@ -345,3 +347,7 @@ def path_trace(scene, gu, ru, spp, seed_base=1):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def set_num_threads(n):
+    lib().orc_set_num_threads(int(n))

@@ -905,6 +905,14 @@ void orc_path_trace(const orc_scene* s, const orc_global_uniforms* gu, const orc
   }
 }
 
+// OMP_NUM_THREADS may have been pinned to 1 by a launcher (torch.distributed.run does that): the caller states the count.
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -113,6 +113,7 @@ void orc_pass_shade(const orc_scene* s, const orc_restir_uniforms* ru, const orc
 /* brute-force estimator of the same integrand: spp independent (primary event, light) samples per pixel */
 void orc_path_trace(const orc_scene* s, const orc_global_uniforms* gu, const orc_restir_uniforms* ru,
                     uint32_t spp, uint32_t seed_base, float* out_rgb /* W*H*3 */);
+void orc_set_num_threads(int n);
 int  orc_num_threads(void);
 
 #ifdef __cplusplus

@@ -29,7 +29,7 @@ def test_header_symbols_exported(V):
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, missing
     assert sorted(V.EXPORTS) == declared
-    assert L.vrs_abi_version() == 1
+    assert L.vrs_abi_version() == 2
 
 
 def test_struct_layouts_match_reference(V):
@@ -188,19 +188,36 @@ def test_bench_row_split_balances_cost_and_keeps_halo():
 
 
 def test_bench_issue_roofline_helper():
-    """bench.py's extra "issue_roofline" object: warp instructions per frame (committed ncu launch list) x live frames/s
-    over 148 SMs x 4 schedulers x SM clock; None whenever its inputs do not apply, never an exception."""
-    import json
-    import os
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    sys.path.insert(0, root)
+    """bench.py's extra "issue_roofline" object: warp instructions per frame (committed ncu launch list of the workload) x
+    live frames/s over 148 SMs x 4 schedulers x SM clock; None whenever its inputs do not apply, never an exception."""
     import bench
-    tj = json.load(open(os.path.join(root, "profiles", "traffic.json")))
-    r = bench.issue_roofline(tj, 2000.0, {"sm_mhz": 1965.0}, "smoke_1080p_temporal", 1)
-    want = sum(k["warp_inst_M"] for k in tj["per_kernel"].values()) * 1e6 * 2000.0 / (148 * 4 * 1965.0e6)
+    tr = bench.load_traffic(bench.DEFAULT_WORKLOAD)
+    assert tr and "k_ris" in tr
+    r = bench.issue_roofline(tr, 450.0, {"sm_mhz": 1965.0}, 1)
+    want = sum(k["warp_inst_M"] * k.get("launches_per_frame", 1) for k in tr.values()) * 1e6 * 450.0 / (148 * 4 * 1965.0e6)
     assert r is not None and abs(r["frac"] - want) < 1e-3 and 0.0 < r["frac"] < 1.0
-    assert bench.issue_roofline(tj, 2000.0, None, "smoke_1080p_temporal", 1) is None
-    assert bench.issue_roofline(tj, 2000.0, {"sm_mhz": 1965.0}, "bunny_4k_full", 1) is None
-    assert bench.issue_roofline(tj, 2000.0, {"sm_mhz": 1965.0}, "smoke_1080p_temporal", 8) is None
-    assert bench.issue_roofline({"per_kernel": {"k": {}}}, 2000.0, {"sm_mhz": 1965.0}, "smoke_1080p_temporal", 1) is None
+    assert bench.issue_roofline(tr, 450.0, None, 1) is None
+    assert bench.issue_roofline({}, 450.0, {"sm_mhz": 1965.0}, 1) is None
+    assert bench.issue_roofline(tr, 450.0, {"sm_mhz": 1965.0}, 8) is None
+    assert bench.issue_roofline({"k": {}}, 450.0, {"sm_mhz": 1965.0}, 1) is None
+    assert bench.load_traffic("no_such_workload") == {}
+
+
+def test_bench_halo_rows_cover_the_orbit(V):
+    """bench.py sizes the band halo from the camera orbit: the fixed 32 rows of round 1 are too few for 6 deg/frame."""
+    import bench
+    lo, hi = [-4.0, 0.5, -2.0], [1.0, 6.0, 3.0]
+    ctr = [(a + b) * 0.5 for a, b in zip(lo, hi)]
+    diag = float(np.sqrt(sum(((b - a) * 0.5) ** 2 for a, b in zip(lo, hi))))
+    h1080 = bench.temporal_halo_rows(V, dict(W=1920, H=1080), lo, hi, ctr, diag)
+    h4k = bench.temporal_halo_rows(V, dict(W=3840, H=2160), lo, hi, ctr, diag)
+    assert h1080 % 8 == 0 and 32 < h1080 < 200 and h1080 < h4k < 400
+    assert abs(h4k - 2 * h1080) <= 16                                    # reprojection distance scales with the resolution
+
+
+def test_bench_config_is_identical_for_both_arms():
+    import bench
+    wl = dict(bench.WORKLOADS[bench.DEFAULT_WORKLOAD])
+    assert bench.DEFAULT_WORKLOAD == "bunny_4k_full" and wl["W"] == 3840 and wl["iters"] == 2 and wl["flags"] == 7
+    c = bench.config_of(wl, bench.DEFAULT_WORKLOAD)
+    assert "partition" not in c and c["name"] == "bunny_4k_full" and c["resolution"] == [3840, 2160]

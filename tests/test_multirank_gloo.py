@@ -19,21 +19,21 @@ def free_port():
     return port
 
 
-def halo_exchange(dist, torch, planes, rank, world, band, halo, H):
-    """Python mirror of vrs::comm_exchange_halo (csrc/vrs_comm.cpp): first/last own rows -> neighbours' halo rows."""
+def halo_exchange(dist, torch, planes, rank, world, band, halo, H, max_rows):
+    """Python mirror of vrs::comm_exchange_halo (csrc/vrs_comm.cpp): first/last own rows -> neighbours' halo rows, at most
+    `max_rows` of them (spatial exchanges move ceil(spatialRadius) rows, the temporal one the whole halo)."""
     y0, y1 = band
     ops = []
     for p in planes:
         t = torch.from_numpy(p)
+        n = min(halo, y1 - y0, max_rows)
         if rank > 0:
-            n = min(halo, y1 - y0)
             ops.append(dist.P2POp(dist.isend, t[y0:y0 + n].contiguous(), rank - 1))
-            lo = max(0, y0 - halo)
+            lo = max(0, y0 - min(halo, max_rows))
             ops.append(dist.P2POp(dist.irecv, t[lo:y0], rank - 1))
         if rank < world - 1:
-            n = min(halo, y1 - y0)
             ops.append(dist.P2POp(dist.isend, t[y1 - n:y1].contiguous(), rank + 1))
-            hi = min(H, y1 + halo)
+            hi = min(H, y1 + min(halo, max_rows))
             ops.append(dist.P2POp(dist.irecv, t[y1:hi], rank + 1))
     for r in dist.batch_isend_irecv(ops):
         r.wait()
@@ -47,7 +47,7 @@ def worker(rank, world, port, flags, frames, out_dir):
     import vrs_pkg
     V = vrs_pkg.load()
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
-    W, H, halo = 96, 36 * world, 32      # bands must be at least as tall as the halo (vrs_comm_init enforces it)
+    W, H, halo, radius = 96, 44 * world, 40, 12.0      # bands must be at least as tall as the halo (vrs_comm_init enforces it)
     lights = V.generate_point_lights([-4.2, -0.2, -1.4], [-1.5, 5.2, 1.6], False, 16)
     scene = common.oracle_scene(O, "smoke", lights)
     lo, hi = scene.world_bbox()
@@ -60,10 +60,11 @@ def worker(rank, world, port, flags, frames, out_dir):
     for f in range(frames):
         cam = O.Camera(common.orbit_eye(ctr, 4.5, 0.3, 20.0 + 1.5 * f), ctr)
         gu = O.global_uniforms(cam, W, H)
-        ru = O.restir_uniforms(cam, prev, W, H, len(lights), M=8, flags=flags, k=5, radius=30.0)
+        ru = O.restir_uniforms(cam, prev, W, H, len(lights), M=8, flags=flags, k=5, radius=radius)
         pc = O.PushConstant(0, 0, 0, f, 1 if f < 2 else 0)
         img = OR.render(gu, ru, pc, f, band[0], band[1],
-                        exchange=lambda planes: halo_exchange(dist, torch, planes, rank, world, band, halo, H))
+                        exchange=lambda planes, kind: halo_exchange(dist, torch, planes, rank, world, band, halo, H,
+                                                                    halo if kind == "temporal" else int(np.ceil(radius))))
         mine = torch.from_numpy(np.ascontiguousarray(img[band[0]:band[1]]))
         parts = [torch.zeros((V.band_for_rank(H, r, world)[1] - V.band_for_rank(H, r, world)[0], W, 4)) for r in range(world)] if rank == 0 else None
         dist.gather(mine, parts, dst=0)

@@ -32,7 +32,8 @@ EXPORTS = [
     "vrs_generate_point_lights", "vrs_perspectiveVK", "vrs_look_at", "vrs_invert", "vrs_mat4_mul", "vrs_pass_initial",
     "vrs_pass_spatial", "vrs_pass_shade", "vrs_render_frame", "vrs_synchronize", "vrs_read_frame", "vrs_read_gbuffer",
     "vrs_read_reservoirs", "vrs_read_trace", "vrs_read_display", "vrs_present_async", "vrs_present_wait", "vrs_write_image", "vrs_get_timings", "vrs_set_pass_timing", "vrs_stream", "vrs_comm_unique_id",
-    "vrs_comm_init", "vrs_peer_export", "vrs_peer_connect", "vrs_band_for_rank",
+    "vrs_comm_init", "vrs_peer_export", "vrs_peer_connect", "vrs_peer_connect_local", "vrs_band_for_rank",
+    "vrs_resize", "vrs_get_counters", "vrs_set_kernel_timing", "vrs_get_kernel_times",
 ]
 
 
@@ -92,6 +93,15 @@ class Timings(C.Structure):
                 ("frame_ms", C.c_float), ("launches", C.c_uint32)]
 
 
+class Counters(C.Structure):
+    _fields_ = [("candidates", C.c_uint32), ("hits", C.c_uint32), ("shadow_rays", C.c_uint32),
+                ("temporal_out_of_halo", C.c_uint32), ("comm_timeouts", C.c_uint32)]
+
+
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 40), ("ms", C.c_float)]
+
+
 def build(verbose=False):
     """Compile libvrs.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     out = None if verbose else subprocess.DEVNULL
@@ -120,7 +130,8 @@ def lib():
                      "vrs_grid_sample_device", "vrs_set_lights", "vrs_collect_emissive_lights", "vrs_vdb_emissive_lights", "vrs_set_triangle_lights", "vrs_get_alias_table",
                      "vrs_pass_initial", "vrs_pass_spatial", "vrs_pass_shade", "vrs_render_frame", "vrs_synchronize",
                      "vrs_read_frame", "vrs_read_gbuffer", "vrs_read_reservoirs", "vrs_read_trace", "vrs_write_image",
-                     "vrs_get_timings", "vrs_set_pass_timing", "vrs_comm_init", "vrs_read_display", "vrs_present_async", "vrs_present_wait"]:
+                     "vrs_get_timings", "vrs_set_pass_timing", "vrs_comm_init", "vrs_read_display", "vrs_present_async", "vrs_present_wait",
+                     "vrs_resize", "vrs_get_counters", "vrs_set_kernel_timing", "vrs_get_kernel_times", "vrs_peer_connect_local"]:
             getattr(L, name).restype = C.c_int
         L.vrs_load_vdb.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.vrs_load_vrsg.argtypes = [C.c_void_p, C.c_char_p]
@@ -155,6 +166,11 @@ def lib():
         L.vrs_peer_export.restype = C.c_int
         L.vrs_peer_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vrs_peer_connect.restype = C.c_int
+        L.vrs_peer_connect_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vrs_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.vrs_get_counters.argtypes = [C.c_void_p, C.c_void_p]
+        L.vrs_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
+        L.vrs_get_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.vrs_create_alias_table.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.vrs_generate_point_lights.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
         L.vrs_band_for_rank.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -485,6 +501,32 @@ class Renderer:
 
     def stream(self):
         return lib().vrs_stream(self._ctx)
+
+    def resize(self, width, height):
+        """RestirPass / SpatialReusePass::createRenderPass(VkExtent2D) + the buffer re-creation a window resize implies."""
+        self._ck(lib().vrs_resize(self._ctx, width, height))
+        self.width, self.height, self.band, self.rows = width, height, (0, height), height
+        self.m_restirUniforms.screenSize[0], self.m_restirUniforms.screenSize[1] = width, height
+        self._ref_cam = None
+
+    def counters(self):
+        c = Counters()
+        self._ck(lib().vrs_get_counters(self._ctx, C.byref(c)))
+        return c
+
+    def setKernelTiming(self, enabled):
+        self._ck(lib().vrs_set_kernel_timing(self._ctx, int(bool(enabled))))
+
+    def kernelTimes(self):
+        """[(kernel name, ms)] of the last frame, in launch order (setKernelTiming(True) frames only)."""
+        buf = (KernelTime * 64)()
+        n = C.c_uint32()
+        self._ck(lib().vrs_get_kernel_times(self._ctx, buf, 64, C.byref(n)))
+        return [(buf[i].name.decode(), float(buf[i].ms)) for i in range(n.value)]
+
+    def peerConnectLocal(self, up=None, down=None):
+        """Wire this band to the contexts rendering the bands above / below it in the same process."""
+        self._ck(lib().vrs_peer_connect_local(self._ctx, up._ctx if up is not None else None, down._ctx if down is not None else None))
 
     def peerExport(self):
         """CUDA-IPC handles of this context's planes (bytes) for the peer-memory halo exchange."""

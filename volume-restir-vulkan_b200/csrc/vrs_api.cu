@@ -78,6 +78,10 @@ struct vrs_ctx {
   unsigned* xflags = nullptr;                // [0] flag written by the up neighbour, [1] by the down neighbour, [2] serial, [3] block counter, [4] error
   cudaStream_t comm_stream = nullptr;        // halo exchanges run here so that they can overlap the next kernels
   cudaEvent_t ev_halo_src = nullptr, ev_halo_done = nullptr;
+  bool history_valid = false;                // false: the previous frame's buffers do not belong to this scene / size (first frame, new lights, new grid, resize)
+  KTimer kt{};                               // optional per-kernel event timing (vrs_set_kernel_timing): frames then launch eagerly
+  bool kt_events = false;
+  uint32_t comm_timeouts = 0;
 };
 
 static std::string g_create_error;
@@ -100,6 +104,48 @@ extern "C" {
 
 const char* vrs_last_error(const vrs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+// Everything whose size depends on the image: per-pixel planes, work queues, display staging (vrs_create / vrs_resize).
+static void free_frame_buffers(vrs_ctx* ctx) {
+  for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) { cudaFree(ctx->g_planes[i][p]); ctx->g_planes[i][p] = nullptr; }
+  for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) { cudaFree(ctx->r_planes[i][p]); ctx->r_planes[i][p] = nullptr; }
+  cudaFree(ctx->accum); ctx->accum = nullptr; cudaFree(ctx->trace); ctx->trace = nullptr;
+  Queues& Q = ctx->queues;
+  cudaFree(Q.counters); cudaFree(Q.cand); cudaFree(Q.cand_ray); cudaFree(Q.flag); cudaFree(Q.block_count); cudaFree(Q.hit_pix);
+  cudaFree(Q.hit_seed); cudaFree(Q.hit_T); cudaFree(Q.shadow); cudaFree(Q.shadow_ray); cudaFree(Q.cover);
+  memset(&Q, 0, sizeof(Q));
+  for (int i = 0; i < 2; ++i) { cudaFree(ctx->display[i]); ctx->display[i] = nullptr; }
+}
+static vrs_status alloc_frame_buffers(vrs_ctx* ctx) {
+  const vrs_config* cfg = &ctx->cfg;
+  ctx->W = cfg->width; ctx->H = cfg->height;
+  ctx->band_y0 = (int)cfg->band_y0; ctx->band_y1 = cfg->band_y1 ? (int)cfg->band_y1 : (int)cfg->height;
+  if (ctx->band_y1 > (int)ctx->H || ctx->band_y0 >= ctx->band_y1) return fail(ctx, VRS_ERR_INVALID, "bad band");
+  ctx->store_y0 = ctx->band_y0 - (int)cfg->halo_rows; if (ctx->store_y0 < 0) ctx->store_y0 = 0;
+  ctx->store_y1 = ctx->band_y1 + (int)cfg->halo_rows; if (ctx->store_y1 > (int)ctx->H) ctx->store_y1 = (int)ctx->H;
+  ctx->npix = (size_t)(ctx->store_y1 - ctx->store_y0) * ctx->W;
+  if (ctx->npix >= ((size_t)1 << 32)) return fail(ctx, VRS_ERR_UNSUPPORTED, "more than 2^32 stored pixels per context");
+  auto alloc = [&](void** p, size_t bytes) {
+    if (cudaMalloc(p, bytes) != cudaSuccess) { ctx->err = "cudaMalloc failed (" + std::to_string(bytes) + " bytes)"; return false; }
+    return cudaMemset(*p, 0, bytes) == cudaSuccess;
+  };
+  for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) if (!alloc((void**)&ctx->g_planes[i][p], ctx->npix * 16)) return VRS_ERR_CUDA;
+  for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) if (!alloc((void**)&ctx->r_planes[i][p], ctx->npix * 16)) return VRS_ERR_CUDA;
+  if (!alloc((void**)&ctx->accum, ctx->npix * 16)) return VRS_ERR_CUDA;
+  if (cfg->enable_trace && !alloc((void**)&ctx->trace, ctx->npix * 16)) return VRS_ERR_CUDA;
+  Queues& Q = ctx->queues;
+  const size_t ncompact = (ctx->npix + 2047) / 2048 + 1;
+  if (!alloc((void**)&Q.counters, 64) || !alloc((void**)&Q.cand, ctx->npix * 4) || !alloc((void**)&Q.cand_ray, ctx->npix * 32) ||
+      !alloc((void**)&Q.flag, ctx->npix + 16) || !alloc((void**)&Q.block_count, ncompact * 4) || !alloc((void**)&Q.hit_pix, ctx->npix * 4) ||
+      !alloc((void**)&Q.hit_seed, ctx->npix * 4) || !alloc((void**)&Q.hit_T, ctx->npix * 4) || !alloc((void**)&Q.shadow, ctx->npix * 4) ||
+      !alloc((void**)&Q.shadow_ray, ctx->npix * 32) || !alloc((void**)&Q.cover, ((size_t)(ctx->W + 7) / 8) * ((size_t)(ctx->H + 7) / 8) + 16))
+    return VRS_ERR_CUDA;
+  for (int i = 0; i < 2; ++i) if (!alloc((void**)&ctx->display[i], ctx->npix * 4)) return VRS_ERR_CUDA;
+  ctx->cur_g = ctx->last_g = ctx->final_r = ctx->src_r = 0;
+  ctx->present_count = 0;
+  ctx->history_valid = false;
+  return VRS_OK;
+}
+
 vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
   if (!cfg || !out || cfg->width == 0 || cfg->height == 0) return fail(nullptr, VRS_ERR_INVALID, "vrs_create: bad config");
   int ndev = 0;
@@ -110,30 +156,14 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
   auto bail = [&](vrs_status s) { g_create_error = ctx->err; vrs_destroy(ctx); return s; };
   if (cfg->device >= 0) ctx->device = cfg->device; else if (cudaGetDevice(&ctx->device) != cudaSuccess) ctx->device = 0;
   if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(VRS_ERR_CUDA); }
-  ctx->W = cfg->width; ctx->H = cfg->height;
-  ctx->band_y0 = (int)cfg->band_y0; ctx->band_y1 = cfg->band_y1 ? (int)cfg->band_y1 : (int)cfg->height;
-  if (ctx->band_y1 > (int)ctx->H || ctx->band_y0 >= ctx->band_y1) { ctx->err = "vrs_create: bad band"; return bail(VRS_ERR_INVALID); }
   if (cfg->spatial_iterations > VRS_MAX_SPATIAL_ITERATIONS) { ctx->err = "vrs_create: spatial_iterations > 4"; return bail(VRS_ERR_INVALID); }
-  ctx->store_y0 = ctx->band_y0 - (int)cfg->halo_rows; if (ctx->store_y0 < 0) ctx->store_y0 = 0;
-  ctx->store_y1 = ctx->band_y1 + (int)cfg->halo_rows; if (ctx->store_y1 > (int)ctx->H) ctx->store_y1 = (int)ctx->H;
-  ctx->npix = (size_t)(ctx->store_y1 - ctx->store_y0) * ctx->W;
   auto alloc = [&](void** p, size_t bytes) {
     if (cudaMalloc(p, bytes) != cudaSuccess) { ctx->err = "cudaMalloc failed (" + std::to_string(bytes) + " bytes)"; return false; }
     return cudaMemset(*p, 0, bytes) == cudaSuccess;
   };
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
-  for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) if (!alloc((void**)&ctx->g_planes[i][p], ctx->npix * 16)) return bail(VRS_ERR_CUDA);
-  for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) if (!alloc((void**)&ctx->r_planes[i][p], ctx->npix * 16)) return bail(VRS_ERR_CUDA);
-  if (!alloc((void**)&ctx->accum, ctx->npix * 16)) return bail(VRS_ERR_CUDA);
-  if (cfg->enable_trace && !alloc((void**)&ctx->trace, ctx->npix * 16)) return bail(VRS_ERR_CUDA);
+  if (vrs_status s = alloc_frame_buffers(ctx)) return bail(s);
   {
-    Queues& Q = ctx->queues;
-    const size_t ncompact = (ctx->npix + 2047) / 2048 + 1;
-    if (!alloc((void**)&Q.counters, 64) || !alloc((void**)&Q.cand, ctx->npix * 4) || !alloc((void**)&Q.cand_ray, ctx->npix * 32) ||
-        !alloc((void**)&Q.flag, ctx->npix + 16) || !alloc((void**)&Q.block_count, ncompact * 4) || !alloc((void**)&Q.hit_pix, ctx->npix * 4) ||
-        !alloc((void**)&Q.hit_seed, ctx->npix * 4) || !alloc((void**)&Q.hit_T, ctx->npix * 4) || !alloc((void**)&Q.shadow, ctx->npix * 4) ||
-        !alloc((void**)&Q.shadow_ray, ctx->npix * 32) || !alloc((void**)&Q.cover, ((size_t)(ctx->W + 7) / 8) * ((size_t)(ctx->H + 7) / 8) + 16))
-      return bail(VRS_ERR_CUDA);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) ctx->persistent_blocks = prop.multiProcessorCount * (getenv("VRS_BLOCKS_PER_SM") ? atoi(getenv("VRS_BLOCKS_PER_SM")) : 12);
   }
@@ -143,15 +173,13 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
       cudaHostAlloc((void**)&ctx->h_params, sizeof(FrameParams) * VRS_PARAM_SLOTS, cudaHostAllocDefault) != cudaSuccess) { ctx->err = "param alloc failed"; return bail(VRS_ERR_CUDA); }
   for (int i = 0; i < VRS_PARAM_SLOTS; ++i)
     if (cudaEventCreateWithFlags(&ctx->param_ev[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
-  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&ctx->ev_halo_src, cudaEventDisableTiming) != cudaSuccess ||
+  // (copy_stream and comm_stream are created on first use: a context that never presents / never uses NCCL holds one stream,
+  // which keeps several band contexts of one process on distinct hardware queues)
+  if (cudaEventCreateWithFlags(&ctx->ev_halo_src, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&ctx->ev_halo_done, cudaEventDisableTiming) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
-  for (int i = 0; i < 2; ++i) {
-    if (!alloc((void**)&ctx->display[i], ctx->npix * 4)) return bail(VRS_ERR_CUDA);
+  for (int i = 0; i < 2; ++i)
     if (cudaEventCreateWithFlags(&ctx->display_ready[i], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->copy_done[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
-  }
   cudaDeviceSynchronize();
   *out = ctx;
   return VRS_OK;
@@ -176,20 +204,14 @@ void vrs_destroy(vrs_ctx* ctx) {
   for (vrs_ctx::Peer* p : {&ctx->peer_up, &ctx->peer_down}) for (void* q : p->opened) cudaIpcCloseMemHandle(q);
   cudaFree(ctx->xflags);
   free_grid(ctx);
-  for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) cudaFree(ctx->g_planes[i][p]);
-  for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) cudaFree(ctx->r_planes[i][p]);
-  cudaFree(ctx->accum); cudaFree(ctx->trace); cudaFree(ctx->d_lights); cudaFree(ctx->d_alias);
-  {
-    Queues& Q = ctx->queues;
-    cudaFree(Q.counters); cudaFree(Q.cand); cudaFree(Q.cand_ray); cudaFree(Q.flag); cudaFree(Q.block_count); cudaFree(Q.hit_pix);
-    cudaFree(Q.hit_seed); cudaFree(Q.hit_T); cudaFree(Q.shadow); cudaFree(Q.shadow_ray); cudaFree(Q.cover);
-  }
+  free_frame_buffers(ctx);
+  cudaFree(ctx->d_lights); cudaFree(ctx->d_alias);
+  if (ctx->kt_events) for (int i = 0; i <= KTimer::MAX; ++i) cudaEventDestroy(ctx->kt.ev[i]);
   for (int i = 0; i < 8; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (int i = 0; i < VRS_PARAM_SLOTS; ++i) if (ctx->param_ev[i]) cudaEventDestroy(ctx->param_ev[i]);
   cudaFree(ctx->d_params); if (ctx->h_params) cudaFreeHost(ctx->h_params);
   for (int i = 0; i < 2; ++i) {
-    cudaFree(ctx->display[i]);
     if (ctx->display_ready[i]) cudaEventDestroy(ctx->display_ready[i]);
     if (ctx->copy_done[i]) cudaEventDestroy(ctx->copy_done[i]);
   }
@@ -289,6 +311,7 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
   }
   invalidate_graphs(ctx);   // captured pointers are stale now
   ctx->has_grid = true;
+  ctx->history_valid = false;   // the previous frame's G-buffer / reservoirs describe another volume
   return VRS_OK;
 }
 
@@ -382,6 +405,7 @@ vrs_status vrs_set_lights(vrs_ctx* ctx, const vrs_point_light* lights, uint32_t 
   CK(cudaMemcpy(ctx->d_alias, ctx->alias_host.data(), (size_t)n * sizeof(vrs_alias_table_cell), cudaMemcpyHostToDevice));
   ctx->lights.lights = (const float4*)ctx->d_lights; ctx->lights.alias = (const float4*)ctx->d_alias;
   ctx->lights.nlights = (int)n; ctx->lights.ntable = (int)n;
+  ctx->history_valid = false;   // stored reservoirs hold indices into the old light table: no temporal merge on the next frame
   return VRS_OK;
 }
 vrs_status vrs_collect_emissive_lights(const vrs_ctx* ctx, float threshold, uint32_t max_lights, vrs_point_light* out, uint32_t* count) {
@@ -486,6 +510,7 @@ static vrs_status make_params(vrs_ctx* ctx, const vrs_global_uniforms* gu, const
   F.W = ctx->W; F.H = ctx->H; F.M = ru->initialLightSampleCount; F.temporalMult = ru->temporalSampleCountMultiplier;
   F.spatialNeighbors = ru->spatialNeighbors; F.spatialRadius = ru->spatialRadius; F.fireflyClamp = ru->fireflyClampThreshold;
   F.flags = ru->flags; F.clock = clock;
+  if (!ctx->history_valid) F.flags &= ~VRS_RESTIR_TEMPORAL_REUSE_FLAG;   // first frame / new lights / new grid / resize: nothing valid to merge
   if (pc) { F.clear[0] = pc->clearColorRed; F.clear[1] = pc->clearColorGreen; F.clear[2] = pc->clearColorBlue; F.frame = pc->frame; F.initialize = pc->initialize; }
   return VRS_OK;
 }
@@ -504,7 +529,9 @@ static vrs_status upload_params(vrs_ctx* ctx, const FrameParams& F) {
 
 // Halo exchange on the communication stream, forked from and joined back into the main stream with events (the same
 // calls work under stream capture).  `wait_now` false leaves the join to the consumer (k_finish waits on ev_halo_done).
-static vrs_status exchange(vrs_ctx* ctx, bool gbuf, int g_index, int r_index, bool wait_now) {
+// `max_rows` limits the rows sent per side (spatial reuse needs ceil(spatialRadius) rows, the temporal reprojection all
+// halo rows the neighbour stores).
+static vrs_status exchange(vrs_ctx* ctx, bool gbuf, int g_index, int r_index, bool wait_now, int max_rows) {
   if (ctx->peer_mode) {
     // one kernel stores the boundary rows into both neighbours' halo rows (NVLink P2P) and publishes the serial;
     // the wait kernel (consumer side) goes right before the first kernel that reads the halos
@@ -515,20 +542,22 @@ static vrs_status exchange(vrs_ctx* ctx, bool gbuf, int g_index, int r_index, bo
     const int band_h = ctx->band_y1 - ctx->band_y0;
     if (ctx->peer_up.present) {          // my first rows -> the rows just below the up neighbour's band
       int rows = ctx->peer_up.store_y1 - ctx->peer_up.band_y1; if (rows > band_h) rows = band_h;
+      if (rows > max_rows) rows = max_rows;
       H.up_count = (size_t)rows * ctx->W; H.up_src_off = (size_t)(ctx->band_y0 - ctx->store_y0) * ctx->W;
       H.up_dst_off = (size_t)(ctx->band_y0 - ctx->peer_up.store_y0) * ctx->W; H.up_flag = ctx->peer_up.flags + 1;     // "written by the down neighbour"
     }
     if (ctx->peer_down.present) {        // my last rows -> the rows just above the down neighbour's band
       int rows = ctx->peer_down.band_y0 - ctx->peer_down.store_y0; if (rows > band_h) rows = band_h;
+      if (rows > max_rows) rows = max_rows;
       H.down_count = (size_t)rows * ctx->W; H.down_src_off = (size_t)(ctx->band_y1 - rows - ctx->store_y0) * ctx->W;
       H.down_dst_off = (size_t)(ctx->band_y1 - rows - ctx->peer_down.store_y0) * ctx->W; H.down_flag = ctx->peer_down.flags + 0;   // "written by the up neighbour"
     }
     H.serial = ctx->xflags + 2; H.block_counter = ctx->xflags + 3;
-    launch_halo_push(ctx->stream, H, 64);
+    launch_halo_push(ctx->stream, H, 64, &ctx->kt);
     CK(cudaGetLastError());
     ctx->timings.launches += 1;
     if (wait_now) {
-      launch_halo_wait(ctx->stream, ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4);
+      launch_halo_wait(ctx->stream, ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4, &ctx->kt);
       CK(cudaGetLastError());
     }
     return VRS_OK;
@@ -540,7 +569,7 @@ static vrs_status exchange(vrs_ctx* ctx, bool gbuf, int g_index, int r_index, bo
   std::string err;
   CK(cudaEventRecord(ctx->ev_halo_src, ctx->stream));
   CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_halo_src, 0));
-  if (!comm_exchange_halo(ctx->comm, ctx->comm_stream, planes, ctx->W, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1, (int)ctx->H, err))
+  if (!comm_exchange_halo(ctx->comm, ctx->comm_stream, planes, ctx->W, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1, (int)ctx->H, max_rows, err))
     return fail(ctx, VRS_ERR_COMM, err);
   CK(cudaEventRecord(ctx->ev_halo_done, ctx->comm_stream));
   if (wait_now) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo_done, 0));
@@ -558,7 +587,7 @@ static vrs_status enqueue_initial(vrs_ctx* ctx, const FrameParams& F, cudaEvent_
   const unsigned* pw[4] = {ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4};
   launch_initial(ctx->stream, ctx->grid, ctx->lights, F, ctx->d_params, planes_of(ctx, ctx->cur_g), planes_of(ctx, 1 - ctx->cur_g),
                  res_of(ctx, ctx->final_r), res_of(ctx, out), ctx->queues, ctx->trace, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1,
-                 ctx->persistent_blocks, prev_halo_ready, peer_wait ? pw : nullptr);
+                 ctx->persistent_blocks, prev_halo_ready, peer_wait ? pw : nullptr, ctx->xflags + 5, &ctx->kt);
   CK(cudaGetLastError());
   ctx->src_r = out; ctx->timings.launches += (uint32_t)initial_pass_launches(F.flags, F.cull && !ctx->trace && !getenv("VRS_NO_CULL") && (long long)ctx->grid.cdim[0] * ctx->grid.cdim[1] * ctx->grid.cdim[2] <= (1ll << 27), ctx->lights);
   return VRS_OK;
@@ -570,7 +599,7 @@ static vrs_status enqueue_spatial(vrs_ctx* ctx, uint32_t iteration, int part = 0
   const int halo = ctx->cfg.halo_rows;
   const int ylo = ctx->peer_up.present ? ctx->band_y0 + halo : ctx->band_y0, yhi = ctx->peer_down.present ? ctx->band_y1 - halo : ctx->band_y1;
   launch_spatial(ctx->stream, ctx->lights, ctx->d_params, planes_of(ctx, ctx->cur_g), res_of(ctx, ctx->src_r), res_of(ctx, dst), ctx->queues,
-                 iteration, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks, part, ylo, yhi);
+                 iteration, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks, part, ylo, yhi, &ctx->kt);
   CK(cudaGetLastError());
   if (part != 1) ctx->src_r = dst;
   ctx->timings.launches += 1;
@@ -578,8 +607,9 @@ static vrs_status enqueue_spatial(vrs_ctx* ctx, uint32_t iteration, int part = 0
 }
 static vrs_status enqueue_shade(vrs_ctx* ctx, const FrameParams& F) {
   launch_shade(ctx->stream, ctx->grid, ctx->lights, F, ctx->d_params, planes_of(ctx, ctx->cur_g), res_of(ctx, ctx->src_r), ctx->accum, ctx->band_y0,
-               ctx->band_y1, ctx->store_y0);
+               ctx->band_y1, ctx->store_y0, &ctx->kt);
   CK(cudaGetLastError());
+  ctx->history_valid = true;
   ctx->final_r = ctx->src_r; ctx->last_g = ctx->cur_g; ctx->cur_g = 1 - ctx->cur_g;   // updateGBufferFrameIdx, Renderer.cpp:108-111
   ctx->timings.launches += 1;
   return VRS_OK;
@@ -614,35 +644,38 @@ static vrs_status enqueue_frame(vrs_ctx* ctx, const FrameParams& F) {
   vrs_status s;
   const bool spatial = (F.flags & VRS_RESTIR_SPATIAL_REUSE_FLAG) != 0 && ctx->cfg.spatial_iterations > 0;
   const bool temporal = (F.flags & VRS_RESTIR_TEMPORAL_REUSE_FLAG) != 0;
+  if (ctx->kt.on) { ctx->kt.n = 0; CK(cudaEventRecord(ctx->kt.ev[0], ctx->stream)); }
   CK(mark(ctx, 0));
   const bool multi = ctx->comm != nullptr || ctx->peer_mode;
+  const int all_rows = 1 << 30;
+  int sp_rows = (int)ceilf(F.spatialRadius); if (sp_rows < 1) sp_rows = 1;      // |int(dy)| <= radius: the rows spatial reuse can reach
   bool halo_in_flight = false;
   if (multi && temporal) {
-    // the consumer-side join (event wait for NCCL, flag-wait kernel for peer memory) sits right before k_finish
-    if ((s = exchange(ctx, !spatial, 1 - ctx->cur_g, ctx->final_r, false))) return s;
+    // The temporal reprojection may land anywhere in the halo (its height is sized from the camera motion), so the
+    // previous frame's G-buffer and final reservoirs travel with all halo rows.  The consumer-side join (event wait for
+    // NCCL, flag-wait kernel for peer memory) sits right before k_finish.
+    if ((s = exchange(ctx, true, 1 - ctx->cur_g, ctx->final_r, false, all_rows))) return s;
     halo_in_flight = true;
   }
   if ((s = enqueue_initial(ctx, F, halo_in_flight && !ctx->peer_mode ? ctx->ev_halo_done : nullptr, halo_in_flight && ctx->peer_mode))) return s;   // main.cpp:405-409
   CK(mark(ctx, 1));
   // Optional (VRS_SPLIT_SPATIAL=1, peer-memory mode): split every spatial iteration by rows - the rows whose neighbourhood
   // lies inside the band run while the halo rows are in flight, the wait for the neighbours' flags comes after them, then
-  // the rows next to the band edges.  Bit-identical (tests/test_gpu_multi.py ran with it), but measured slower on 2 B200
-  // (4K, 1.43 ms vs 1.36 ms per frame): the second pass over the hit list and the thin boundary launch cost more than the
-  // wait they hide, so it is off by default.
+  // the rows next to the band edges.  Bit-identical, but measured slower on 2 B200 (4K, 1.43 ms vs 1.36 ms per frame).
   static const bool no_split = !(getenv("VRS_SPLIT_SPATIAL") && getenv("VRS_SPLIT_SPATIAL")[0] == '1');
   const bool split = multi && spatial && ctx->peer_mode && !no_split && spatial_supports_row_split() && F.spatialRadius <= (float)ctx->cfg.halo_rows;
-  if (multi && spatial && (s = exchange(ctx, true, ctx->cur_g, ctx->src_r, !split))) return s;
+  if (multi && spatial && (s = exchange(ctx, true, ctx->cur_g, ctx->src_r, !split, sp_rows))) return s;
   CK(mark(ctx, 2));
   if (spatial) {
     for (uint32_t it = 0; it < ctx->cfg.spatial_iterations; ++it) {                                   // main.cpp:410-413
       if (split) {
         if ((s = enqueue_spatial(ctx, it, 1))) return s;
-        launch_halo_wait(ctx->stream, ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4);
+        launch_halo_wait(ctx->stream, ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4, &ctx->kt);
         CK(cudaGetLastError());
         ctx->timings.launches += 1;
         if ((s = enqueue_spatial(ctx, it, 2))) return s;
       } else if ((s = enqueue_spatial(ctx, it))) return s;
-      if (multi && it + 1 < ctx->cfg.spatial_iterations && (s = exchange(ctx, false, 0, ctx->src_r, !split))) return s;
+      if (multi && it + 1 < ctx->cfg.spatial_iterations && (s = exchange(ctx, false, 0, ctx->src_r, !split, sp_rows))) return s;
     }
   }
   CK(mark(ctx, 3));
@@ -660,7 +693,7 @@ vrs_status vrs_render_frame(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
   static const bool no_graph = getenv("VRS_NO_GRAPH") != nullptr;
   static const bool no_graph_comm = getenv("VRS_NO_GRAPH_COMM") != nullptr;
   (void)no_graph_comm;
-  if (no_graph || ctx->comm) {     // NCCL send/recv under stream capture hangs here (NCCL 2.28.9): NCCL contexts launch eagerly
+  if (no_graph || ctx->comm || ctx->kt.on) {     // NCCL send/recv under stream capture hangs here (NCCL 2.28.9): NCCL contexts launch eagerly
     if ((s = enqueue_frame(ctx, F))) return s;
     ctx->timings_valid = ctx->pass_timing;
     return VRS_OK;
@@ -699,6 +732,7 @@ vrs_status vrs_render_frame(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
   }
   CK(cudaGraphLaunch(it->second.exec, ctx->stream));
   ctx->timings_valid = ctx->pass_timing;
+  ctx->history_valid = true;
   return VRS_OK;
 }
 
@@ -706,7 +740,16 @@ vrs_status vrs_synchronize(vrs_ctx* ctx) {
   if (!ctx) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaStreamSynchronize(ctx->comm_stream));
+  if (ctx->comm_stream) CK(cudaStreamSynchronize(ctx->comm_stream));
+  if (ctx->peer_mode) {          // did a halo wait give up?  (k_halo_wait sets xflags[4]; stale halo rows must not pass as VRS_OK)
+    unsigned err = 0;
+    CK(cudaMemcpy(&err, ctx->xflags + 4, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) {
+      ctx->comm_timeouts += err;
+      CK(cudaMemset(ctx->xflags + 4, 0, sizeof(unsigned)));
+      return fail(ctx, VRS_ERR_COMM, "halo exchange timed out: a neighbouring band never published its rows; the frame was computed on stale halo rows");
+    }
+  }
   return VRS_OK;
 }
 
@@ -783,6 +826,7 @@ vrs_status vrs_read_trace(vrs_ctx* ctx, uint32_t* trace4) {
 vrs_status vrs_present_async(vrs_ctx* ctx, uint8_t* rgba8) {
   if (!ctx || !rgba8) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
+  if (!ctx->copy_stream) CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   const int b = (int)(ctx->present_count & 1u);
   if (ctx->present_count >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->copy_done[b], 0));   // staging buffer is free again
   const size_t off = (size_t)(ctx->band_y0 - ctx->store_y0) * ctx->W, n = (size_t)(ctx->band_y1 - ctx->band_y0) * ctx->W;
@@ -798,7 +842,7 @@ vrs_status vrs_present_async(vrs_ctx* ctx, uint8_t* rgba8) {
 vrs_status vrs_present_wait(vrs_ctx* ctx) {
   if (!ctx) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  CK(cudaStreamSynchronize(ctx->copy_stream));
+  if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
   return VRS_OK;
 }
 vrs_status vrs_read_display(vrs_ctx* ctx, uint8_t* rgba8) {
@@ -882,8 +926,94 @@ vrs_status vrs_comm_init(vrs_ctx* ctx, const uint8_t id128[128], int rank, int n
   if (nranks > 1 && ctx->band_y1 - ctx->band_y0 < (int)ctx->cfg.halo_rows)
     return fail(ctx, VRS_ERR_INVALID, "band shorter than halo_rows: halos are exchanged with adjacent ranks only");
   std::string err;
+  if (!ctx->comm_stream) CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   ctx->comm = comm_create(id128, rank, nranks, err);
   if (!ctx->comm) return fail(ctx, VRS_ERR_COMM, err);
+  return VRS_OK;
+}
+
+vrs_status vrs_peer_connect_local(vrs_ctx* ctx, vrs_ctx* up, vrs_ctx* down) {
+  if (!ctx) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if ((up || down) && ctx->band_y1 - ctx->band_y0 < (int)ctx->cfg.halo_rows)
+    return fail(ctx, VRS_ERR_INVALID, "band shorter than halo_rows: halos are exchanged with adjacent bands only");
+  auto wire = [&](vrs_ctx* o, vrs_ctx::Peer& P) -> vrs_status {
+    if (!o) return VRS_OK;
+    if (o->W != ctx->W || o->H != ctx->H) return fail(ctx, VRS_ERR_INVALID, "peer context renders another image size");
+    if (o->device != ctx->device) {
+      int can = 0;
+      CK(cudaDeviceCanAccessPeer(&can, ctx->device, o->device));
+      if (!can) return fail(ctx, VRS_ERR_UNSUPPORTED, "no peer access between the devices of the two contexts");
+      cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ctx->err = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); return VRS_ERR_CUDA; }
+      cudaGetLastError();
+    }
+    P.band_y0 = o->band_y0; P.band_y1 = o->band_y1; P.store_y0 = o->store_y0; P.store_y1 = o->store_y1;
+    for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) P.g[i][p] = o->g_planes[i][p];
+    for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) P.r[i][p] = o->r_planes[i][p];
+    P.flags = o->xflags;
+    P.present = true;
+    return VRS_OK;
+  };
+  vrs_status s;
+  if ((s = wire(up, ctx->peer_up))) return s;
+  if ((s = wire(down, ctx->peer_down))) return s;
+  if (up && up->band_y1 != ctx->band_y0) return fail(ctx, VRS_ERR_INVALID, "the up neighbour's band does not end where this band starts");
+  if (down && down->band_y0 != ctx->band_y1) return fail(ctx, VRS_ERR_INVALID, "the down neighbour's band does not start where this band ends");
+  invalidate_graphs(ctx);
+  ctx->peer_mode = up || down;
+  return VRS_OK;
+}
+
+vrs_status vrs_resize(vrs_ctx* ctx, uint32_t width, uint32_t height) {
+  if (!ctx || width == 0 || height == 0) return VRS_ERR_INVALID;
+  if (ctx->comm || ctx->peer_mode) return fail(ctx, VRS_ERR_INVALID, "vrs_resize: context belongs to a multi-GPU group (its neighbours hold pointers into its planes)");
+  cudaSetDevice(ctx->device);
+  invalidate_graphs(ctx);
+  if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
+  free_frame_buffers(ctx);
+  ctx->cfg.width = width; ctx->cfg.height = height; ctx->cfg.band_y0 = 0; ctx->cfg.band_y1 = 0;
+  vrs_status s = alloc_frame_buffers(ctx);
+  if (s) return s;
+  ctx->timings_valid = false;
+  CK(cudaDeviceSynchronize());
+  return VRS_OK;
+}
+
+vrs_status vrs_get_counters(vrs_ctx* ctx, vrs_counters* out) {
+  if (!ctx || !out) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  uint32_t q[8] = {0}; unsigned x[8] = {0};
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(q, ctx->queues.counters, sizeof(q), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(x, ctx->xflags, sizeof(x), cudaMemcpyDeviceToHost));
+  out->candidates = q[0]; out->hits = q[1]; out->shadow_rays = q[2];
+  out->temporal_out_of_halo = x[5];
+  out->comm_timeouts = ctx->comm_timeouts + x[4];
+  return VRS_OK;
+}
+
+vrs_status vrs_set_kernel_timing(vrs_ctx* ctx, int enabled) {
+  if (!ctx) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (enabled && !ctx->kt_events) {
+    for (int i = 0; i <= KTimer::MAX; ++i) CK(cudaEventCreate(&ctx->kt.ev[i]));
+    ctx->kt_events = true;
+  }
+  ctx->kt.on = enabled != 0; ctx->kt.n = 0;
+  return VRS_OK;
+}
+vrs_status vrs_get_kernel_times(vrs_ctx* ctx, vrs_kernel_time* out, uint32_t capacity, uint32_t* count) {
+  if (!ctx || !out || !count || !ctx->kt.on) return VRS_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  uint32_t n = 0;
+  for (int i = 0; i < ctx->kt.n && n < capacity; ++i, ++n) {
+    memset(&out[n], 0, sizeof(out[n]));
+    strncpy(out[n].name, ctx->kt.name[i], sizeof(out[n].name) - 1);
+    CK(cudaEventElapsedTime(&out[n].ms, ctx->kt.ev[i], ctx->kt.ev[i + 1]));
+  }
+  *count = n;
   return VRS_OK;
 }
 

@@ -74,16 +74,20 @@ void comm_destroy(Comm* c) {
 }
 
 bool comm_exchange_halo(Comm* c, cudaStream_t stream, const std::vector<float4*>& planes, uint32_t width, int band_y0, int band_y1,
-                        int store_y0, int store_y1, int height, std::string& err) {
+                        int store_y0, int store_y1, int height, int max_rows, std::string& err) {
   Api* a = api(err); if (!a) return false;
   const int up = c->rank - 1, down = c->rank + 1;
-  const int halo_up = band_y0 - store_y0, halo_down = store_y1 - band_y1;     // rows we receive
+  int halo_up = band_y0 - store_y0, halo_down = store_y1 - band_y1;           // rows we receive
   // rows the neighbours keep of our band = their halo; bands are uniform so it equals our own configured halo,
   // clipped by the image: the previous rank stores [its band_y1, its band_y1 + halo) = our first rows.
   const int cfg_halo = halo_up > halo_down ? halo_up : halo_down;
   int send_up = cfg_halo, send_down = cfg_halo;
   if (send_up > band_y1 - band_y0) send_up = band_y1 - band_y0;
   if (send_down > band_y1 - band_y0) send_down = band_y1 - band_y0;
+  if (send_up > max_rows) send_up = max_rows;                                  // (spatial exchanges move ceil(radius) rows, not the whole halo)
+  if (send_down > max_rows) send_down = max_rows;
+  if (halo_up > max_rows) halo_up = max_rows;
+  if (halo_down > max_rows) halo_down = max_rows;
   (void)height;
   auto row_ptr = [&](float4* p, int row) { return p + (size_t)(row - store_y0) * width; };
   ncclResult_t r = a->GroupStart();
@@ -91,7 +95,7 @@ bool comm_exchange_halo(Comm* c, cudaStream_t stream, const std::vector<float4*>
     if (r != 0) break;
     if (up >= 0) {
       if (send_up > 0) r = a->Send(row_ptr(p, band_y0), (size_t)send_up * width * 4, kNcclFloat, up, c->comm, stream);
-      if (r == 0 && halo_up > 0) r = a->Recv(row_ptr(p, store_y0), (size_t)halo_up * width * 4, kNcclFloat, up, c->comm, stream);
+      if (r == 0 && halo_up > 0) r = a->Recv(row_ptr(p, band_y0 - halo_up), (size_t)halo_up * width * 4, kNcclFloat, up, c->comm, stream);
     }
     if (r == 0 && down < c->nranks) {
       if (send_down > 0) r = a->Send(row_ptr(p, band_y1 - send_down), (size_t)send_down * width * 4, kNcclFloat, down, c->comm, stream);

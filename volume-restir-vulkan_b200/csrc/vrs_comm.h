@@ -16,5 +16,5 @@ void comm_destroy(Comm* c);
 // For every plane (RGBA32F, `width` pixels per row, first stored row = store_y0): send the first / last rows of the
 // own band [band_y0, band_y1) to the previous / next rank and receive their rows into the halo rows.
 bool comm_exchange_halo(Comm* c, cudaStream_t stream, const std::vector<float4*>& planes, uint32_t width, int band_y0, int band_y1,
-                        int store_y0, int store_y1, int height, std::string& err);
+                        int store_y0, int store_y1, int height, int max_rows, std::string& err);
 }  // namespace vrs

@@ -144,8 +144,10 @@ struct PrimaryJob {
   }
   __device__ __forceinline__ void retire(const GridDev& G, const Ray<0>& ray, uint32_t seed) {
     if (ray.hit) {
-      const uint32_t vcode = uint32_t(ray.vox[0] - G.vmin[0]) + uint32_t(G.vdim[0]) * (uint32_t(ray.vox[1] - G.vmin[1]) + uint32_t(G.vdim[1]) * uint32_t(ray.vox[2] - G.vmin[2]));
-      cur.worldPos[idx] = make_float4(ray.t, __uint_as_float(vcode), __uint_as_float(seed), 1.0f);     // scratch until k_ris
+      // scratch until k_ris: {t, cell of the directory (< 2^30), RNG state, voxel inside the cell (9 bits)} — a voxel index over the
+      // whole window would not fit 32 bits for large sparse grids
+      const uint32_t off = (uint32_t)(((ray.vox[0] & 7) << 6) | ((ray.vox[1] & 7) << 3) | (ray.vox[2] & 7));
+      cur.worldPos[idx] = make_float4(ray.t, __uint_as_float((uint32_t)ray.cell), __uint_as_float(seed), __uint_as_float(off));
       Q.flag[idx] = 1;
     }
     if (trace) { trace[(size_t)idx * 4 + 1] = ray.ntent; trace[(size_t)idx * 4 + 2] = ray.ncells; trace[(size_t)idx * 4 + 3] = seed; }
@@ -212,10 +214,12 @@ __device__ __forceinline__ void ris_hit_setup(const GridDev& G, const FrameParam
   seed = __float_as_uint(scratch.z);
   V3 org, dir; primary_ray(F, x, y, org, dir);
   const V3 P = add(org, muls(dir, scratch.x));
-  vcode = __float_as_uint(scratch.y);
-  const int i = (int)(vcode % (uint32_t)G.vdim[0]) + G.vmin[0];
-  const int j = (int)((vcode / (uint32_t)G.vdim[0]) % (uint32_t)G.vdim[1]) + G.vmin[1];
-  const int k = (int)(vcode / ((uint32_t)G.vdim[0] * (uint32_t)G.vdim[1])) + G.vmin[2];
+  const uint32_t cell = __float_as_uint(scratch.y), off = __float_as_uint(scratch.w);
+  const int i = G.vmin[0] + 8 * (int)(cell % (uint32_t)G.cdim[0]) + (int)(off >> 6);
+  const int j = G.vmin[1] + 8 * (int)((cell / (uint32_t)G.cdim[0]) % (uint32_t)G.cdim[1]) + (int)((off >> 3) & 7u);
+  const int k = G.vmin[2] + 8 * (int)(cell / ((uint32_t)G.cdim[0] * (uint32_t)G.cdim[1])) + (int)(off & 7u);
+  // (parity traces only; wraps above 2^32 voxels exactly like the oracle's uint32 expression)
+  vcode = uint32_t(i - G.vmin[0]) + uint32_t(G.vdim[0]) * (uint32_t(j - G.vmin[1]) + uint32_t(G.vdim[1]) * uint32_t(k - G.vmin[2]));
   const float dens = density_at(G, i, j, k);
   V3 grad = v3(density_at(G, i + 1, j, k) - density_at(G, i - 1, j, k), density_at(G, i, j + 1, k) - density_at(G, i, j - 1, k),
                density_at(G, i, j, k + 1) - density_at(G, i, j, k - 1));
@@ -551,7 +555,8 @@ __global__ void __launch_bounds__(128, 9) k_shadow(const GridDev G, Queues Q, in
 }
 
 __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, Planes prev, ResPlanes prevR,
-                                                ResPlanes outR, Queues Q, uint32_t* __restrict__ trace, int store_y0, int store_y1) {
+                                                ResPlanes outR, Queues Q, uint32_t* __restrict__ trace, int store_y0, int store_y1,
+                                                unsigned* __restrict__ out_of_halo) {
   const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
@@ -572,7 +577,8 @@ __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FramePa
       q[1] = (q[1] + 1.0f) * 0.5f * float(F.H);
       if (q[0] > 0.0f && q[1] > 0.0f && q[0] < float(F.W) && q[1] < float(F.H)) {
         int fx = int(q[0]), fy = int(q[1]);
-        if (fy >= store_y0 && fy < store_y1) {                                                         // rows held by this context
+        if (fy < store_y0 || fy >= store_y1) atomicAdd(out_of_halo, 1u);                               // halo_rows too small for this camera motion (vrs_get_counters)
+        else {                                                                                         // rows held by this context
           size_t pidx = (size_t)(fy - store_y0) * F.W + (size_t)fx;
           if (!(prev.worldPos[pidx].w < 0.5f)) {                 // a previous miss holds no data (its zero normal fails :274 anyway)
             GInfo pg = ginfo_from_planes(prev, pidx, F.camPos);                                        // prevGInfo.camPos = gInfo.camPos (:259)
@@ -584,7 +590,7 @@ __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FramePa
                   Res pr = unpackReservoir(prevR.info[pidx], prevR.weight[pidx]);                      // at prevFrag
                   uint32_t cap = uint32_t(F.temporalMult) * res.M;
                   if (cap < pr.M) pr.M = cap;
-                  combineReservoirsGeom(L, res, pr, gi, pg, seed);
+                  if (pr.lightIndex < (uint32_t)L.nlights) combineReservoirsGeom(L, res, pr, gi, pg, seed);   // (a stale index can only come from a foreign history)
                 }
               }
             }
@@ -969,7 +975,7 @@ static int resident_grid(K kernel, int block_threads, int fallback_per_sm) {
 // kernels — so that a captured CUDA graph of the frame stays valid while the per-frame values change.
 void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, Planes prev,
                     ResPlanes prevR, ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1,
-                    int persistent_blocks, cudaEvent_t prev_halo_ready, const unsigned* const* peer_wait) {
+                    int persistent_blocks, cudaEvent_t prev_halo_ready, const unsigned* const* peer_wait, unsigned* out_of_halo, KTimer* kt) {
   // tuning knobs of the persistent raymarch kernels: idle lanes that trigger a refill | cell visits per scheduling decision << 8
   // | warps that a small launch is spread over (lanes_for) << 16
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
@@ -998,14 +1004,18 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
     const int tiles_y = ((int)F.H + COVER_TILE - 1) / COVER_TILE;
     cudaMemsetAsync(Q.cover, 0, (size_t)tiles_x * tiles_y, st);
     k_cover<<<(unsigned)((ncell * 8 + 127) / 128), 128, 0, st>>>(G, dF, Q, tiles_x, tiles_y);
+    ktick(kt, st, "k_cover");
   }
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_classify<<<grid, block, 0, st>>>(G, dF, cur, Q, trace, y0, y1, store_y0, tiles_x);
+  ktick(kt, st, "k_classify");
   k_primary<<<persistent_blocks, 128, 0, st>>>(G, dF, cur, Q, trace, store_y0, refill);
+  ktick(kt, st, "k_primary");
   // compaction runs over every stored row (8-byte aligned flag loads); flags outside the band rows stay 0
   const size_t npix = (size_t)(store_y1 - store_y0) * F.W;
   const uint32_t nblocks = (uint32_t)((npix + COMPACT_BLOCK - 1) / COMPACT_BLOCK);
   k_hit_compact<<<nblocks, 256, 0, st>>>(Q.flag, npix, Q.counters, Q.hit_pix);
+  ktick(kt, st, "k_hit_compact");
   const bool vis = (F.flags & FLAG_VISIBILITY) != 0, temporal = (F.flags & FLAG_TEMPORAL) != 0;
   const int needs_finish = (vis || temporal) ? 1 : 0;
   static const bool one_wave = !getenv("VRS_NO_ONE_WAVE");
@@ -1020,11 +1030,12 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
     if (ris_minb >= 8) k_ris_thread<8><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
     else k_ris_thread<7><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
   }
-  if (vis) k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill);
+  ktick(kt, st, "k_ris");
+  if (vis) { k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill); ktick(kt, st, "k_shadow"); }
   // the previous frame's halo rows (multi-GPU) are only needed by the temporal merge: everything above overlapped their exchange
   if (needs_finish && prev_halo_ready) cudaStreamWaitEvent(st, prev_halo_ready, 0);
-  if (needs_finish && peer_wait) k_halo_wait<<<1, 1, 0, st>>>(peer_wait[0], peer_wait[1], peer_wait[2], const_cast<unsigned*>(peer_wait[3]));
-  if (needs_finish) k_finish<<<g_finish, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1);
+  if (needs_finish && peer_wait) { k_halo_wait<<<1, 1, 0, st>>>(peer_wait[0], peer_wait[1], peer_wait[2], const_cast<unsigned*>(peer_wait[3])); ktick(kt, st, "k_halo_wait"); }
+  if (needs_finish) { k_finish<<<g_finish, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1, out_of_halo); ktick(kt, st, "k_finish"); }
 }
 bool spatial_supports_row_split() { return !(getenv("VRS_SPATIAL") && getenv("VRS_SPATIAL")[0] == 'c'); }
 int initial_pass_launches(int flags, bool culling, const LightsDev& L) {
@@ -1036,7 +1047,7 @@ int initial_pass_launches(int flags, bool culling, const LightsDev& L) {
   return 3 /* classify, primary, compact */ + ris + (culling ? 1 : 0) + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
 }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
-                    uint32_t iteration, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi) {
+                    uint32_t iteration, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt) {
   static const bool thread_form = !(getenv("VRS_SPATIAL") && getenv("VRS_SPATIAL")[0] == 'c');
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   static const int target_warps = sms * (getenv("VRS_MIN_WARPS_PER_SM") ? atoi(getenv("VRS_MIN_WARPS_PER_SM")) : MIN_WARPS_PER_SM);
@@ -1051,15 +1062,18 @@ void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, P
   if (thread_form && minb >= 8) k_spatial_thread<8><<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
   else if (thread_form) k_spatial_thread<7><<<g7, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
   else if (part != 2) k_spatial_coop<<<coop_blocks, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, target_warps);   // (no row split: part 1 does all)
+  ktick(kt, s, "k_spatial");
 }
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, ResPlanes rs,
-                  float4* accum, int y0, int y1, int store_y0) {
+                  float4* accum, int y0, int y1, int store_y0, KTimer* kt) {
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_shade<<<grid, block, 0, s>>>(G, L, dF, cur, rs, accum, y0, y1, store_y0);
+  ktick(kt, s, "k_shade");
 }
-void launch_halo_push(cudaStream_t s, const HaloPush& H, int blocks) { k_halo_push<<<blocks, 256, 0, s>>>(H); }
-void launch_halo_wait(cudaStream_t s, const unsigned* serial, const unsigned* from_up, const unsigned* from_down, unsigned* error) {
+void launch_halo_push(cudaStream_t s, const HaloPush& H, int blocks, KTimer* kt) { k_halo_push<<<blocks, 256, 0, s>>>(H); ktick(kt, s, "k_halo_push"); }
+void launch_halo_wait(cudaStream_t s, const unsigned* serial, const unsigned* from_up, const unsigned* from_down, unsigned* error, KTimer* kt) {
   k_halo_wait<<<1, 1, 0, s>>>(serial, from_up, from_down, error);
+  ktick(kt, s, "k_halo_wait");
 }
 void launch_export(cudaStream_t s, Planes cur, ResPlanes rs, float4* out6, size_t first_pix, size_t n) {
   k_export<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(cur, rs, out6, first_pix, n);
