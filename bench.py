@@ -230,6 +230,7 @@ def calibrated_bands(V, wl, path, world, rank, device, dist, halo, rounds=3, fra
         u.initialLightSampleCount, u.spatialNeighbors, u.flags = wl["M"], wl["k"], wl["flags"]
         R.CameraManip.setLookat(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, 0.0), ctr)
         R.createRestirUniformBuffer()
+        R.setPassTiming(True)
         tot = 0.0
         for f in range(frames):
             R.CameraManip.setLookat(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, 30.0 * f), ctr)     # spread over the orbit

@@ -176,9 +176,16 @@ vrs_status vrs_pass_spatial(vrs_ctx* ctx, const vrs_restir_uniforms* ru, uint32_
  * like Renderer::updateGBufferFrameIdx (src/Renderer.cpp:108-111). */
 vrs_status vrs_pass_shade(vrs_ctx* ctx, const vrs_restir_uniforms* ru, const vrs_push_constant_restir* pc, uint32_t clock);
 /* The three calls above in main.cpp:405-433 order (spatial x spatial_iterations when the flag is set);
- * asynchronous on the context stream, captured in a CUDA graph after the first call. */
+ * asynchronous, replayed from CUDA graphs; consecutive frames overlap (frames in flight, nvvk/appbase_vk.cpp:412-418):
+ * vrs_synchronize / any vrs_read_* returns the state after the last frame enqueued. */
 vrs_status vrs_render_frame(vrs_ctx* ctx, const vrs_global_uniforms* gu, const vrs_restir_uniforms* ru,
                             const vrs_push_constant_restir* pc, uint32_t clock);
+/* The same frame on several contexts driven by ONE host thread — bands of one image wired with vrs_peer_connect_local
+ * (several GPUs of one process, or several bands on one GPU).  The frame is enqueued phase by phase across the contexts
+ * (initial pass of every band, then the temporal merge of every band, then each spatial iteration, then the shade), so
+ * that a band's wait for its neighbours' halo rows is always enqueued after the stores it waits for. */
+vrs_status vrs_render_frame_group(vrs_ctx** ctxs, uint32_t n, const vrs_global_uniforms* gu, const vrs_restir_uniforms* ru,
+                                  const vrs_push_constant_restir* pc, uint32_t clock);
 vrs_status vrs_synchronize(vrs_ctx* ctx);
 
 /* ---- readback (none in the reference: it presents to a swapchain) -------------------------- */
@@ -202,8 +209,9 @@ vrs_status vrs_write_image(vrs_ctx* ctx, const char* path);
 typedef struct { float initial_ms, spatial_ms, shade_ms, exchange_ms, frame_ms; uint32_t launches; } vrs_timings;
 /* CUDA-event times of the last vrs_render_frame on the context stream (valid after vrs_synchronize). */
 vrs_status vrs_get_timings(vrs_ctx* ctx, vrs_timings* out);
-/* Per-pass CUDA events are recorded inside every frame by default; they cost a few microseconds of a sub-millisecond
-   frame.  enabled = 0 leaves them out (vrs_get_timings then fails with VRS_ERR_INVALID until re-enabled and a frame ran). */
+/* Per-pass CUDA events inside every frame (off by default: vrs_get_timings fails with VRS_ERR_INVALID until they are
+   enabled and a frame ran).  While enabled, frames do not overlap: the front half of frame n+1 (everything of the
+   initial pass that does not read frame n) otherwise runs on a second stream while the back half of frame n executes. */
 vrs_status vrs_set_pass_timing(vrs_ctx* ctx, int enabled);
 void*      vrs_stream(vrs_ctx* ctx);                                                    /* cudaStream_t */
 /* Work counters of the last frame (valid after vrs_synchronize) and the cumulative health counters of the halo exchange:
@@ -227,7 +235,7 @@ vrs_status vrs_comm_init(vrs_ctx* ctx, const uint8_t id128[128], int rank, int n
  * and from then on ONE kernel per exchange stores the boundary rows straight into the neighbours' halo rows over NVLink
  * and releases a system-scope flag; consumers acquire the flag in a one-thread wait kernel.  Being plain kernels, the
  * exchange is part of the captured CUDA graph of the frame. */
-#define VRS_PEER_BLOB_BYTES 1152
+#define VRS_PEER_BLOB_BYTES 1664
 vrs_status vrs_peer_export(vrs_ctx* ctx, uint8_t blob[VRS_PEER_BLOB_BYTES]);
 vrs_status vrs_peer_connect(vrs_ctx* ctx, int rank, int nranks, const uint8_t* all_blobs /* nranks x VRS_PEER_BLOB_BYTES */);
 /* The same wiring between contexts of ONE process (any mix of devices with peer access, or several bands on one device):

@@ -1,6 +1,6 @@
 """-m gpu, ONE device: the multi-GPU band schedule (halo pushes + flag waits inside the frame graphs, vrs_peer_connect_local)
-with every band a context of this process on the same GPU.  The halo exchange is the same kernels and the same schedule as
-across GPUs (there the stores travel over NVLink), so a 1-GPU box proves: bands == single frame bit for bit on the bench's
+with every band a context of this process on the same GPU, driven by vrs_render_frame_group.  The halo exchange is the
+same kernels and the same phase schedule as across GPUs (there the stores travel over NVLink), so a 1-GPU box proves: bands == single frame bit for bit on the bench's
 own 6 deg/frame orbit, the halo sizing rule, the out-of-halo counter and the exchange time-out path."""
 import numpy as np
 import pytest
@@ -47,9 +47,9 @@ def run_bands(V, name, nbands, frames, halo=None, W=None, H=None, M=None, edges=
     bad = []
     for f in range(frames):
         eye = bench.orbit_eye(ctr, radius, 0.0, bench.ORBIT_DEG * f)
-        for b in bands:                              # enqueue every band before synchronising any (they wait for each other's rows)
+        for b in bands:
             b.CameraManip.setLookat(eye, ctr)
-            b.renderFrame(clock=f)
+        V.render_frame_group(bands, f)               # one host thread: phases interleaved across the bands (vrs_render_frame_group)
         for b in bands:
             b.synchronize()
         full.CameraManip.setLookat(eye, ctr)
@@ -106,7 +106,7 @@ def test_halo_wait_timeout_is_an_error(V):
     b.peerConnectLocal(a, None)
     a.CameraManip.setLookat(bench.orbit_eye(ctr, 1.25 * diag, 0.0, 0.0), ctr)
     a.createRestirUniformBuffer()
-    a.renderFrame(clock=0)                           # b never renders
+    a.renderFrame(clock=0)                           # b never renders (vrs_render_frame on one band only)
     with pytest.raises(V.VrsError) as e:
         a.synchronize()
     assert e.value.status == 6                       # VRS_ERR_COMM

@@ -21,6 +21,7 @@ u = R.m_restirUniforms
 u.initialLightSampleCount, u.spatialNeighbors, u.flags = wl["M"], wl["k"], wl["flags"]
 R.CameraManip.setLookat(bench.orbit_eye(ctr, 1.25 * diag, 0.0, 0.0), ctr)
 R.createRestirUniformBuffer()
+R.setPassTiming(True)
 tot, n = 0.0, 0
 for f in range(frames):                       # graph replay: frame time as the bench sees it
     R.CameraManip.setLookat(bench.orbit_eye(ctr, 1.25 * diag, 0.0, 6.0 * f), ctr)
@@ -28,7 +29,17 @@ for f in range(frames):                       # graph replay: frame time as the 
     t = R.timings()
     if f >= 8:
         tot += t.frame_ms; n += 1
-print("band %d..%d of %s: frame %.4f ms (graph replay), hits %d" % (y0, y1, name, tot / n, R.counters().hits))
+print("band %d..%d of %s: frame %.4f ms (graph replay, no overlap), hits %d" % (y0, y1, name, tot / n, R.counters().hits))
+R.setPassTiming(False)
+import time  # noqa: E402
+for rep in range(2):
+    R.synchronize(); t0 = time.perf_counter()
+    for f in range(frames, frames + 200):
+        R.CameraManip.setLookat(bench.orbit_eye(ctr, 1.25 * diag, 0.0, 6.0 * f), ctr)
+        R.renderFrame(clock=f)
+    R.synchronize()
+    print("  200 frames back to back (frames in flight%s): %.4f ms per frame (wall, includes the host-side uniform producers)" % (" OFF" if os.environ.get("VRS_PIPELINE") == "0" else "", 1e3 * (time.perf_counter() - t0) / 200))
+frames += 200
 R.setKernelTiming(True)
 acc = {}
 for f in range(frames, frames + 12):

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "libvrs.so")
 VISIBILITY_REUSE_FLAG, TEMPORAL_REUSE_FLAG, SPATIAL_REUSE_FLAG, USE_ENVIRONMENT_FLAG = 1, 2, 4, 8
 FINAL_VISIBILITY_FLAG, FINALIZE_W_FLAG = 16, 32
 
-PEER_BLOB_BYTES = 1152
+PEER_BLOB_BYTES = 1664
 
 STATUS = {0: "VRS_OK", 1: "VRS_ERR_INVALID", 2: "VRS_ERR_CUDA", 3: "VRS_ERR_IO", 4: "VRS_ERR_FORMAT",
           5: "VRS_ERR_UNSUPPORTED", 6: "VRS_ERR_COMM", 7: "VRS_ERR_NO_DEVICE"}
@@ -33,7 +33,7 @@ EXPORTS = [
     "vrs_pass_spatial", "vrs_pass_shade", "vrs_render_frame", "vrs_synchronize", "vrs_read_frame", "vrs_read_gbuffer",
     "vrs_read_reservoirs", "vrs_read_trace", "vrs_read_display", "vrs_present_async", "vrs_present_wait", "vrs_write_image", "vrs_get_timings", "vrs_set_pass_timing", "vrs_stream", "vrs_comm_unique_id",
     "vrs_comm_init", "vrs_peer_export", "vrs_peer_connect", "vrs_peer_connect_local", "vrs_band_for_rank",
-    "vrs_resize", "vrs_get_counters", "vrs_set_kernel_timing", "vrs_get_kernel_times",
+    "vrs_resize", "vrs_get_counters", "vrs_set_kernel_timing", "vrs_get_kernel_times", "vrs_render_frame_group",
 ]
 
 
@@ -167,6 +167,8 @@ def lib():
         L.vrs_peer_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.vrs_peer_connect.restype = C.c_int
         L.vrs_peer_connect_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.vrs_render_frame_group.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.vrs_render_frame_group.restype = C.c_int
         L.vrs_resize.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         L.vrs_get_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.vrs_set_kernel_timing.argtypes = [C.c_void_p, C.c_int]
@@ -269,6 +271,23 @@ def comm_unique_id():
     if s:
         raise VrsError(s, lib().vrs_last_error(None).decode())
     return bytes(buf)
+
+
+def render_frame_group(renderers, clock):
+    """renderFrame() of several band Renderers of one image from one host thread (vrs_render_frame_group): every band
+    gets the same camera; phases are interleaved across the bands so that no band waits for rows not yet enqueued."""
+    for r in renderers:
+        r.updateUniformBuffer(); r.updateRestirUniformBuffer(); r.updateFrame()
+        r._last_initialize = r.m_pcRestirPost.initialize
+    r0 = renderers[0]
+    arr = (C.c_void_p * len(renderers))(*[r._ctx for r in renderers])
+    s = lib().vrs_render_frame_group(arr, len(renderers), C.byref(r0.m_globalUniforms), C.byref(r0.m_restirUniforms), C.byref(r0.m_pcRestirPost), clock)
+    if s:
+        raise VrsError(s, "; ".join(lib().vrs_last_error(r._ctx).decode() for r in renderers))
+    for r in renderers:
+        r.clock = clock + 1
+        if r.m_pcRestirPost.frame > 10:
+            r.m_pcRestirPost.initialize = 0
 
 
 class CameraManip:

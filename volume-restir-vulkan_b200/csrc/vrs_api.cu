@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -21,7 +22,17 @@
 using namespace vrs;
 
 #define VRS_PARAM_SLOTS 8
-struct GraphEntry { cudaGraphExec_t exec = nullptr; uint32_t launches = 0; int next_cur_g = 0, next_final_r = 0, next_src_r = 0, last_g = 0; };
+// Frames in flight (the reference keeps 2-3 swapchain images in flight, nvvk/appbase_vk.cpp:412-418): the front half of
+// frame n+1 (coverage, classification, primary event, RIS, shadow rays: nothing in it reads the previous frame) runs on its
+// own stream while the back half of frame n (temporal merge, spatial reuse, shade, halo exchanges) is still executing.
+// Buffers are sized for that: 3 G-buffers (frame n writes n % 3 and reads (n - 1) % 3 as "previous"), 3 pairs of reservoir
+// buffers (frame n ping-pongs inside pair n % 3 and reads the final one of frame n - 1), 2 sets of work queues and 2 device
+// parameter blocks (n % 2).  front(n) waits for back(n - 2), back(n) for front(n) and, by stream order, back(n - 1).
+#define VRS_NG 3
+#define VRS_NR 6
+#define VRS_NQ 2
+struct GraphEntry { cudaGraphExec_t exec = nullptr; uint32_t launches = 0; };
+struct FrameIdx { int g = 0, gprev = 0, ra = 0, rb = 0, q = 0; };
 
 struct vrs_ctx {
   vrs_config cfg;
@@ -32,14 +43,22 @@ struct vrs_ctx {
   int band_y0 = 0, band_y1 = 0, store_y0 = 0, store_y1 = 0;
   size_t npix = 0;                       // stored pixels = (store_y1 - store_y0) * W
 
-  float4* g_planes[2][4] = {{nullptr}};  // worldPos, albedo, normal, matProps
-  float4* r_planes[3][2] = {{nullptr}};  // info, weight
+  float4* g_planes[VRS_NG][4] = {{nullptr}};  // worldPos, albedo, normal, matProps
+  float4* r_planes[VRS_NR][2] = {{nullptr}};  // info, weight
   float4* accum = nullptr;
   uint32_t* trace = nullptr;
-  int cur_g = 0;                         // Renderer::m_currentGBufferFrameIdx
-  int last_g = 0;
-  int final_r = 0;                       // reservoirs of the previous frame (temporal input)
+  uint64_t frame_no = 0;                 // frames begun so far: the frame being built is frame_no (Renderer::m_currentGBufferFrameIdx generalised)
+  FrameIdx cur{};                        // buffer indices of the frame being built (per-pass API) / last built
+  int last_g = 0;                        // G-buffer of the last completed frame
+  int final_r = 0;                       // final reservoirs of the last completed frame (temporal input of the next)
   int src_r = 0;                         // most recently written reservoir buffer inside the frame
+  int last_q = 0;                        // queue set of the last frame (vrs_get_counters)
+  cudaStream_t front_stream = nullptr;   // front halves run here (frames in flight)
+  cudaEvent_t ev_front_done[VRS_NQ] = {nullptr}, ev_back_done[VRS_NQ] = {nullptr};
+  bool back_recorded[VRS_NQ] = {false, false};
+  bool halo_pending = false;             // a halo push has been enqueued whose consumer-side wait has not
+  bool pipeline = true;
+  bool replaying = false;                 // a captured half is being replayed: bodies only advance host-side state
 
   HostGrid host_grid;
   bool has_grid = false;
@@ -56,23 +75,23 @@ struct vrs_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t display_ready[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
   uint32_t present_count = 0;
-  FrameParams* d_params = nullptr;           // the one device-resident copy every kernel reads
+  FrameParams* d_params = nullptr;           // VRS_NQ device-resident copies (frame n reads copy n % 2)
   FrameParams* h_params = nullptr;           // pinned ring feeding it
   cudaEvent_t param_ev[VRS_PARAM_SLOTS] = {nullptr};
   uint64_t param_serial = 0;
   std::map<uint64_t, GraphEntry> graphs;     // captured frames, keyed by ping-pong phase + structural flags
   std::map<uint64_t, int> seen;
   bool capturing = false;
-  Queues queues{};
+  Queues queues[VRS_NQ]{};
   int persistent_blocks = 148 * 12;
 
   cudaEvent_t ev[8] = {nullptr};
   vrs_timings timings{};
   bool timings_valid = false;
-  bool pass_timing = true;                   // record the per-pass events inside each frame (vrs_set_pass_timing)
+  bool pass_timing = false;                  // record the per-pass events inside each frame (vrs_set_pass_timing); off: frames overlap
   Comm* comm = nullptr;
   // peer-memory exchange (vrs_peer_connect): neighbours' planes opened through CUDA IPC
-  struct Peer { bool present = false; float4* g[2][4] = {{nullptr}}; float4* r[3][2] = {{nullptr}}; unsigned* flags = nullptr; int store_y0 = 0, store_y1 = 0, band_y0 = 0, band_y1 = 0; std::vector<void*> opened; };
+  struct Peer { bool present = false; float4* g[VRS_NG][4] = {{nullptr}}; float4* r[VRS_NR][2] = {{nullptr}}; unsigned* flags = nullptr; int store_y0 = 0, store_y1 = 0, band_y0 = 0, band_y1 = 0; std::vector<void*> opened; };
   Peer peer_up, peer_down;
   bool peer_mode = false;
   unsigned* xflags = nullptr;                // [0] flag written by the up neighbour, [1] by the down neighbour, [2] serial, [3] block counter, [4] error
@@ -106,13 +125,15 @@ const char* vrs_last_error(const vrs_ctx* ctx) { return ctx ? ctx->err.c_str() :
 
 // Everything whose size depends on the image: per-pixel planes, work queues, display staging (vrs_create / vrs_resize).
 static void free_frame_buffers(vrs_ctx* ctx) {
-  for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) { cudaFree(ctx->g_planes[i][p]); ctx->g_planes[i][p] = nullptr; }
-  for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) { cudaFree(ctx->r_planes[i][p]); ctx->r_planes[i][p] = nullptr; }
+  for (int i = 0; i < VRS_NG; ++i) for (int p = 0; p < 4; ++p) { cudaFree(ctx->g_planes[i][p]); ctx->g_planes[i][p] = nullptr; }
+  for (int i = 0; i < VRS_NR; ++i) for (int p = 0; p < 2; ++p) { cudaFree(ctx->r_planes[i][p]); ctx->r_planes[i][p] = nullptr; }
   cudaFree(ctx->accum); ctx->accum = nullptr; cudaFree(ctx->trace); ctx->trace = nullptr;
-  Queues& Q = ctx->queues;
-  cudaFree(Q.counters); cudaFree(Q.cand); cudaFree(Q.cand_ray); cudaFree(Q.flag); cudaFree(Q.block_count); cudaFree(Q.hit_pix);
-  cudaFree(Q.hit_seed); cudaFree(Q.hit_T); cudaFree(Q.shadow); cudaFree(Q.shadow_ray); cudaFree(Q.cover);
-  memset(&Q, 0, sizeof(Q));
+  for (int k = 0; k < VRS_NQ; ++k) {
+    Queues& Q = ctx->queues[k];
+    cudaFree(Q.counters); cudaFree(Q.cand); cudaFree(Q.cand_ray); cudaFree(Q.flag); cudaFree(Q.block_count); cudaFree(Q.hit_pix);
+    cudaFree(Q.hit_seed); cudaFree(Q.hit_T); cudaFree(Q.shadow); cudaFree(Q.shadow_ray); cudaFree(Q.cover);
+    memset(&Q, 0, sizeof(Q));
+  }
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->display[i]); ctx->display[i] = nullptr; }
 }
 static vrs_status alloc_frame_buffers(vrs_ctx* ctx) {
@@ -128,19 +149,23 @@ static vrs_status alloc_frame_buffers(vrs_ctx* ctx) {
     if (cudaMalloc(p, bytes) != cudaSuccess) { ctx->err = "cudaMalloc failed (" + std::to_string(bytes) + " bytes)"; return false; }
     return cudaMemset(*p, 0, bytes) == cudaSuccess;
   };
-  for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) if (!alloc((void**)&ctx->g_planes[i][p], ctx->npix * 16)) return VRS_ERR_CUDA;
-  for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) if (!alloc((void**)&ctx->r_planes[i][p], ctx->npix * 16)) return VRS_ERR_CUDA;
+  for (int i = 0; i < VRS_NG; ++i) for (int p = 0; p < 4; ++p) if (!alloc((void**)&ctx->g_planes[i][p], ctx->npix * 16)) return VRS_ERR_CUDA;
+  for (int i = 0; i < VRS_NR; ++i) for (int p = 0; p < 2; ++p) if (!alloc((void**)&ctx->r_planes[i][p], ctx->npix * 16)) return VRS_ERR_CUDA;
   if (!alloc((void**)&ctx->accum, ctx->npix * 16)) return VRS_ERR_CUDA;
   if (cfg->enable_trace && !alloc((void**)&ctx->trace, ctx->npix * 16)) return VRS_ERR_CUDA;
-  Queues& Q = ctx->queues;
   const size_t ncompact = (ctx->npix + 2047) / 2048 + 1;
-  if (!alloc((void**)&Q.counters, 64) || !alloc((void**)&Q.cand, ctx->npix * 4) || !alloc((void**)&Q.cand_ray, ctx->npix * 32) ||
-      !alloc((void**)&Q.flag, ctx->npix + 16) || !alloc((void**)&Q.block_count, ncompact * 4) || !alloc((void**)&Q.hit_pix, ctx->npix * 4) ||
-      !alloc((void**)&Q.hit_seed, ctx->npix * 4) || !alloc((void**)&Q.hit_T, ctx->npix * 4) || !alloc((void**)&Q.shadow, ctx->npix * 4) ||
-      !alloc((void**)&Q.shadow_ray, ctx->npix * 32) || !alloc((void**)&Q.cover, ((size_t)(ctx->W + 7) / 8) * ((size_t)(ctx->H + 7) / 8) + 16))
-    return VRS_ERR_CUDA;
+  for (int k = 0; k < VRS_NQ; ++k) {
+    Queues& Q = ctx->queues[k];
+    if (!alloc((void**)&Q.counters, 64) || !alloc((void**)&Q.cand, ctx->npix * 4) || !alloc((void**)&Q.cand_ray, ctx->npix * 32) ||
+        !alloc((void**)&Q.flag, ctx->npix + 16) || !alloc((void**)&Q.block_count, ncompact * 4) || !alloc((void**)&Q.hit_pix, ctx->npix * 4) ||
+        !alloc((void**)&Q.hit_seed, ctx->npix * 4) || !alloc((void**)&Q.hit_T, ctx->npix * 4) || !alloc((void**)&Q.shadow, ctx->npix * 4) ||
+        !alloc((void**)&Q.shadow_ray, ctx->npix * 32) || !alloc((void**)&Q.cover, ((size_t)(ctx->W + 7) / 8) * ((size_t)(ctx->H + 7) / 8) + 16))
+      return VRS_ERR_CUDA;
+  }
   for (int i = 0; i < 2; ++i) if (!alloc((void**)&ctx->display[i], ctx->npix * 4)) return VRS_ERR_CUDA;
-  ctx->cur_g = ctx->last_g = ctx->final_r = ctx->src_r = 0;
+  ctx->frame_no = 0; ctx->cur = FrameIdx(); ctx->last_g = ctx->final_r = ctx->src_r = ctx->last_q = 0;
+  ctx->back_recorded[0] = ctx->back_recorded[1] = false;
+  ctx->halo_pending = false;
   ctx->present_count = 0;
   ctx->history_valid = false;
   return VRS_OK;
@@ -161,7 +186,12 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
     if (cudaMalloc(p, bytes) != cudaSuccess) { ctx->err = "cudaMalloc failed (" + std::to_string(bytes) + " bytes)"; return false; }
     return cudaMemset(*p, 0, bytes) == cudaSuccess;
   };
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->front_stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
+  for (int i = 0; i < VRS_NQ; ++i)
+    if (cudaEventCreateWithFlags(&ctx->ev_front_done[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_back_done[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
+  ctx->pipeline = !(getenv("VRS_PIPELINE") && getenv("VRS_PIPELINE")[0] == '0');
   if (vrs_status s = alloc_frame_buffers(ctx)) return bail(s);
   {
     cudaDeviceProp prop;
@@ -169,7 +199,7 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
   }
   for (int i = 0; i < 8; ++i) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
   if (!alloc((void**)&ctx->xflags, 64)) return bail(VRS_ERR_CUDA);
-  if (!alloc((void**)&ctx->d_params, sizeof(FrameParams)) ||
+  if (!alloc((void**)&ctx->d_params, sizeof(FrameParams) * VRS_NQ) ||
       cudaHostAlloc((void**)&ctx->h_params, sizeof(FrameParams) * VRS_PARAM_SLOTS, cudaHostAllocDefault) != cudaSuccess) { ctx->err = "param alloc failed"; return bail(VRS_ERR_CUDA); }
   for (int i = 0; i < VRS_PARAM_SLOTS; ++i)
     if (cudaEventCreateWithFlags(&ctx->param_ev[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
@@ -186,6 +216,7 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
 }
 
 static void invalidate_graphs(vrs_ctx* ctx) {
+  if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   ctx->graphs.clear(); ctx->seen.clear();
@@ -199,8 +230,10 @@ static void free_grid(vrs_ctx* ctx) {
 void vrs_destroy(vrs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) comm_destroy(ctx->comm);
+  for (int i = 0; i < VRS_NQ; ++i) { if (ctx->ev_front_done[i]) cudaEventDestroy(ctx->ev_front_done[i]); if (ctx->ev_back_done[i]) cudaEventDestroy(ctx->ev_back_done[i]); }
   for (vrs_ctx::Peer* p : {&ctx->peer_up, &ctx->peer_down}) for (void* q : p->opened) cudaIpcCloseMemHandle(q);
   cudaFree(ctx->xflags);
   free_grid(ctx);
@@ -219,6 +252,7 @@ void vrs_destroy(vrs_ctx* ctx) {
   if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
   if (ctx->ev_halo_src) cudaEventDestroy(ctx->ev_halo_src);
   if (ctx->ev_halo_done) cudaEventDestroy(ctx->ev_halo_done);
+  if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -306,6 +340,7 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
       attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
       attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaStreamSetAttribute(ctx->front_stream, cudaStreamAttributeAccessPolicyWindow, &attr);
       cudaGetLastError();       // best effort: the window is an optimisation, never an error
     }
   }
@@ -515,26 +550,33 @@ static vrs_status make_params(vrs_ctx* ctx, const vrs_global_uniforms* gu, const
   return VRS_OK;
 }
 
-// Per-frame values travel through one device-resident FrameParams (fed from a ring of pinned host slots), so the kernels'
-// launch arguments never change and the whole frame can be replayed as a CUDA graph.
-static vrs_status upload_params(vrs_ctx* ctx, const FrameParams& F) {
+// Per-frame values travel through device-resident FrameParams blocks (fed from a ring of pinned host slots), so the
+// kernels' launch arguments never change and the frame halves can be replayed as CUDA graphs.  Frame n uses block n % 2.
+static vrs_status upload_params(vrs_ctx* ctx, const FrameParams& F, int q, cudaStream_t st) {
   const int slot = (int)(ctx->param_serial % VRS_PARAM_SLOTS);
   if (ctx->param_serial >= VRS_PARAM_SLOTS) CK(cudaEventSynchronize(ctx->param_ev[slot]));   // slot free again (normally long since)
   ctx->h_params[slot] = F;
-  CK(cudaMemcpyAsync(ctx->d_params, &ctx->h_params[slot], sizeof(FrameParams), cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaEventRecord(ctx->param_ev[slot], ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_params + q, &ctx->h_params[slot], sizeof(FrameParams), cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(ctx->param_ev[slot], st));
   ctx->param_serial++;
   return VRS_OK;
 }
 
-// Halo exchange on the communication stream, forked from and joined back into the main stream with events (the same
-// calls work under stream capture).  `wait_now` false leaves the join to the consumer (k_finish waits on ev_halo_done).
-// `max_rows` limits the rows sent per side (spatial reuse needs ceil(spatialRadius) rows, the temporal reprojection all
-// halo rows the neighbour stores).
-static vrs_status exchange(vrs_ctx* ctx, bool gbuf, int g_index, int r_index, bool wait_now, int max_rows) {
+static FrameIdx frame_idx(uint64_t n) {
+  FrameIdx f;
+  f.g = (int)(n % VRS_NG); f.gprev = (int)((n + VRS_NG - 1) % VRS_NG);
+  f.ra = 2 * (int)(n % 3); f.rb = f.ra + 1;
+  f.q = (int)(n % VRS_NQ);
+  return f;
+}
+
+// ---- halo exchange, producer and consumer side.  halo_push sends rows of the given planes to both neighbours and leaves a
+// pending mark; halo_wait (placed by the next phase, right before the first kernel that reads halo rows) joins it.
+// `max_rows` limits the rows sent per side: spatial reuse needs ceil(spatialRadius) rows, the temporal reprojection every
+// halo row the neighbour stores.
+static vrs_status halo_push(vrs_ctx* ctx, cudaStream_t st, bool gbuf, int g_index, int r_index, int max_rows) {
   if (ctx->peer_mode) {
-    // one kernel stores the boundary rows into both neighbours' halo rows (NVLink P2P) and publishes the serial;
-    // the wait kernel (consumer side) goes right before the first kernel that reads the halos
+    // one kernel stores the boundary rows into both neighbours' halo rows (NVLink P2P / same-device stores) and publishes the serial
     HaloPush H; memset(&H, 0, sizeof(H));
     auto add = [&](float4* mine, float4* up, float4* down) { H.src[H.nplanes] = mine; H.up_dst[H.nplanes] = up; H.down_dst[H.nplanes] = down; H.nplanes++; };
     if (gbuf) for (int p = 0; p < 4; ++p) add(ctx->g_planes[g_index][p], ctx->peer_up.present ? ctx->peer_up.g[g_index][p] : nullptr, ctx->peer_down.present ? ctx->peer_down.g[g_index][p] : nullptr);
@@ -553,13 +595,10 @@ static vrs_status exchange(vrs_ctx* ctx, bool gbuf, int g_index, int r_index, bo
       H.down_dst_off = (size_t)(ctx->band_y1 - rows - ctx->peer_down.store_y0) * ctx->W; H.down_flag = ctx->peer_down.flags + 0;   // "written by the up neighbour"
     }
     H.serial = ctx->xflags + 2; H.block_counter = ctx->xflags + 3;
-    launch_halo_push(ctx->stream, H, 64, &ctx->kt);
+    launch_halo_push(st, H, 64, &ctx->kt);
     CK(cudaGetLastError());
     ctx->timings.launches += 1;
-    if (wait_now) {
-      launch_halo_wait(ctx->stream, ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4, &ctx->kt);
-      CK(cudaGetLastError());
-    }
+    ctx->halo_pending = true;
     return VRS_OK;
   }
   if (!ctx->comm) return VRS_OK;
@@ -567,51 +606,144 @@ static vrs_status exchange(vrs_ctx* ctx, bool gbuf, int g_index, int r_index, bo
   if (gbuf) for (int p = 0; p < 4; ++p) planes.push_back(ctx->g_planes[g_index][p]);
   if (r_index >= 0) for (int p = 0; p < 2; ++p) planes.push_back(ctx->r_planes[r_index][p]);
   std::string err;
-  CK(cudaEventRecord(ctx->ev_halo_src, ctx->stream));
+  CK(cudaEventRecord(ctx->ev_halo_src, st));
   CK(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_halo_src, 0));
   if (!comm_exchange_halo(ctx->comm, ctx->comm_stream, planes, ctx->W, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1, (int)ctx->H, max_rows, err))
     return fail(ctx, VRS_ERR_COMM, err);
   CK(cudaEventRecord(ctx->ev_halo_done, ctx->comm_stream));
-  if (wait_now) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo_done, 0));
+  ctx->halo_pending = true;
+  return VRS_OK;
+}
+static vrs_status halo_wait(vrs_ctx* ctx, cudaStream_t st) {
+  if (!ctx->halo_pending) return VRS_OK;
+  ctx->halo_pending = false;
+  if (ctx->peer_mode) {
+    launch_halo_wait(st, ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4, &ctx->kt);
+    CK(cudaGetLastError());
+    ctx->timings.launches += 1;
+  } else if (ctx->comm) {
+    CK(cudaStreamWaitEvent(st, ctx->ev_halo_done, 0));
+  }
   return VRS_OK;
 }
 
 // timing events must become event-record nodes when the frame is being captured into a graph
-static cudaError_t mark(vrs_ctx* ctx, int i) {
+static cudaError_t mark(vrs_ctx* ctx, int i, cudaStream_t st) {
   if (!ctx->pass_timing) return cudaSuccess;
-  return ctx->capturing ? cudaEventRecordWithFlags(ctx->ev[i], ctx->stream, cudaEventRecordExternal) : cudaEventRecord(ctx->ev[i], ctx->stream);
+  return ctx->capturing ? cudaEventRecordWithFlags(ctx->ev[i], st, cudaEventRecordExternal) : cudaEventRecord(ctx->ev[i], st);
+}
+static bool culling_on(vrs_ctx* ctx, const FrameParams& F) {
+  return F.cull && !ctx->trace && !getenv("VRS_NO_CULL") && (long long)ctx->grid.cdim[0] * ctx->grid.cdim[1] * ctx->grid.cdim[2] <= (1ll << 27);
 }
 
-static vrs_status enqueue_initial(vrs_ctx* ctx, const FrameParams& F, cudaEvent_t prev_halo_ready, bool peer_wait = false) {
-  int out = (ctx->final_r + 1) % 3;
-  const unsigned* pw[4] = {ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4};
-  launch_initial(ctx->stream, ctx->grid, ctx->lights, F, ctx->d_params, planes_of(ctx, ctx->cur_g), planes_of(ctx, 1 - ctx->cur_g),
-                 res_of(ctx, ctx->final_r), res_of(ctx, out), ctx->queues, ctx->trace, ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1,
-                 ctx->persistent_blocks, prev_halo_ready, peer_wait ? pw : nullptr, ctx->xflags + 5, &ctx->kt);
+// ---- the frame as phases.  Front: everything of the initial pass that is independent of the previous frame.  Back phases:
+//   0             [join the pending halo push] temporal merge + visibility (k_finish); with spatial reuse on several GPUs, push
+//                 the G-buffer + tmp reservoir rows spatial reuse can reach
+//   1 .. iters    [join] spatial iteration i - 1; push the new reservoir rows when another iteration follows
+//   iters + 1     shade; on several GPUs push what the next frame's temporal reprojection reads (all halo rows)
+// A phase never waits for a push of the same phase, so phases of several contexts may be interleaved by one host thread in
+// any order that keeps the phase number non-decreasing (vrs_render_frame_group).
+static vrs_status enqueue_front(vrs_ctx* ctx, const FrameParams& F, const FrameIdx& fi, cudaStream_t st) {
+  CK(mark(ctx, 0, st));
+  launch_initial_front(st, ctx->grid, ctx->lights, F, ctx->d_params + fi.q, planes_of(ctx, fi.g), res_of(ctx, fi.ra), ctx->queues[fi.q], ctx->trace,
+                       ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks, &ctx->kt);
   CK(cudaGetLastError());
-  ctx->src_r = out; ctx->timings.launches += (uint32_t)initial_pass_launches(F.flags, F.cull && !ctx->trace && !getenv("VRS_NO_CULL") && (long long)ctx->grid.cdim[0] * ctx->grid.cdim[1] * ctx->grid.cdim[2] <= (1ll << 27), ctx->lights);
+  ctx->timings.launches += (uint32_t)initial_front_launches(F.flags, culling_on(ctx, F), ctx->lights);
+  ctx->src_r = fi.ra;
   return VRS_OK;
 }
-// part 0: every row; 1: rows whose neighbourhood lies inside the band (no halo needed); 2: the rest.  The reservoir
-// ping-pong advances after part 0 or 2.
-static vrs_status enqueue_spatial(vrs_ctx* ctx, uint32_t iteration, int part = 0) {
-  int dst = (ctx->src_r + 1) % 3;
-  const int halo = ctx->cfg.halo_rows;
-  const int ylo = ctx->peer_up.present ? ctx->band_y0 + halo : ctx->band_y0, yhi = ctx->peer_down.present ? ctx->band_y1 - halo : ctx->band_y1;
-  launch_spatial(ctx->stream, ctx->lights, ctx->d_params, planes_of(ctx, ctx->cur_g), res_of(ctx, ctx->src_r), res_of(ctx, dst), ctx->queues,
-                 iteration, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks, part, ylo, yhi, &ctx->kt);
+static int back_phases(vrs_ctx* ctx, const FrameParams& F) {
+  const bool spatial = (F.flags & VRS_RESTIR_SPATIAL_REUSE_FLAG) != 0 && ctx->cfg.spatial_iterations > 0;
+  return 2 + (spatial ? (int)ctx->cfg.spatial_iterations : 0);
+}
+static vrs_status enqueue_spatial(vrs_ctx* ctx, const FrameIdx& fi, uint32_t iteration, cudaStream_t st) {
+  const int dst = ctx->src_r == fi.ra ? fi.rb : fi.ra;
+  launch_spatial(st, ctx->lights, ctx->d_params + fi.q, planes_of(ctx, fi.g), res_of(ctx, ctx->src_r), res_of(ctx, dst), ctx->queues[fi.q],
+                 iteration, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks, 0, 0, 0, &ctx->kt);
   CK(cudaGetLastError());
-  if (part != 1) ctx->src_r = dst;
+  ctx->src_r = dst;
   ctx->timings.launches += 1;
   return VRS_OK;
 }
-static vrs_status enqueue_shade(vrs_ctx* ctx, const FrameParams& F) {
-  launch_shade(ctx->stream, ctx->grid, ctx->lights, F, ctx->d_params, planes_of(ctx, ctx->cur_g), res_of(ctx, ctx->src_r), ctx->accum, ctx->band_y0,
-               ctx->band_y1, ctx->store_y0, &ctx->kt);
-  CK(cudaGetLastError());
+static vrs_status enqueue_back_phase(vrs_ctx* ctx, const FrameParams& F, const FrameIdx& fi, int phase, bool want_temporal_push, cudaStream_t st) {
+  vrs_status s;
+  const bool spatial = (F.flags & VRS_RESTIR_SPATIAL_REUSE_FLAG) != 0 && ctx->cfg.spatial_iterations > 0;
+  const int iters = spatial ? (int)ctx->cfg.spatial_iterations : 0;
+  const bool multi = ctx->comm != nullptr || ctx->peer_mode;
+  int sp_rows = (int)ceilf(F.spatialRadius); if (sp_rows < 1) sp_rows = 1;      // |int(dy)| <= radius: the rows spatial reuse can reach
+  if (phase == 0) {
+    const bool needs_finish = (F.flags & (VRS_RESTIR_VISIBILITY_REUSE_FLAG | VRS_RESTIR_TEMPORAL_REUSE_FLAG)) != 0;
+    // the previous frame's G-buffer + final reservoir halo rows (pushed at the end of that frame) are read by the temporal merge
+    if ((s = halo_wait(ctx, st))) return s;
+    launch_initial_finish(st, ctx->lights, F, ctx->d_params + fi.q, planes_of(ctx, fi.g), planes_of(ctx, fi.gprev), res_of(ctx, ctx->final_r), res_of(ctx, fi.ra),
+                          ctx->queues[fi.q], ctx->trace, ctx->store_y0, ctx->store_y1, ctx->xflags + 5, &ctx->kt);   // main.cpp:405-409
+    CK(cudaGetLastError());
+    if (needs_finish) ctx->timings.launches += 1;
+    CK(mark(ctx, 1, st));
+    if (multi && spatial && (s = halo_push(ctx, st, true, fi.g, ctx->src_r, sp_rows))) return s;
+    CK(mark(ctx, 2, st));
+  } else if (phase <= iters) {                                                                       // main.cpp:410-413
+    if ((s = halo_wait(ctx, st))) return s;
+    if ((s = enqueue_spatial(ctx, fi, (uint32_t)(phase - 1), st))) return s;
+    if (multi && phase < iters && (s = halo_push(ctx, st, false, 0, ctx->src_r, sp_rows))) return s;
+  } else {
+    CK(mark(ctx, 3, st));
+    launch_shade(st, ctx->grid, ctx->lights, F, ctx->d_params + fi.q, planes_of(ctx, fi.g), res_of(ctx, ctx->src_r), ctx->accum, ctx->band_y0,
+                 ctx->band_y1, ctx->store_y0, &ctx->kt);                                             // main.cpp:416-433
+    CK(cudaGetLastError());
+    ctx->timings.launches += 1;
+    CK(mark(ctx, 4, st));
+    // what the NEXT frame's temporal reprojection may read of this frame: G-buffer + final reservoirs over every halo row.
+    // It is joined by phase 0 of the next frame, i.e. it overlaps that frame's front half.
+    if (multi && want_temporal_push && (s = halo_push(ctx, st, true, fi.g, ctx->src_r, 1 << 30))) return s;
+  }
+  return VRS_OK;
+}
+// host-side state of a completed frame (Renderer::updateGBufferFrameIdx, Renderer.cpp:108-111, generalised)
+static void finish_frame_state(vrs_ctx* ctx, const FrameIdx& fi) {
+  // a later front half that reuses this frame's queue set / parameter block / G-buffer slot waits for this event
+  if (cudaEventRecord(ctx->ev_back_done[fi.q], ctx->stream) == cudaSuccess) ctx->back_recorded[fi.q] = true;
+  ctx->final_r = ctx->src_r; ctx->last_g = fi.g; ctx->last_q = fi.q;
+  ctx->frame_no++;
   ctx->history_valid = true;
-  ctx->final_r = ctx->src_r; ctx->last_g = ctx->cur_g; ctx->cur_g = 1 - ctx->cur_g;   // updateGBufferFrameIdx, Renderer.cpp:108-111
-  ctx->timings.launches += 1;
+}
+
+// Graph cache: the launch sequence of a frame half depends only on the buffer rotation (frame_no % 6), on where the previous
+// frame left its final reservoirs, on the structural flags and on whether a halo push is pending.
+static uint64_t graph_key(vrs_ctx* ctx, const FrameParams& F, int half, bool want_temporal_push) {
+  uint64_t k = (uint64_t)(ctx->frame_no % 6) | ((uint64_t)(F.flags & 0x3f) << 6) | ((uint64_t)ctx->cfg.spatial_iterations << 12) |
+               ((uint64_t)(F.cull ? 1 : 0) << 16) | ((uint64_t)(ctx->pass_timing ? 1 : 0) << 17) | ((uint64_t)half << 19);
+  if (half == 1) k |= ((uint64_t)ctx->final_r << 3) | ((uint64_t)(ctx->peer_mode ? 1 : 0) << 15) | ((uint64_t)(ctx->halo_pending ? 1 : 0) << 18) |
+                      ((uint64_t)(want_temporal_push ? 1 : 0) << 20);
+  return k;
+}
+static vrs_status run_captured(vrs_ctx* ctx, uint64_t key, cudaStream_t st, const std::function<vrs_status()>& body) {
+  auto it = ctx->graphs.find(key);
+  if (it == ctx->graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    const uint32_t before = ctx->timings.launches;
+    CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    ctx->capturing = true;
+    vrs_status s = body();
+    ctx->capturing = false;
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (s) { if (graph) cudaGraphDestroy(graph); return s; }
+    if (e != cudaSuccess) { ctx->err = std::string("graph capture: ") + cudaGetErrorString(e); return VRS_ERR_CUDA; }
+    GraphEntry ge;
+    e = cudaGraphInstantiate(&ge.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) { ctx->err = std::string("graph instantiate: ") + cudaGetErrorString(e); return VRS_ERR_CUDA; }
+    ge.launches = ctx->timings.launches - before;
+    it = ctx->graphs.emplace(key, ge).first;
+  } else {
+    // replay: the body only advances host-side state (buffer rotation, pending marks); it enqueues nothing
+    ctx->replaying = true;
+    vrs_status s = body();
+    ctx->replaying = false;
+    if (s) return s;
+    ctx->timings.launches += it->second.launches;
+  }
+  CK(cudaGraphLaunch(it->second.exec, st));
   return VRS_OK;
 }
 
@@ -619,126 +751,114 @@ vrs_status vrs_pass_initial(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
   if (!ctx || !gu || !ru) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
   FrameParams F; vrs_status s = make_params(ctx, gu, ru, nullptr, clock, F); if (s) return s;
-  if ((s = upload_params(ctx, F))) return s;
-  return enqueue_initial(ctx, F, nullptr);
+  const FrameIdx fi = frame_idx(ctx->frame_no);
+  ctx->cur = fi;
+  CK(cudaStreamSynchronize(ctx->front_stream));          // the per-pass calls run on the main stream, strictly in order
+  if ((s = upload_params(ctx, F, fi.q, ctx->stream))) return s;
+  if ((s = enqueue_front(ctx, F, fi, ctx->stream))) return s;
+  return enqueue_back_phase(ctx, F, fi, 0, false, ctx->stream);
 }
 vrs_status vrs_pass_spatial(vrs_ctx* ctx, const vrs_restir_uniforms* ru, uint32_t clock, uint32_t iteration) {
   if (!ctx || !ru || iteration >= VRS_MAX_SPATIAL_ITERATIONS) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
   FrameParams F; vrs_status s = make_params(ctx, nullptr, ru, nullptr, clock, F); if (s) return s;
-  if ((s = upload_params(ctx, F))) return s;
-  return enqueue_spatial(ctx, iteration);
+  if ((s = upload_params(ctx, F, ctx->cur.q, ctx->stream))) return s;
+  return enqueue_spatial(ctx, ctx->cur, iteration, ctx->stream);
 }
 vrs_status vrs_pass_shade(vrs_ctx* ctx, const vrs_restir_uniforms* ru, const vrs_push_constant_restir* pc, uint32_t clock) {
   if (!ctx || !ru || !pc) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
   FrameParams F; vrs_status s = make_params(ctx, nullptr, ru, pc, clock, F); if (s) return s;
-  if ((s = upload_params(ctx, F))) return s;
-  return enqueue_shade(ctx, F);
-}
-
-// One frame in main.cpp:405-433 order.  With several GPUs the halo rows the temporal merge needs (previous frame's
-// G-buffer + final reservoirs) are exchanged at the START of the frame on the communication stream and joined just
-// before k_finish, so the transfer hides behind classify / raymarch / RIS / shadow rays.
-static vrs_status enqueue_frame(vrs_ctx* ctx, const FrameParams& F) {
-  vrs_status s;
-  const bool spatial = (F.flags & VRS_RESTIR_SPATIAL_REUSE_FLAG) != 0 && ctx->cfg.spatial_iterations > 0;
-  const bool temporal = (F.flags & VRS_RESTIR_TEMPORAL_REUSE_FLAG) != 0;
-  if (ctx->kt.on) { ctx->kt.n = 0; CK(cudaEventRecord(ctx->kt.ev[0], ctx->stream)); }
-  CK(mark(ctx, 0));
-  const bool multi = ctx->comm != nullptr || ctx->peer_mode;
-  const int all_rows = 1 << 30;
-  int sp_rows = (int)ceilf(F.spatialRadius); if (sp_rows < 1) sp_rows = 1;      // |int(dy)| <= radius: the rows spatial reuse can reach
-  bool halo_in_flight = false;
-  if (multi && temporal) {
-    // The temporal reprojection may land anywhere in the halo (its height is sized from the camera motion), so the
-    // previous frame's G-buffer and final reservoirs travel with all halo rows.  The consumer-side join (event wait for
-    // NCCL, flag-wait kernel for peer memory) sits right before k_finish.
-    if ((s = exchange(ctx, true, 1 - ctx->cur_g, ctx->final_r, false, all_rows))) return s;
-    halo_in_flight = true;
-  }
-  if ((s = enqueue_initial(ctx, F, halo_in_flight && !ctx->peer_mode ? ctx->ev_halo_done : nullptr, halo_in_flight && ctx->peer_mode))) return s;   // main.cpp:405-409
-  CK(mark(ctx, 1));
-  // Optional (VRS_SPLIT_SPATIAL=1, peer-memory mode): split every spatial iteration by rows - the rows whose neighbourhood
-  // lies inside the band run while the halo rows are in flight, the wait for the neighbours' flags comes after them, then
-  // the rows next to the band edges.  Bit-identical, but measured slower on 2 B200 (4K, 1.43 ms vs 1.36 ms per frame).
-  static const bool no_split = !(getenv("VRS_SPLIT_SPATIAL") && getenv("VRS_SPLIT_SPATIAL")[0] == '1');
-  const bool split = multi && spatial && ctx->peer_mode && !no_split && spatial_supports_row_split() && F.spatialRadius <= (float)ctx->cfg.halo_rows;
-  if (multi && spatial && (s = exchange(ctx, true, ctx->cur_g, ctx->src_r, !split, sp_rows))) return s;
-  CK(mark(ctx, 2));
-  if (spatial) {
-    for (uint32_t it = 0; it < ctx->cfg.spatial_iterations; ++it) {                                   // main.cpp:410-413
-      if (split) {
-        if ((s = enqueue_spatial(ctx, it, 1))) return s;
-        launch_halo_wait(ctx->stream, ctx->xflags + 2, ctx->peer_up.present ? ctx->xflags + 0 : nullptr, ctx->peer_down.present ? ctx->xflags + 1 : nullptr, ctx->xflags + 4, &ctx->kt);
-        CK(cudaGetLastError());
-        ctx->timings.launches += 1;
-        if ((s = enqueue_spatial(ctx, it, 2))) return s;
-      } else if ((s = enqueue_spatial(ctx, it))) return s;
-      if (multi && it + 1 < ctx->cfg.spatial_iterations && (s = exchange(ctx, false, 0, ctx->src_r, !split, sp_rows))) return s;
-    }
-  }
-  CK(mark(ctx, 3));
-  if ((s = enqueue_shade(ctx, F))) return s;                                                          // main.cpp:416-433
-  CK(mark(ctx, 4));
+  if ((s = upload_params(ctx, F, ctx->cur.q, ctx->stream))) return s;
+  launch_shade(ctx->stream, ctx->grid, ctx->lights, F, ctx->d_params + ctx->cur.q, planes_of(ctx, ctx->cur.g), res_of(ctx, ctx->src_r), ctx->accum, ctx->band_y0,
+               ctx->band_y1, ctx->store_y0, &ctx->kt);
+  CK(cudaGetLastError());
+  finish_frame_state(ctx, ctx->cur);
   return VRS_OK;
 }
 
+// One frame in main.cpp:405-433 order.
 vrs_status vrs_render_frame(vrs_ctx* ctx, const vrs_global_uniforms* gu, const vrs_restir_uniforms* ru, const vrs_push_constant_restir* pc, uint32_t clock) {
   if (!ctx || !gu || !ru || !pc) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
   FrameParams F; vrs_status s = make_params(ctx, gu, ru, pc, clock, F); if (s) return s;
-  if ((s = upload_params(ctx, F))) return s;
   ctx->timings.launches = 0;
   static const bool no_graph = getenv("VRS_NO_GRAPH") != nullptr;
-  static const bool no_graph_comm = getenv("VRS_NO_GRAPH_COMM") != nullptr;
-  (void)no_graph_comm;
-  if (no_graph || ctx->comm || ctx->kt.on) {     // NCCL send/recv under stream capture hangs here (NCCL 2.28.9): NCCL contexts launch eagerly
-    if ((s = enqueue_frame(ctx, F))) return s;
-    ctx->timings_valid = ctx->pass_timing;
+  // NCCL send/recv under stream capture hangs here (NCCL 2.28.9): NCCL contexts launch eagerly.  Per-kernel timing and
+  // per-pass timing want one stream with nothing overlapping the kernels they bracket.
+  const bool eager = no_graph || ctx->comm || ctx->kt.on;
+  const bool overlap = ctx->pipeline && !ctx->kt.on && !ctx->pass_timing;
+  const FrameIdx fi = frame_idx(ctx->frame_no);
+  ctx->cur = fi;
+  const bool want_temporal_push = (ru->flags & VRS_RESTIR_TEMPORAL_REUSE_FLAG) != 0;
+  cudaStream_t fs = overlap ? ctx->front_stream : ctx->stream;
+  if (ctx->kt.on) { ctx->kt.n = 0; CK(cudaEventRecord(ctx->kt.ev[0], ctx->stream)); }
+  // ---- front half: needs the queue set / parameter block / G-buffer that frame n - 2 (n - 3) used
+  if (overlap && ctx->back_recorded[fi.q]) CK(cudaStreamWaitEvent(fs, ctx->ev_back_done[fi.q], 0));
+  if ((s = upload_params(ctx, F, fi.q, fs))) return s;
+  if (eager) s = enqueue_front(ctx, F, fi, fs);
+  else s = run_captured(ctx, graph_key(ctx, F, 0, false), fs, [&]() -> vrs_status {
+    if (ctx->replaying) { ctx->src_r = fi.ra; return VRS_OK; }
+    return enqueue_front(ctx, F, fi, fs);
+  });
+  if (s) return s;
+  if (overlap) { CK(cudaEventRecord(ctx->ev_front_done[fi.q], fs)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_front_done[fi.q], 0)); }
+  // ---- back half
+  const int nph = back_phases(ctx, F);
+  auto back = [&]() -> vrs_status {
+    if (ctx->replaying) {       // host-side state only: reservoir rotation and the pending mark of the last push
+      const bool spatial = (F.flags & VRS_RESTIR_SPATIAL_REUSE_FLAG) != 0 && ctx->cfg.spatial_iterations > 0;
+      if (spatial) for (uint32_t i = 0; i < ctx->cfg.spatial_iterations; ++i) ctx->src_r = ctx->src_r == fi.ra ? fi.rb : fi.ra;
+      ctx->halo_pending = (ctx->comm != nullptr || ctx->peer_mode) && want_temporal_push;
+      return VRS_OK;
+    }
+    for (int ph = 0; ph < nph; ++ph) { vrs_status s2 = enqueue_back_phase(ctx, F, fi, ph, want_temporal_push, ctx->stream); if (s2) return s2; }
     return VRS_OK;
-  }
-  // The launch sequence depends only on which buffers are current (6 ping-pong phases) and on the structural flags.
-  const uint64_t key = (uint64_t)ctx->cur_g | ((uint64_t)ctx->final_r << 1) | ((uint64_t)(F.flags & 0x3f) << 3) | ((uint64_t)ctx->cfg.spatial_iterations << 9) |
-                       ((uint64_t)(ctx->comm ? 1 : 0) << 12) | ((uint64_t)(ctx->peer_mode ? 1 : 0) << 13) | ((uint64_t)(F.cull ? 1 : 0) << 14) | ((uint64_t)(ctx->pass_timing ? 1 : 0) << 15);
-  auto it = ctx->graphs.find(key);
-  if (it == ctx->graphs.end() && ctx->seen[key]++ == 0) {
-    // first frame of a phase runs eagerly: NCCL sets up its peer connections on first use, which must not happen under capture
-    if ((s = enqueue_frame(ctx, F))) return s;
-    ctx->timings_valid = ctx->pass_timing;
-    return VRS_OK;
-  }
-  if (it == ctx->graphs.end()) {
-    const int cur_g = ctx->cur_g, final_r = ctx->final_r;
-    cudaGraph_t graph = nullptr;
-    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    ctx->capturing = true;
-    s = enqueue_frame(ctx, F);
-    ctx->capturing = false;
-    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
-    if (s) { if (graph) cudaGraphDestroy(graph); return s; }
-    if (e != cudaSuccess) { ctx->err = std::string("graph capture: ") + cudaGetErrorString(e); return VRS_ERR_CUDA; }
-    GraphEntry ge;
-    e = cudaGraphInstantiate(&ge.exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) { ctx->err = std::string("graph instantiate: ") + cudaGetErrorString(e); return VRS_ERR_CUDA; }
-    ge.launches = ctx->timings.launches; ge.next_cur_g = ctx->cur_g; ge.next_final_r = ctx->final_r; ge.next_src_r = ctx->src_r; ge.last_g = ctx->last_g;
-    (void)cur_g; (void)final_r;
-    it = ctx->graphs.emplace(key, ge).first;
-  } else {
-    const GraphEntry& ge = it->second;            // replay: same buffer rotation the capture performed
-    ctx->cur_g = ge.next_cur_g; ctx->final_r = ge.next_final_r; ctx->src_r = ge.next_src_r; ctx->last_g = ge.last_g;
-    ctx->timings.launches = ge.launches;
-  }
-  CK(cudaGraphLaunch(it->second.exec, ctx->stream));
+  };
+  s = eager ? back() : run_captured(ctx, graph_key(ctx, F, 1, want_temporal_push), ctx->stream, back);
+  if (s) return s;
+  finish_frame_state(ctx, fi);
   ctx->timings_valid = ctx->pass_timing;
-  ctx->history_valid = true;
+  return VRS_OK;
+}
+
+// The same frame on several contexts driven by ONE host thread (bands of one image: several GPUs of one process, or several
+// bands on one GPU): phase k of every context is enqueued before phase k + 1 of any, so a context's wait for its neighbours'
+// rows is always enqueued after the pushes it waits for — safe even when the contexts' streams share a hardware queue.
+vrs_status vrs_render_frame_group(vrs_ctx** ctxs, uint32_t n, const vrs_global_uniforms* gu, const vrs_restir_uniforms* ru,
+                                  const vrs_push_constant_restir* pc, uint32_t clock) {
+  if (!ctxs || n == 0 || !gu || !ru || !pc) return VRS_ERR_INVALID;
+  std::vector<FrameParams> F(n);
+  std::vector<FrameIdx> fi(n);
+  const bool want_temporal_push = (ru->flags & VRS_RESTIR_TEMPORAL_REUSE_FLAG) != 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    vrs_ctx* ctx = ctxs[i];
+    if (!ctx) return VRS_ERR_INVALID;
+    if (ctx->comm) return fail(ctx, VRS_ERR_INVALID, "vrs_render_frame_group drives peer-memory contexts (vrs_peer_connect_local), not NCCL ones");
+    cudaSetDevice(ctx->device);
+    vrs_status s = make_params(ctx, gu, ru, pc, clock, F[i]); if (s) return s;
+    ctx->timings.launches = 0;
+    fi[i] = frame_idx(ctx->frame_no); ctx->cur = fi[i];
+    CK(cudaStreamSynchronize(ctx->front_stream));
+    if ((s = upload_params(ctx, F[i], fi[i].q, ctx->stream))) return s;
+    if ((s = enqueue_front(ctx, F[i], fi[i], ctx->stream))) return s;
+  }
+  const int nph = back_phases(ctxs[0], F[0]);
+  for (int ph = 0; ph < nph; ++ph)
+    for (uint32_t i = 0; i < n; ++i) {
+      vrs_ctx* ctx = ctxs[i];
+      cudaSetDevice(ctx->device);
+      if (back_phases(ctx, F[i]) != nph) return fail(ctx, VRS_ERR_INVALID, "contexts of a group must share spatial_iterations");
+      vrs_status s = enqueue_back_phase(ctx, F[i], fi[i], ph, want_temporal_push, ctx->stream); if (s) return s;
+    }
+  for (uint32_t i = 0; i < n; ++i) { finish_frame_state(ctxs[i], fi[i]); ctxs[i]->timings_valid = false; }
   return VRS_OK;
 }
 
 vrs_status vrs_synchronize(vrs_ctx* ctx) {
   if (!ctx) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
+  CK(cudaStreamSynchronize(ctx->front_stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->comm_stream) CK(cudaStreamSynchronize(ctx->comm_stream));
   if (ctx->peer_mode) {          // did a halo wait give up?  (k_halo_wait sets xflags[4]; stale halo rows must not pass as VRS_OK)
@@ -874,18 +994,18 @@ vrs_status vrs_write_image(vrs_ctx* ctx, const char* path) {
 }
 
 // ------------------------------------------------------------------------------------------ multi-GPU
-// ---- peer-memory exchange set-up: blob = { band_y0, band_y1, store_y0, store_y1 (int32) | 15 x cudaIpcMemHandle_t }
+// ---- peer-memory exchange set-up: blob = { band_y0, band_y1, store_y0, store_y1 (int32) | 25 x cudaIpcMemHandle_t }
 vrs_status vrs_peer_export(vrs_ctx* ctx, uint8_t blob[VRS_PEER_BLOB_BYTES]) {
   if (!ctx || !blob) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  static_assert(16 + 15 * sizeof(cudaIpcMemHandle_t) <= VRS_PEER_BLOB_BYTES, "blob too small");
+  static_assert(16 + (VRS_NG * 4 + VRS_NR * 2 + 1) * sizeof(cudaIpcMemHandle_t) <= VRS_PEER_BLOB_BYTES, "blob too small");
   memset(blob, 0, VRS_PEER_BLOB_BYTES);
   int32_t hdr[4] = {ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1};
   memcpy(blob, hdr, 16);
   cudaIpcMemHandle_t* h = (cudaIpcMemHandle_t*)(blob + 16);
   int k = 0;
-  for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) CK(cudaIpcGetMemHandle(&h[k++], ctx->g_planes[i][p]));
-  for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) CK(cudaIpcGetMemHandle(&h[k++], ctx->r_planes[i][p]));
+  for (int i = 0; i < VRS_NG; ++i) for (int p = 0; p < 4; ++p) CK(cudaIpcGetMemHandle(&h[k++], ctx->g_planes[i][p]));
+  for (int i = 0; i < VRS_NR; ++i) for (int p = 0; p < 2; ++p) CK(cudaIpcGetMemHandle(&h[k++], ctx->r_planes[i][p]));
   CK(cudaIpcGetMemHandle(&h[k++], ctx->xflags));
   return VRS_OK;
 }
@@ -902,8 +1022,8 @@ vrs_status vrs_peer_connect(vrs_ctx* ctx, int rank, int nranks, const uint8_t* a
     int k = 0;
     auto open = [&](void** out) -> vrs_status { cudaIpcMemHandle_t hh; memcpy(&hh, &h[k++], sizeof(hh)); CK(cudaIpcOpenMemHandle(out, hh, cudaIpcMemLazyEnablePeerAccess)); P.opened.push_back(*out); return VRS_OK; };
     vrs_status s;
-    for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) if ((s = open((void**)&P.g[i][p]))) return s;
-    for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) if ((s = open((void**)&P.r[i][p]))) return s;
+    for (int i = 0; i < VRS_NG; ++i) for (int p = 0; p < 4; ++p) if ((s = open((void**)&P.g[i][p]))) return s;
+    for (int i = 0; i < VRS_NR; ++i) for (int p = 0; p < 2; ++p) if ((s = open((void**)&P.r[i][p]))) return s;
     if ((s = open((void**)&P.flags))) return s;
     P.present = true;
     return VRS_OK;
@@ -949,8 +1069,8 @@ vrs_status vrs_peer_connect_local(vrs_ctx* ctx, vrs_ctx* up, vrs_ctx* down) {
       cudaGetLastError();
     }
     P.band_y0 = o->band_y0; P.band_y1 = o->band_y1; P.store_y0 = o->store_y0; P.store_y1 = o->store_y1;
-    for (int i = 0; i < 2; ++i) for (int p = 0; p < 4; ++p) P.g[i][p] = o->g_planes[i][p];
-    for (int i = 0; i < 3; ++i) for (int p = 0; p < 2; ++p) P.r[i][p] = o->r_planes[i][p];
+    for (int i = 0; i < VRS_NG; ++i) for (int p = 0; p < 4; ++p) P.g[i][p] = o->g_planes[i][p];
+    for (int i = 0; i < VRS_NR; ++i) for (int p = 0; p < 2; ++p) P.r[i][p] = o->r_planes[i][p];
     P.flags = o->xflags;
     P.present = true;
     return VRS_OK;
@@ -985,7 +1105,7 @@ vrs_status vrs_get_counters(vrs_ctx* ctx, vrs_counters* out) {
   cudaSetDevice(ctx->device);
   uint32_t q[8] = {0}; unsigned x[8] = {0};
   CK(cudaStreamSynchronize(ctx->stream));
-  CK(cudaMemcpy(q, ctx->queues.counters, sizeof(q), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(q, ctx->queues[ctx->last_q].counters, sizeof(q), cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(x, ctx->xflags, sizeof(x), cudaMemcpyDeviceToHost));
   out->candidates = q[0]; out->hits = q[1]; out->shadow_rays = q[2];
   out->temporal_out_of_halo = x[5];

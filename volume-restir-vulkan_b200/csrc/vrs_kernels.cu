@@ -303,59 +303,6 @@ __global__ void __launch_bounds__(128, MINB) k_ris_thread(const GridDev G, const
 }
 
 
-// One thread per hit pixel, M-candidate loop with the light-table fetches software-pipelined two candidates ahead.
-__global__ void __launch_bounds__(128, 6) k_ris_prefetch(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
-                                             Queues Q, uint32_t* __restrict__ trace, int store_y0, int needs_finish) {
-  const FrameParams& F = *Fp;
-  const uint32_t nhit = Q.counters[Q_HIT];
-  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
-    uint32_t idx, vcode, seed; GInfo gi;
-    ris_hit_setup(G, F, cur, Q, s, store_y0, idx, vcode, seed, gi);
-    const V3 P = gi.worldPos;
-    Res res = newReservoir();
-    if (dot(gi.normal, gi.normal) != 0.0f) {                                                           // :205
-      const ShadePre pre = shade_pre(gi);
-      // The draws of candidate c are draws 3c+1..3c+3 of the pixel's LCG stream whatever the data, so a second RNG state
-      // runs ahead of the loop: the alias cell of candidate c+2 and the light of candidate c+1 are requested while
-      // candidate c is evaluated, which takes the two dependent L2 fetches (restir.rgen:97-134) off the critical path.
-      uint32_t sP = seed;
-      uint32_t selA, colB; float pdfA, lewA, r2B; float4 lpA, cellB;
-      {
-        const float r1 = rnd(sP), r2 = rnd(sP); lcg(sP);
-        aliasTableSample(L, r1, r2, selA, pdfA);
-        lpA = __ldg(&L.lights[2 * selA]); lewA = __ldg(reinterpret_cast<const float*>(L.lights) + 8 * (size_t)selA + 7);
-        const float q1 = rnd(sP); r2B = rnd(sP); lcg(sP);
-        colB = aliasColumn(L, q1); cellB = __ldg(&L.alias[colB]);
-      }
-      uint32_t selM = 0u; float selSumW = 0.0f;
-      const uint32_t M = F.M;
-      for (uint32_t c = 0; c < M; ++c) {                                                               // :206-226
-        uint32_t selN; float pdfN;
-        aliasPick(cellB, colB, r2B, selN, pdfN);                                                       // candidate c+1: light request
-        const float4 lpN = __ldg(&L.lights[2 * selN]);
-        const float lewN = __ldg(reinterpret_cast<const float*>(L.lights) + 8 * (size_t)selN + 7);
-        { const float q1 = rnd(sP); r2B = rnd(sP); lcg(sP); colB = aliasColumn(L, q1); cellB = __ldg(&L.alias[colB]); }   // candidate c+2: alias request
-        const uint32_t sampleSeed = seed;                                                              // :213
-        lcg(seed); lcg(seed);                                                                          // r1, r2 were drawn by the look-ahead state
-        const float pHat = evaluatePHatLight(v3(lpA.x, lpA.y, lpA.z), lewA, gi, pre);                  // reservoir.glsl:45-54
-        const float weight = pHat / pdfA;
-        res.M += 1;
-        res.sumWeights += weight;                                                                      // reservoir.glsl:30-43
-        const float replacePossibility = weight / res.sumWeights;
-        if (rnd(seed) < replacePossibility) {
-          res.lightIndex = selA; res.lightKind = 0; res.pHat = pHat; res.sampleSeed = sampleSeed;
-          selM = res.M; selSumW = res.sumWeights;                                                      // w = (sumW + weight) / (M * pHat), formed once below
-        }
-        selA = selN; pdfA = pdfN; lpA = lpN; lewA = lewN;
-      }
-      if (selM != 0u) res.w = selSumW / (float(selM) * res.pHat);                                      // reservoir.glsl:51
-    }
-    ris_hit_store(G, L, F, outR, Q, trace, needs_finish, s, idx, vcode, seed, P, res);
-  }
-}
-
-
-
 // ---- A3, cooperative form.  The candidates of restir.rgen:206-226 are independent except for the running sum of the
 // streaming reservoir, so a warp takes a group of up to 32 hit pixels and turns the work 90 degrees twice:
 //   step 1  lane = pixel      gradient normal, G-buffer stores, per-pixel shading terms -> shared memory
@@ -973,9 +920,11 @@ static int resident_grid(K kernel, int block_threads, int fallback_per_sm) {
 // ------------------------------------------------------------------------------------------------- launchers
 // `F` is the host copy (launch geometry, which kernels run); `dF` is the same struct in device memory, read by the
 // kernels — so that a captured CUDA graph of the frame stays valid while the per-frame values change.
-void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, Planes prev,
-                    ResPlanes prevR, ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1,
-                    int persistent_blocks, cudaEvent_t prev_halo_ready, const unsigned* const* peer_wait, unsigned* out_of_halo, KTimer* kt) {
+// Front half of the initial pass (everything that does not depend on the previous frame): coverage mask, classification,
+// primary volume event, hit list, RIS candidates, shadow rays.  Writes cur G-buffer, the tmp reservoir outR and the work
+// queues Q; the host runtime may run it concurrently with the back half of the previous frame (frames in flight).
+void launch_initial_front(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur,
+                          ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1, int persistent_blocks, KTimer* kt) {
   // tuning knobs of the persistent raymarch kernels: idle lanes that trigger a refill | cell visits per scheduling decision << 8
   // | warps that a small launch is spread over (lanes_for) << 16
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
@@ -988,9 +937,9 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   }();
   static const int refill = (getenv("VRS_REFILL") ? atoi(getenv("VRS_REFILL")) : REFILL_MIN_IDLE) |
                             ((getenv("VRS_CELLS") ? atoi(getenv("VRS_CELLS")) : CELLS_PER_DECISION) << 8) | (target_warps << 16);
-  // RIS stage: t(hread) | p(refetch) | c(oop) | a(uto).  Measured on B200 (profiles/r01_summary.md): with light tables that
-  // stay L1-resident the plain per-thread loop is fastest; once they spill to L2 (thousands of lights) the cooperative
-  // kernel, which keeps the dependent table fetches of several pixels in flight, wins.
+  // RIS stage: t(hread) | c(oop) | a(uto).  Measured on B200 (profiles/r01_summary.md): with light tables that stay
+  // L1-resident the plain per-thread loop is fastest; once they spill to L2 (thousands of lights) the cooperative kernel,
+  // which keeps the dependent table fetches of several pixels in flight, wins.
   static const char ris_env = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'a';
   static const uint32_t small_launch = getenv("VRS_RIS_SMALL") ? (uint32_t)atoi(getenv("VRS_RIS_SMALL")) : RIS_SMALL_LAUNCH;
   const bool big_tables = (size_t)L.nlights * 32 + (size_t)L.ntable * 16 > (size_t)64 * 1024;
@@ -1018,33 +967,32 @@ void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const
   ktick(kt, st, "k_hit_compact");
   const bool vis = (F.flags & FLAG_VISIBILITY) != 0, temporal = (F.flags & FLAG_TEMPORAL) != 0;
   const int needs_finish = (vis || temporal) ? 1 : 0;
-  static const bool one_wave = !getenv("VRS_NO_ONE_WAVE");
-  static const int ris_minb = getenv("VRS_RIS_MINB") ? atoi(getenv("VRS_RIS_MINB")) : 8;
-  static const int g_thread = one_wave ? (ris_minb >= 8 ? resident_grid(k_ris_thread<8>, 128, 8) : resident_grid(k_ris_thread<7>, 128, 7)) : persistent_blocks, g_prefetch = one_wave ? resident_grid(k_ris_prefetch, 128, 6) : persistent_blocks;
-  static const int g_finish = one_wave ? resident_grid(k_finish, 128, 8) : persistent_blocks;
-  if (ris_env == 't') { if (ris_minb >= 8) k_ris_thread<8><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, 0u); else k_ris_thread<7><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, 0u); }
-  else if (ris_env == 'p') k_ris_prefetch<<<g_prefetch, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish);
+  static const int g_thread = resident_grid(k_ris_thread<8>, 128, 8);
+  if (ris_env == 't') k_ris_thread<8><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, 0u);
   else if (ris_env == 'c' || big_tables) k_ris_coop<<<ris_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, target_warps, 0xFFFFFFFFu);
   else {   // auto, small tables: the hit count (known only on the device) picks the form; the other launch returns at once
     k_ris_coop<<<ris_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, target_warps, small_launch);
-    if (ris_minb >= 8) k_ris_thread<8><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
-    else k_ris_thread<7><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
+    k_ris_thread<8><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
   }
   ktick(kt, st, "k_ris");
   if (vis) { k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill); ktick(kt, st, "k_shadow"); }
-  // the previous frame's halo rows (multi-GPU) are only needed by the temporal merge: everything above overlapped their exchange
-  if (needs_finish && prev_halo_ready) cudaStreamWaitEvent(st, prev_halo_ready, 0);
-  if (needs_finish && peer_wait) { k_halo_wait<<<1, 1, 0, st>>>(peer_wait[0], peer_wait[1], peer_wait[2], const_cast<unsigned*>(peer_wait[3])); ktick(kt, st, "k_halo_wait"); }
-  if (needs_finish) { k_finish<<<g_finish, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1, out_of_halo); ktick(kt, st, "k_finish"); }
 }
-bool spatial_supports_row_split() { return !(getenv("VRS_SPATIAL") && getenv("VRS_SPATIAL")[0] == 'c'); }
-int initial_pass_launches(int flags, bool culling, const LightsDev& L) {
-  const bool vis = (flags & FLAG_VISIBILITY) != 0, temporal = (flags & FLAG_TEMPORAL) != 0;
+// Back half of the initial pass: apply the shadow transmittance, temporal merge with the previous frame's G-buffer /
+// final reservoirs (restir.rgen:229-284), final pack.  No-op when neither visibility nor temporal reuse is on.
+void launch_initial_finish(cudaStream_t st, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, Planes prev, ResPlanes prevR,
+                           ResPlanes outR, const Queues& Q, uint32_t* trace, int store_y0, int store_y1, unsigned* out_of_halo, KTimer* kt) {
+  if ((F.flags & (FLAG_VISIBILITY | FLAG_TEMPORAL)) == 0) return;
+  static const int g_finish = resident_grid(k_finish, 128, 8);
+  k_finish<<<g_finish, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1, out_of_halo);
+  ktick(kt, st, "k_finish");
+}
+int initial_front_launches(int flags, bool culling, const LightsDev& L) {
+  const bool vis = (flags & FLAG_VISIBILITY) != 0;
   // auto mode with small light tables launches both RIS forms (the device-side hit count decides which one works)
   const char ris_env = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'a';
   const bool big_tables = (size_t)L.nlights * 32 + (size_t)L.ntable * 16 > (size_t)64 * 1024;
   const int ris = (ris_env == 'a' && !big_tables) ? 2 : 1;
-  return 3 /* classify, primary, compact */ + ris + (culling ? 1 : 0) + (vis ? 1 : 0) + ((vis || temporal) ? 1 : 0);
+  return 3 /* classify, primary, compact */ + ris + (culling ? 1 : 0) + (vis ? 1 : 0);
 }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt) {
@@ -1056,11 +1004,8 @@ void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, P
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spatial_coop, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
     return sms * per_sm;
   }();
-  static const int minb = getenv("VRS_SPATIAL_MINB") ? atoi(getenv("VRS_SPATIAL_MINB")) : 8;
-  static const bool one_wave = !getenv("VRS_NO_ONE_WAVE");
-  static const int g8 = one_wave ? resident_grid(k_spatial_thread<8>, 128, 8) : persistent_blocks, g7 = one_wave ? resident_grid(k_spatial_thread<7>, 128, 7) : persistent_blocks;
-  if (thread_form && minb >= 8) k_spatial_thread<8><<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
-  else if (thread_form) k_spatial_thread<7><<<g7, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
+  static const int g8 = resident_grid(k_spatial_thread<8>, 128, 8);
+  if (thread_form) k_spatial_thread<8><<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
   else if (part != 2) k_spatial_coop<<<coop_blocks, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, target_warps);   // (no row split: part 1 does all)
   ktick(kt, s, "k_spatial");
 }

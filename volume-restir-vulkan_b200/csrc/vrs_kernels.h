@@ -26,13 +26,13 @@ inline void ktick(KTimer* kt, cudaStream_t s, const char* name) {
   cudaEventRecord(kt->ev[++kt->n], s);
 }
 
-void launch_initial(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, Planes prev,
-                    ResPlanes prevR, ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1,
-                    int persistent_blocks, cudaEvent_t prev_halo_ready, const unsigned* const* peer_wait, unsigned* out_of_halo, KTimer* kt);
-int initial_pass_launches(int flags, bool culling, const LightsDev& L);
+void launch_initial_front(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur,
+                          ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1, int persistent_blocks, KTimer* kt);
+void launch_initial_finish(cudaStream_t st, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, Planes prev, ResPlanes prevR,
+                           ResPlanes outR, const Queues& Q, uint32_t* trace, int store_y0, int store_y1, unsigned* out_of_halo, KTimer* kt);
+int initial_front_launches(int flags, bool culling, const LightsDev& L);
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt);
-bool spatial_supports_row_split();
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, ResPlanes rs,
                   float4* accum, int y0, int y1, int store_y0, KTimer* kt);
 void launch_halo_push(cudaStream_t s, const HaloPush& H, int blocks, KTimer* kt);
