@@ -566,9 +566,10 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def oracle_setup(workload):
+def oracle_setup(workload, lights_override=None):
     """The oracle's own scene for a workload: its own numpy .vrsg reader, its own light generator, no libvrs.so in this
-    process (procedural stand-in assets are generated by a child process)."""
+    process (procedural stand-in assets are generated by a child process).  `lights_override` (parity tests): use these
+    lights instead of generating them."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import grid_py
     import oracle as O
@@ -596,6 +597,8 @@ def oracle_setup(workload):
         return lights
 
     lights, ctr, diag = scene_lights(O.generate_point_lights, wl, lo, hi, emissive)
+    if lights_override is not None:
+        lights = np.ascontiguousarray(lights_override, np.float32).reshape(-1, 8)
     wl = dict(wl, lights=len(lights))
     scene = O.OracleScene(dens, vmin, g.voxel_size, g.translation, lights)
     return O, wl, scene, ctr, diag

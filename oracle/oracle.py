@@ -259,9 +259,10 @@ class OracleScene:
         lib().orc_scene_prepare(C.byref(s))
 
     def world_bbox(self):
-        s = self.c
-        lo = [s.A * (s.vmin[a] - 0.5) + s.B[a] for a in range(3)]
-        hi = [s.A * (s.vmin[a] + s.vdim[a] - 0.5) + s.B[a] for a in range(3)]
+        """fp32 like vrs_get_grid_info (so that lights generated inside the box are the same bits on both sides)."""
+        s, f = self.c, np.float32
+        lo = [float(f(s.A) * (f(s.vmin[a]) - f(0.5)) + f(s.B[a])) for a in range(3)]
+        hi = [float(f(s.A) * (f(s.vmin[a] + s.vdim[a]) - f(0.5)) + f(s.B[a])) for a in range(3)]
         return lo, hi
 
 

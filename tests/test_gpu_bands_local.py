@@ -89,10 +89,10 @@ def test_two_bands_equal_one_frame_bunny_4k(V):
 
 
 def test_small_halo_is_detected_not_silent(V):
-    """With the old fixed 32-row halo the same orbit drops temporal merges: the counter must say so."""
-    bad, ooh, _ = run_bands(V, "smoke_1080p_temporal", 2, 4, halo=32, check_counter=False)
-    assert ooh > 0
-    assert bad, "a too-small halo changed nothing?"
+    """A halo smaller than the orbit's reprojection distance drops temporal merges: the counter must say so."""
+    # (vertical reprojection grows with the distance from the image centre row: split where it is large)
+    bad, ooh, _ = run_bands(V, "smoke_1080p_temporal", 3, 4, halo=8, check_counter=False, edges=[0, 300, 800, 1080])
+    assert ooh > 0, (ooh, bad)
 
 
 def test_halo_wait_timeout_is_an_error(V):

@@ -501,6 +501,32 @@ __global__ void __launch_bounds__(128, 9) k_shadow(const GridDev G, Queues Q, in
   march_loop<1>(G, job, &Q.counters[Q_SHADOW_HEAD], njobs, refill & 0xff, (refill >> 8) & 0xff, lanes_for(njobs, nwarps, (uint32_t)(refill >> 16)));
 }
 
+// A/B forms (VRS_MARCH=s): one thread per ray, plain nested loops, no warp-level scheduling
+__global__ void __launch_bounds__(128, 8) k_shadow_simple(const GridDev G, Queues Q) {
+  const uint32_t njobs = Q.counters[Q_SHADOW];
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < njobs; j += gridDim.x * blockDim.x) {
+    ShadowJob job{Q, 0u};
+    Ray<1> ray; uint32_t seed;
+    job.fetch(G, j, ray, seed);
+    int st = RAY_SKIP;
+    while (st != RAY_DONE) st = st == RAY_SKIP ? ray.cell_step(G) : ray.collide_step(G, seed);
+    job.retire(G, ray, seed);
+  }
+}
+__global__ void __launch_bounds__(128, 8) k_primary_simple(const GridDev G, const FrameParams* __restrict__ Fp, Planes cur, Queues Q,
+                                                           uint32_t* __restrict__ trace, int store_y0) {
+  const FrameParams& F = *Fp;
+  const uint32_t njobs = Q.counters[Q_CAND];
+  for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < njobs; j += gridDim.x * blockDim.x) {
+    PrimaryJob job{F, cur, Q, trace, store_y0, 0u};
+    Ray<0> ray; uint32_t seed;
+    job.fetch(G, j, ray, seed);
+    int st = RAY_SKIP;
+    while (st != RAY_DONE) st = st == RAY_SKIP ? ray.cell_step(G) : ray.collide_step(G, seed);
+    job.retire(G, ray, seed);
+  }
+}
+
 __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, Planes prev, ResPlanes prevR,
                                                 ResPlanes outR, Queues Q, uint32_t* __restrict__ trace, int store_y0, int store_y1,
                                                 unsigned* __restrict__ out_of_halo) {
@@ -958,7 +984,10 @@ void launch_initial_front(cudaStream_t st, const GridDev& G, const LightsDev& L,
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_classify<<<grid, block, 0, st>>>(G, dF, cur, Q, trace, y0, y1, store_y0, tiles_x);
   ktick(kt, st, "k_classify");
-  k_primary<<<persistent_blocks, 128, 0, st>>>(G, dF, cur, Q, trace, store_y0, refill);
+  static const bool simple_march = getenv("VRS_MARCH") && getenv("VRS_MARCH")[0] == 's';
+  static const int g_ps = resident_grid(k_primary_simple, 128, 8) * (getenv("VRS_MARCH_WAVES") ? atoi(getenv("VRS_MARCH_WAVES")) : 1), g_ss = resident_grid(k_shadow_simple, 128, 8) * (getenv("VRS_MARCH_WAVES") ? atoi(getenv("VRS_MARCH_WAVES")) : 1);
+  if (simple_march) k_primary_simple<<<g_ps, 128, 0, st>>>(G, dF, cur, Q, trace, store_y0);
+  else k_primary<<<persistent_blocks, 128, 0, st>>>(G, dF, cur, Q, trace, store_y0, refill);
   ktick(kt, st, "k_primary");
   // compaction runs over every stored row (8-byte aligned flag loads); flags outside the band rows stay 0
   const size_t npix = (size_t)(store_y1 - store_y0) * F.W;
@@ -975,7 +1004,11 @@ void launch_initial_front(cudaStream_t st, const GridDev& G, const LightsDev& L,
     k_ris_thread<8><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
   }
   ktick(kt, st, "k_ris");
-  if (vis) { k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill); ktick(kt, st, "k_shadow"); }
+  if (vis) {
+    if (simple_march) k_shadow_simple<<<g_ss, 128, 0, st>>>(G, Q);
+    else k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill);
+    ktick(kt, st, "k_shadow");
+  }
 }
 // Back half of the initial pass: apply the shadow transmittance, temporal merge with the previous frame's G-buffer /
 // final reservoirs (restir.rgen:229-284), final pack.  No-op when neither visibility nor temporal reuse is on.
