@@ -149,8 +149,10 @@ static vrs_status alloc_frame_buffers(vrs_ctx* ctx) {
     if (cudaMalloc(p, bytes) != cudaSuccess) { ctx->err = "cudaMalloc failed (" + std::to_string(bytes) + " bytes)"; return false; }
     return cudaMemset(*p, 0, bytes) == cudaSuccess;
   };
-  for (int i = 0; i < VRS_NG; ++i) for (int p = 0; p < 4; ++p) if (!alloc((void**)&ctx->g_planes[i][p], ctx->npix * 16)) return VRS_ERR_CUDA;
-  for (int i = 0; i < VRS_NR; ++i) for (int p = 0; p < 2; ++p) if (!alloc((void**)&ctx->r_planes[i][p], ctx->npix * 16)) return VRS_ERR_CUDA;
+  // planes are exported through CUDA IPC (vrs_peer_export): whole multiples of 2 MB, so that each is an allocation block of its own
+  const size_t plane_bytes = ((ctx->npix * 16 + ((size_t)2 << 20) - 1) >> 21) << 21;
+  for (int i = 0; i < VRS_NG; ++i) for (int p = 0; p < 4; ++p) if (!alloc((void**)&ctx->g_planes[i][p], plane_bytes)) return VRS_ERR_CUDA;
+  for (int i = 0; i < VRS_NR; ++i) for (int p = 0; p < 2; ++p) if (!alloc((void**)&ctx->r_planes[i][p], plane_bytes)) return VRS_ERR_CUDA;
   if (!alloc((void**)&ctx->accum, ctx->npix * 16)) return VRS_ERR_CUDA;
   if (cfg->enable_trace && !alloc((void**)&ctx->trace, ctx->npix * 16)) return VRS_ERR_CUDA;
   const size_t ncompact = (ctx->npix + 2047) / 2048 + 1;
@@ -198,7 +200,9 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
     if (cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess) ctx->persistent_blocks = prop.multiProcessorCount * (getenv("VRS_BLOCKS_PER_SM") ? atoi(getenv("VRS_BLOCKS_PER_SM")) : 12);
   }
   for (int i = 0; i < 8; ++i) if (cudaEventCreate(&ctx->ev[i]) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
-  if (!alloc((void**)&ctx->xflags, 64)) return bail(VRS_ERR_CUDA);
+  // The exchange flags are exported through CUDA IPC: a handle names a whole allocation block, and small cudaMalloc requests are
+  // carved out of shared 2 MB blocks — an own 2 MB allocation makes the opened pointer land on the flags, not on a block base.
+  if (!alloc((void**)&ctx->xflags, (size_t)2 << 20)) return bail(VRS_ERR_CUDA);
   if (!alloc((void**)&ctx->d_params, sizeof(FrameParams) * VRS_NQ) ||
       cudaHostAlloc((void**)&ctx->h_params, sizeof(FrameParams) * VRS_PARAM_SLOTS, cudaHostAllocDefault) != cudaSuccess) { ctx->err = "param alloc failed"; return bail(VRS_ERR_CUDA); }
   for (int i = 0; i < VRS_PARAM_SLOTS; ++i)
