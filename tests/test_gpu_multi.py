@@ -61,6 +61,7 @@ def worker(rank, world, port, flags, frames, out_dir, mode):
         eye = common.orbit_eye(ctr, 4.2, 0.2, 10.0 + 1.0 * f)
         R.CameraManip.setLookat(eye, ctr)
         R.renderFrame(clock=f)
+        R.synchronize()
         mine = torch.from_numpy(R.readFrame())
         parts = [torch.zeros((V.band_for_rank(H, r, world)[1] - V.band_for_rank(H, r, world)[0], W, 4)) for r in range(world)] if rank == 0 else None
         dist.gather(mine, parts, dst=0)
@@ -127,14 +128,17 @@ def bench_worker(rank, world, port, name, frames, out_dir, mode):
         eye = bench.orbit_eye(ctr, radius, 0.0, bench.ORBIT_DEG * f)
         R.CameraManip.setLookat(eye, ctr)
         R.renderFrame(clock=f)
-        mine = torch.from_numpy(R.readFrame())
-        parts = [torch.zeros((edges[r + 1] - edges[r], W, 4)) for r in range(world)] if rank == 0 else None
+        R.synchronize()                                  # raises VRS_ERR_COMM when a halo wait timed out
+        rows_max = max(edges[r + 1] - edges[r] for r in range(world))          # gloo gather wants equal shapes: pad the bands
+        mine = torch.zeros((rows_max, W, 4))
+        mine[:band[1] - band[0]] = torch.from_numpy(R.readFrame())
+        parts = [torch.zeros((rows_max, W, 4)) for r in range(world)] if rank == 0 else None
         dist.gather(mine, parts, dst=0)
         if rank == 0:
             full.CameraManip.setLookat(eye, ctr)
             full.renderFrame(clock=f)
             ref = full.readFrame()
-            got = torch.cat(parts, 0).numpy()
+            got = torch.cat([parts[r][:edges[r + 1] - edges[r]] for r in range(world)], 0).numpy()
             ok = ok and bool((got.view(np.uint32) == ref.view(np.uint32)).all())
     ooh = torch.tensor([float(R.counters().temporal_out_of_halo)])
     dist.all_reduce(ooh)

@@ -886,16 +886,18 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloPush H) {
 }
 __global__ void k_halo_wait(const unsigned* serial, const unsigned* flag_from_up, const unsigned* flag_from_down, unsigned* error) {
   const unsigned want = *serial;
+  unsigned long long t0, now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (int side = 0; side < 2; ++side) {
     const unsigned* f = side == 0 ? flag_from_up : flag_from_down;
     if (!f) continue;
     unsigned v = 0;
-    long long spins = 0;
     for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
       if ((int)(v - want) >= 0) break;
       __nanosleep(200);
-      if (++spins > 20000000LL) { *error = 1u; break; }   // ~4 s: give up instead of hanging the GPU
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > 4000000000ull) { *error = 1u; break; }   // 4 s: give up instead of hanging the GPU (vrs_synchronize reports VRS_ERR_COMM)
     }
   }
 }
