@@ -54,6 +54,8 @@ struct vrs_ctx {
   int src_r = 0;                         // most recently written reservoir buffer inside the frame
   int last_q = 0;                        // queue set of the last frame (vrs_get_counters)
   cudaStream_t front_stream = nullptr;   // front halves run here (frames in flight)
+  cudaStream_t aux_stream = nullptr;     // the end-of-frame halo push runs here, next to the shade pass (created on first use)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_front_done[VRS_NQ] = {nullptr}, ev_back_done[VRS_NQ] = {nullptr};
   bool back_recorded[VRS_NQ] = {false, false};
   bool halo_pending = false;             // a halo push has been enqueued whose consumer-side wait has not
@@ -256,6 +258,7 @@ void vrs_destroy(vrs_ctx* ctx) {
   if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
   if (ctx->ev_halo_src) cudaEventDestroy(ctx->ev_halo_src);
   if (ctx->ev_halo_done) cudaEventDestroy(ctx->ev_halo_done);
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
   if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -599,7 +602,12 @@ static vrs_status halo_push(vrs_ctx* ctx, cudaStream_t st, bool gbuf, int g_inde
       H.down_dst_off = (size_t)(ctx->band_y1 - rows - ctx->peer_down.store_y0) * ctx->W; H.down_flag = ctx->peer_down.flags + 0;   // "written by the up neighbour"
     }
     H.serial = ctx->xflags + 2; H.block_counter = ctx->xflags + 3;
-    launch_halo_push(st, H, 64, &ctx->kt);
+    // enough blocks to keep NVLink busy: one per 2048 float4 of payload, between 64 and 4 per SM
+    size_t blocks = (H.up_count + H.down_count) * (size_t)H.nplanes / 2048;
+    const size_t max_blocks = (size_t)(ctx->persistent_blocks / 3);
+    if (blocks < 64) blocks = 64;
+    if (blocks > max_blocks) blocks = max_blocks;
+    launch_halo_push(st, H, (int)blocks, &ctx->kt);
     CK(cudaGetLastError());
     ctx->timings.launches += 1;
     ctx->halo_pending = true;
@@ -692,14 +700,26 @@ static vrs_status enqueue_back_phase(vrs_ctx* ctx, const FrameParams& F, const F
     if (multi && phase < iters && (s = halo_push(ctx, st, false, 0, ctx->src_r, sp_rows))) return s;
   } else {
     CK(mark(ctx, 3, st));
+    // What the NEXT frame's temporal reprojection may read of this frame: G-buffer + final reservoirs over every halo row
+    // (tens of MB at 4K).  Both are final here, so the push runs on a side stream next to the shade pass (fork / join, also
+    // under graph capture); its consumer-side wait is phase 0 of the next frame, i.e. it overlaps that frame's front half.
+    const bool push_t = multi && want_temporal_push;
+    const bool side = push_t && ctx->peer_mode && !ctx->kt.on;
+    if (side) {
+      if (!ctx->aux_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+      }
+      CK(cudaEventRecord(ctx->ev_fork, st)); CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+      if ((s = halo_push(ctx, ctx->aux_stream, true, fi.g, ctx->src_r, 1 << 30))) return s;
+    }
     launch_shade(st, ctx->grid, ctx->lights, F, ctx->d_params + fi.q, planes_of(ctx, fi.g), res_of(ctx, ctx->src_r), ctx->accum, ctx->band_y0,
                  ctx->band_y1, ctx->store_y0, &ctx->kt);                                             // main.cpp:416-433
     CK(cudaGetLastError());
     ctx->timings.launches += 1;
     CK(mark(ctx, 4, st));
-    // what the NEXT frame's temporal reprojection may read of this frame: G-buffer + final reservoirs over every halo row.
-    // It is joined by phase 0 of the next frame, i.e. it overlaps that frame's front half.
-    if (multi && want_temporal_push && (s = halo_push(ctx, st, true, fi.g, ctx->src_r, 1 << 30))) return s;
+    if (side) { CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream)); CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); }
+    else if (push_t && (s = halo_push(ctx, st, true, fi.g, ctx->src_r, 1 << 30))) return s;
   }
   return VRS_OK;
 }

@@ -487,10 +487,14 @@ struct Ray {
     tau = tau - seg;
     t = tcell;
     if (last) return RAY_DONE;
-    bool out;                                                // leave the cell along `axis`
-    if (axis == 0)      { c[0] += sgn[0]; cell += sgn[0];                           tn[0] = tn[0] + dt[0]; out = (unsigned)c[0] >= (unsigned)G.cdim[0]; }
-    else if (axis == 1) { c[1] += sgn[1]; cell += sgn[1] * G.cdim[0];               tn[1] = tn[1] + dt[1]; out = (unsigned)c[1] >= (unsigned)G.cdim[1]; }
-    else                { c[2] += sgn[2]; cell += sgn[2] * (G.cdim[0] * G.cdim[1]); tn[2] = tn[2] + dt[2]; out = (unsigned)c[2] >= (unsigned)G.cdim[2]; }
+    // leave the cell along `axis`, branch-free: lanes of a warp leave along different axes, and a three-way branch would run
+    // its arms one after the other with a third of the lanes each (ncu: 1.7 - 5.7 lanes per instruction in those arms)
+    const int m0 = -(int)(axis == 0), m1 = -(int)(axis == 1), m2 = -(int)(axis == 2);
+    c[0] += sgn[0] & m0; c[1] += sgn[1] & m1; c[2] += sgn[2] & m2;
+    cell += (sgn[0] & m0) + ((sgn[1] * G.cdim[0]) & m1) + ((sgn[2] * (G.cdim[0] * G.cdim[1])) & m2);
+    const float n0 = tn[0] + dt[0], n1 = tn[1] + dt[1], n2 = tn[2] + dt[2];
+    tn[0] = axis == 0 ? n0 : tn[0]; tn[1] = axis == 1 ? n1 : tn[1]; tn[2] = axis == 2 ? n2 : tn[2];
+    const bool out = (unsigned)c[0] >= (unsigned)G.cdim[0] || (unsigned)c[1] >= (unsigned)G.cdim[1] || (unsigned)c[2] >= (unsigned)G.cdim[2];   // only the coordinate that moved can have left the window
     return out ? RAY_DONE : RAY_SKIP;
   }
 
@@ -508,8 +512,11 @@ struct Ray {
       float u2 = rnd(seed);
       if (u2 * mu_d < dens) { hit = true; vox[0] = vx; vox[1] = vy; vox[2] = vz; return false; }
     } else {
-      T = T * (1.0f - dens / mu_d);
-      if (!(T > 1e-5f)) { T = 0.0f; return false; }          // opaque for every practical purpose: stop marching
+      // (dens = 0: 0 / mu_d = 0, T * 1 = T, nothing changes — and a zero numerator would send the IEEE division to its slow path)
+      if (dens != 0.0f) {
+        T = T * (1.0f - dens / mu_d);
+        if (!(T > 1e-5f)) { T = 0.0f; return false; }        // opaque for every practical purpose: stop marching
+      }
     }
     tau = neglog1m(rnd(seed));
     return true;

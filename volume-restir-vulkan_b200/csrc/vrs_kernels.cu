@@ -51,7 +51,7 @@ __device__ __forceinline__ void primary_ray(const FrameParams& F, int x, int y, 
 // bounding rectangle touches are marked.  A primary ray can only collide inside a non-empty cell, so a pixel in an
 // unmarked tile is a miss without marching: k_classify does not queue it.  Cells that reach behind the eye, or that
 // would cover a large part of the screen (camera inside the volume), switch the mask off for the frame instead.
-__global__ void __launch_bounds__(128) k_cover(const GridDev G, const FrameParams* __restrict__ Fp, Queues Q, int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(128) k_cover(const GridDev G, const FrameParams* __restrict__ Fp, Queues Q, int tiles_x, int tiles_y, int band_ty0, int band_ty1) {
   const FrameParams& F = *Fp;
   // 8 lanes per cell: lane k projects corner k, the bounding rectangle is reduced with shuffles, the lanes share the tile loop
   const int ncell = G.cdim[0] * G.cdim[1] * G.cdim[2];
@@ -83,8 +83,13 @@ __global__ void __launch_bounds__(128) k_cover(const GridDev G, const FrameParam
   if (bad) { if (k == 0) Q.counters[Q_COVER_ALL] = 1u; return; }
   minx = floorf(minx) - 2.0f; miny = floorf(miny) - 2.0f; maxx = ceilf(maxx) + 2.0f; maxy = ceilf(maxy) + 2.0f;
   if (maxx < 0.0f || maxy < 0.0f || minx > float(F.W - 1) || miny > float(F.H - 1)) return;                       // off screen
-  const int tx0 = (int)fmaxf(minx, 0.0f) / COVER_TILE, ty0 = (int)fmaxf(miny, 0.0f) / COVER_TILE;
-  const int tx1 = (int)fminf(maxx, float(F.W - 1)) / COVER_TILE, ty1 = (int)fminf(maxy, float(F.H - 1)) / COVER_TILE;
+  const int tx0 = (int)fmaxf(minx, 0.0f) / COVER_TILE;
+  int ty0 = (int)fmaxf(miny, 0.0f) / COVER_TILE;
+  const int tx1 = (int)fminf(maxx, float(F.W - 1)) / COVER_TILE;
+  int ty1 = (int)fminf(maxy, float(F.H - 1)) / COVER_TILE;
+  if (ty0 < band_ty0) ty0 = band_ty0;                         // only the tile rows of this context's band are ever tested (k_classify)
+  if (ty1 > band_ty1) ty1 = band_ty1;
+  if (ty1 < ty0) return;
   const int nx = tx1 - tx0 + 1, ny = ty1 - ty0 + 1;
   if ((long long)nx * ny > 4096) { if (k == 0) Q.counters[Q_COVER_ALL] = 1u; return; }
   for (int i = k; i < nx * ny; i += 8) {
@@ -287,13 +292,18 @@ __global__ void __launch_bounds__(128, MINB) k_ris_thread(const GridDev G, const
         // candidate, (sumW + weight) / (M * pHat), only survives for the selected one: remember its sumW and M and do
         // that division once after the loop (same operands, same result).
         const float pHat = evaluatePHat(L, sel, gi, pre);
-        const float weight = pHat / pdf;
         res.M += 1;
-        res.sumWeights += weight;
-        const float replacePossibility = weight / res.sumWeights;
-        if (rnd(seed) < replacePossibility) {
-          res.lightIndex = sel; res.lightKind = 0; res.pHat = pHat; res.sampleSeed = sampleSeed;
-          selM = res.M; selSumW = res.sumWeights;
+        const float u = rnd(seed);
+        // pHat = 0 (light behind the surface) with a positive pdf: weight = 0 / pdf = 0, the sum does not move and nothing can be
+        // selected — same bits as the divisions, which would take div.rn's slow path for the zero numerator
+        if (!(pHat == 0.0f && pdf > 0.0f)) {
+          const float weight = pHat / pdf;
+          res.sumWeights += weight;
+          const float replacePossibility = weight / res.sumWeights;
+          if (u < replacePossibility) {
+            res.lightIndex = sel; res.lightKind = 0; res.pHat = pHat; res.sampleSeed = sampleSeed;
+            selM = res.M; selSumW = res.sumWeights;
+          }
         }
       }
       if (selM != 0u) res.w = selSumW / (float(selM) * res.pHat);                                      // reservoir.glsl:51
@@ -335,9 +345,6 @@ __global__ void __launch_bounds__(128, 6) k_ris_coop(const GridDev G, const Ligh
   const uint32_t nwarps = gridDim.x * 4u, warp = blockIdx.x * 4u + (threadIdx.x >> 5);
   const uint32_t gsz = group_size_for(nhit, nwarps, (uint32_t)target_warps, 32u);
   const uint32_t M = F.M;
-  // LCG jump by 3 * lane draws: state' = jA * state + jC
-  uint32_t jA = 1u, jC = 0u;
-  for (int i = 0; i < 3 * lane; ++i) { jA = jA * 1664525u; jC = jC * 1664525u + 1013904223u; }
   const float pre_a = gmax(0.001f, G.roughness * G.roughness);                     // disneyBRDF.glsl:53 (roughness is per grid)
 
   for (uint32_t g0 = warp * gsz; g0 < nhit; g0 += nwarps * gsz) {
@@ -347,10 +354,12 @@ __global__ void __launch_bounds__(128, 6) k_ris_coop(const GridDev G, const Ligh
     // ---------------- step 1: lane = pixel
     uint32_t idx = 0, vcode = 0, seed = 0;
     bool valid = false;
+    V3 Ppix = v3(0.f, 0.f, 0.f), Npix = v3(0.f, 0.f, 0.f);
     if (pix) {
       GInfo gi;
       ris_hit_setup(G, F, cur, Q, s, store_y0, idx, vcode, seed, gi);
       const V3 P = gi.worldPos, n = gi.normal;
+      Ppix = P; Npix = n;
       valid = dot(gi.normal, gi.normal) != 0.0f;                                                       // :205
       const ShadePre pre = shade_pre(gi);
       sm.P[0][lane] = P.x; sm.P[1][lane] = P.y; sm.P[2][lane] = P.z;
@@ -360,57 +369,55 @@ __global__ void __launch_bounds__(128, 6) k_ris_coop(const GridDev G, const Ligh
       sm.albedoLum[lane] = gi.albedoLum;
       sm.seed0[lane] = seed;
     }
-    const unsigned vmask = __ballot_sync(full, valid);
     __syncwarp();
 
     float sumW = 0.0f, sel_sumW = 0.0f;
     uint32_t selc = 0xFFFFFFFFu, sel_seed = 0u;
     for (uint32_t c0 = 0; c0 < M; c0 += 32u) {
-      const bool cact = c0 + (uint32_t)lane < M;
+      const uint32_t cn = M - c0 < 32u ? M - c0 : 32u;
       uint32_t head = 0u, tail = 0u;
-      unsigned rem = vmask;
-      // Phase A is a three-stage software pipeline over the pixels of the group, so that the two dependent L2 fetches of
-      // a candidate (alias cell -> light) are in flight while the warp works on the pixels before it:
-      //   stage 1 draws r1, r2 of pixel pN and requests its alias cells      (consumed one iteration later)
-      //   stage 2 picks the light of pixel pA and requests it                (consumed one iteration later)
-      //   stage 3 culls the candidates of pixel pL behind the surface and appends the others to the phase-B list
-      int pA = -1, pL = -1;
+      uint32_t zero_mask = 0u;                         // candidates of this lane's pixel whose weight is exactly 0 (light behind the surface)
+      // Phase A, lane = pixel: every lane walks the candidates of its own pixel (own RNG stream, own P and n in registers) as a
+      // three-stage software pipeline, so that the two dependent table fetches of a candidate (alias cell -> light) are in flight
+      // while the lane works on the candidates before it:
+      //   stage 1 draws r1, r2 of candidate `it` and requests its alias cell       (consumed one iteration later)
+      //   stage 2 picks the light of candidate `it - 1` and requests it            (consumed one iteration later)
+      //   stage 3 culls candidate `it - 2` when the light is behind the surface, else appends it to the phase-B list
+      uint32_t sA = seed;                              // runs ahead of `seed`, which step 3 advances
       uint32_t colA = 0u; float r2A = 0.0f, pdfL = 0.0f, lewL = 0.0f;
       float4 cellA = make_float4(0.f, 0.f, 0.f, 0.f), lpL = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (;;) {
-        int pN2 = pA; uint32_t selN = 0u; float pdfN = 0.0f, lewN = 0.0f; float4 lpN = lpL;
-        if (pA >= 0) {                                                                                 // stage 2
+      for (uint32_t it = 0; it < cn + 2u; ++it) {
+        uint32_t selN = 0u; float pdfN = 0.0f, lewN = 0.0f; float4 lpN = lpL;
+        if (it >= 1u && it <= cn) {                                                                    // stage 2
           aliasPick(cellA, colA, r2A, selN, pdfN);
           lpN = __ldg(&L.lights[2 * selN]);
           lewN = __ldg(reinterpret_cast<const float*>(L.lights) + 8 * (size_t)selN + 7);
         }
-        int pN1 = -1; uint32_t colN = 0u; float r2N = 0.0f; float4 cellN = cellA;
-        if (rem) {                                                                                     // stage 1
-          pN1 = __ffs(rem) - 1; rem &= rem - 1u;
-          uint32_t st = jA * sm.seed0[pN1] + jC;
-          const float r1 = rnd(st); r2N = rnd(st);                                                     // :116, GLSL left-to-right
+        uint32_t colN = 0u; float r2N = 0.0f; float4 cellN = cellA;
+        if (it < cn) {                                                                                 // stage 1
+          const float r1 = rnd(sA); r2N = rnd(sA);                                                     // :116, GLSL left-to-right
+          lcg(sA);                                                                                     // the selection draw of updateReservoir
           colN = aliasColumn(L, r1);
           cellN = __ldg(&L.alias[colN]);
         }
-        if (pL >= 0) {                                                                                 // stage 3
-          const int p = pL;
-          const V3 wi = sub(v3(lpL.x, lpL.y, lpL.z), v3(sm.P[0][p], sm.P[1][p], sm.P[2][p]));          // restirUtils.glsl:41-44
-          const bool back = dot(wi, v3(sm.n[0][p], sm.n[1][p], sm.n[2][p])) < 0.0f;
-          if (cact && back) {                                                                          // pHat = 0 -> weight = 0 / pdf
-            float wz = 0.0f;
-            if (!(pdfL > 0.0f)) wz = 0.0f / pdfL;
-            sm.w[p * 33 + lane] = wz;
+        if (it >= 2u) {                                                                                // stage 3
+          const uint32_t cc = it - 2u;
+          const V3 wi = sub(v3(lpL.x, lpL.y, lpL.z), Ppix);                                            // restirUtils.glsl:41-44
+          const bool back = dot(wi, Npix) < 0.0f;
+          if (valid && back) {                                                                         // pHat = 0 -> weight = 0 / pdf
+            if (pdfL > 0.0f) zero_mask |= 1u << cc;
+            else sm.w[lane * 33 + (int)cc] = 0.0f / pdfL;
           }
-          const bool keep = cact && !back;
+          const bool keep = valid && !back;
           const unsigned m = __ballot_sync(full, keep);
           if (keep) {
             const uint32_t e = (tail + (uint32_t)__popc(m & lt_mask)) & 63u;
-            sm.l_pc[e] = ((uint32_t)p << 8) | (uint32_t)lane; sm.l_pdf[e] = pdfL;
+            sm.l_pc[e] = ((uint32_t)lane << 8) | cc; sm.l_pdf[e] = pdfL;
             sm.l_lp[0][e] = lpL.x; sm.l_lp[1][e] = lpL.y; sm.l_lp[2][e] = lpL.z; sm.l_lew[e] = lewL;
           }
           tail += (uint32_t)__popc(m);
         }
-        const bool flush = pN1 < 0 && pN2 < 0;
+        const bool flush = it == cn + 1u;
         __syncwarp();
         while (tail - head >= 32u || (flush && tail != head)) {
           // ---------------- phase B: lane = work-list entry (no global loads: the light travels in the list)
@@ -433,22 +440,26 @@ __global__ void __launch_bounds__(128, 6) k_ris_coop(const GridDev G, const Ligh
           head += cnt;
           __syncwarp();
         }
-        if (flush) break;
-        pL = pN2; pdfL = pdfN; lpL = lpN; lewL = lewN;
-        pA = pN1; colA = colN; r2A = r2N; cellA = cellN;
+        pdfL = pdfN; lpL = lpN; lewL = lewN;
+        colA = colN; r2A = r2N; cellA = cellN;
       }
       // ---------------- step 3: lane = pixel, the serial part of updateReservoir (reservoir.glsl:30-43) for this chunk
       if (valid) {
-        const uint32_t cn = M - c0 < 32u ? M - c0 : 32u;
         for (uint32_t cc = 0; cc < cn; ++cc) {
           const uint32_t sb = seed;                                                                    // gi.sampleSeed (:213)
           lcg(seed); lcg(seed);
+          const float u = rnd(seed);
+          // A zero weight (three quarters of the candidates on the bunny: light behind the surface) changes nothing: sumW + 0 = sumW
+          // and rnd < 0 / sumW is false (also for 0 / 0 = NaN); only the draw is consumed.  Skipping the division there matters:
+          // a zero numerator takes div.rn's slow path (ncu: 15 % of this kernel's instructions were that subroutine).
+          if ((zero_mask >> cc) & 1u) continue;
           const float wt = sm.w[lane * 33 + (int)cc];
-          sumW += wt;
-          const float replacePossibility = wt / sumW;
-          if (rnd(seed) < replacePossibility) { selc = c0 + cc; sel_seed = sb; sel_sumW = sumW; }
+          if (wt != 0.0f) {
+            sumW += wt;
+            const float replacePossibility = wt / sumW;
+            if (u < replacePossibility) { selc = c0 + cc; sel_seed = sb; sel_sumW = sumW; }
+          }
         }
-        sm.seed0[lane] = seed;
       }
       __syncwarp();
     }
@@ -979,8 +990,9 @@ void launch_initial_front(cudaStream_t st, const GridDev& G, const LightsDev& L,
   if (F.cull && !trace && !no_cull && Q.cover && ncell <= (1ll << 27)) {          // (8 threads per cell in a 32-bit grid index)
     tiles_x = ((int)F.W + COVER_TILE - 1) / COVER_TILE;
     const int tiles_y = ((int)F.H + COVER_TILE - 1) / COVER_TILE;
-    cudaMemsetAsync(Q.cover, 0, (size_t)tiles_x * tiles_y, st);
-    k_cover<<<(unsigned)((ncell * 8 + 127) / 128), 128, 0, st>>>(G, dF, Q, tiles_x, tiles_y);
+    const int band_ty0 = y0 / COVER_TILE, band_ty1 = (y1 - 1) / COVER_TILE;
+    cudaMemsetAsync(Q.cover + (size_t)band_ty0 * tiles_x, 0, (size_t)tiles_x * (band_ty1 - band_ty0 + 1), st);
+    k_cover<<<(unsigned)((ncell * 8 + 127) / 128), 128, 0, st>>>(G, dF, Q, tiles_x, tiles_y, band_ty0, band_ty1);
     ktick(kt, st, "k_cover");
   }
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
