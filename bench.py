@@ -428,16 +428,22 @@ def run_ours(args):
 
     # ---- per-kernel event times (frames launched kernel by kernel, one event after each kernel on the context stream)
     kernel_ms = {}
-    if world == 1:
-        R.setKernelTiming(True)
-        extend_inputs(14)
-        for i in range(14):
-            step()
-            if i >= 2:
-                for name, ms in R.kernelTimes():
-                    kernel_ms[name] = kernel_ms.get(name, 0.0) + ms / 12.0
-        R.setKernelTiming(False)
-        barrier()
+    R.setKernelTiming(True)
+    extend_inputs(14)
+    barrier()
+    for i in range(14):
+        step()
+        if i >= 2:
+            for name, ms in R.kernelTimes():
+                kernel_ms[name] = kernel_ms.get(name, 0.0) + ms / 12.0
+    R.setKernelTiming(False)
+    barrier()
+    kernel_ms_ranks = None
+    if dist is not None:            # per rank: k_halo_wait is the time a band waits for its neighbours (skew), k_halo_push the transfer
+        allk = [None] * world
+        dist.all_gather_object(allk, kernel_ms)
+        kernel_ms_ranks = {n_: [round(k_.get(n_, 0.0), 5) for k_ in allk] for n_ in kernel_ms}
+        kernel_ms = {n_: max(v_) for n_, v_ in kernel_ms_ranks.items()}
 
     # ---- end to end through the public API: host uniforms in, host frame buffer out, every step.
     # The result a caller of the reference gets per frame is the presented 8-bit image (restir_post.frag:104 ->
@@ -517,7 +523,7 @@ def run_ours(args):
                 e["dram_bytes_per_launch"] = tk.get("dram_bytes_per_launch")
                 e["dram_gbs"] = round(tk["dram_bytes_per_launch"] * tk.get("launches_per_frame", 1) / (ms * 1e-3) / 1e9, 1)
             per_kernel[name] = e
-        if kernel_ms:
+        if kernel_ms and world == 1:
             dom = max((n_ for n_ in kernel_ms if n_ in KERNEL_BYTES_PER_PX), key=lambda n_: kernel_ms[n_])
             nl = wl["iters"] if dom == "k_spatial" else 1
             dom_ms = kernel_ms[dom] / nl
@@ -555,6 +561,7 @@ def run_ours(args):
             "temporal_out_of_halo": int(ooh),
             "gpu_launches": int(launches * args.steps * len(reps)), "clocks": clocks, "wall_s": round(t_wall, 3),
             "per_rank_initial_ms": per_rank_initial if world > 1 else None,
+            "per_rank_kernel_ms": kernel_ms_ranks,
             "issue_roofline": issue_roofline(traffic, fps, clocks, world),
         }
         if not args.no_cpu_baseline and world == 1:
