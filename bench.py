@@ -213,13 +213,13 @@ def split_rows(cost, world, min_rows=32):
     return [(edges[r], edges[r + 1]) for r in range(world)]
 
 
-def calibrated_bands(V, wl, path, world, rank, device, dist, halo, rounds=3, frames=12):
+def calibrated_bands(V, wl, path, world, rank, device, dist, halo, min_rows, rounds=3, frames=12):
     """Start from the hit-count model, then correct it with measurements: every rank renders its band (no exchange, timing
     only) for a few frames, the per-band times are all-gathered and turned into a per-band correction of the row costs.
     Which rows a rank renders never changes a pixel (tests/test_gpu_multi.py); only the load balance does."""
     import torch
     cost = balanced_bands(V, wl, path, world, device)
-    bands = split_rows(cost, world, halo)
+    bands = split_rows(cost, world, min_rows)
     for _ in range(rounds):
         band = bands[rank]
         R = V.Renderer(wl["W"], wl["H"], spatial_iterations=wl["iters"], band=band, halo_rows=halo, device=device)
@@ -247,7 +247,7 @@ def calibrated_bands(V, wl, path, world, rank, device, dist, halo, rounds=3, fra
         corr = corr / corr.mean()
         for (y0, y1), c in zip(bands, corr):
             cost[y0:y1] *= 0.5 * (1.0 + c)                                               # damped
-        bands = split_rows(cost, world, halo)
+        bands = split_rows(cost, world, min_rows)
     return bands
 
 
@@ -301,7 +301,7 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()       # the stand-in asset (if any) is on disk for every rank
         path = asset_path(V, wl["asset"])
-    halo = 32
+    halo, reach = 32, 32
     if world > 1:
         P = V.Renderer(16, 16, spatial_iterations=0, device=local)
         P.loadVDB(path)
@@ -309,8 +309,12 @@ def run_ours(args):
         lo, hi = list(gi.world_bbox_min), list(gi.world_bbox_max)
         _, ctr0, diag0 = scene_lights(lambda *a: None, dict(wl, lights=1), lo, hi, None)
         P.destroy()
-        halo = temporal_halo_rows(V, wl, lo, hi, ctr0, diag0) if wl["flags"] & 2 else 32
-    bands = calibrated_bands(V, wl, path, world, rank, local, dist, halo) if world > 1 else [(0, H)]
+        # rows the temporal reprojection can move on this orbit.  Peer memory: such pixels are read in place from the adjacent
+        # band (which therefore must be at least that tall), halo rows only serve spatial reuse (radius 30).  NCCL: they must
+        # be shipped, the halo is that tall.
+        reach = temporal_halo_rows(V, wl, lo, hi, ctr0, diag0) if wl["flags"] & 2 else 32
+        halo = reach if args.exchange == "nccl" else 32
+    bands = calibrated_bands(V, wl, path, world, rank, local, dist, halo, reach) if world > 1 else [(0, H)]
     band = bands[rank] if world > 1 else None
     R = V.Renderer(W, H, spatial_iterations=wl["iters"], band=band, halo_rows=halo, device=local)
     R.loadVDB(path)
@@ -542,8 +546,9 @@ def run_ours(args):
             "metric": "ReSTIR frames/s", "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_desc(wl),
             "config": config_of(wl, args.workload),
-            "partition": ("cost-balanced bands (hit-count model corrected by 3 timed calibration rounds) x%d %s, halo %d rows (sized from the orbit's reprojection distance)"
-                          % (world, [b[1] - b[0] for b in bands], halo)) if world > 1 else "single GPU",
+            "partition": ("cost-balanced bands (hit-count model corrected by 3 timed calibration rounds) x%d %s, halo %d rows, temporal reach %d rows (%s)"
+                          % (world, [b[1] - b[0] for b in bands], halo, reach,
+                             "shipped as halo rows" if args.exchange == "nccl" else "read in place from the adjacent band over NVLink")) if world > 1 else "single GPU",
             "repetitions_ms_per_step": [round(r_, 5) for r_ in reps], "timed_region_s": round(sum(reps) * args.steps / 1e3, 3),
             "mpixels_per_s": round(px * fps / 1e6, 1), "mpixel_samples_per_s": round(px * wl["M"] * fps / 1e6, 1),
             "hit_fraction": round(hit_fraction, 4), "hit_pixel_samples_per_s_M": round(hits_total * wl["M"] * fps / 1e6, 1),

@@ -33,8 +33,9 @@ def run_bands(V, name, nbands, frames, halo=None, W=None, H=None, M=None, edges=
     full = make(V, wl, path, None, 32)
     lights, ctr, diag = full._scene
     gi = full.gridInfo()
+    reach = bench.temporal_halo_rows(V, wl, list(gi.world_bbox_min), list(gi.world_bbox_max), ctr, diag, frames=frames + 1)
     if halo is None:
-        halo = bench.temporal_halo_rows(V, wl, list(gi.world_bbox_min), list(gi.world_bbox_max), ctr, diag, frames=frames + 1)
+        halo = 32          # spatial reuse only (radius 30): temporal reprojections that leave a band are read in place from the adjacent band
     if edges is None:
         edges = [round(i * wl["H"] / nbands) for i in range(nbands + 1)]
     bands = [make(V, wl, path, (edges[i], edges[i + 1]), halo, lights) for i in range(nbands)]
@@ -69,29 +70,29 @@ def run_bands(V, name, nbands, frames, halo=None, W=None, H=None, M=None, edges=
         r_.destroy()
     if check_counter:
         assert ooh == 0, "temporal reprojection left the halo rows (%d pixels) although the halo was sized from the orbit" % ooh
-    return bad, ooh, halo
+    return bad, ooh, reach
 
 
 def test_two_and_three_bands_equal_one_frame_smoke_1080p(V):
     """configs[1] at full size on the bench orbit, 2 and 3 bands (uneven edges like the cost-balanced split)."""
-    bad, _, halo = run_bands(V, "smoke_1080p_temporal", 2, 5)
+    bad, _, reach = run_bands(V, "smoke_1080p_temporal", 2, 5)
     assert not bad, bad
-    assert halo > 32                                 # the 6 deg/frame orbit reprojects further than the old fixed 32-row halo
+    assert reach > 32                                # the 6 deg/frame orbit reprojects further than the 32-row halo: those pixels come from the neighbour's band
     bad, _, _ = run_bands(V, "smoke_1080p_full", 3, 4, edges=[0, 420, 640, 1080])
     assert not bad, bad
 
 
 def test_two_bands_equal_one_frame_bunny_4k(V):
     """configs[3] (bench default) at 3840x2160 with 10k lights, full spatiotemporal, 2 bands, 3 frames of the bench orbit."""
-    bad, _, halo = run_bands(V, "bunny_4k_full", 2, 3)
+    bad, _, reach = run_bands(V, "bunny_4k_full", 2, 3)
     assert not bad, bad
-    assert halo >= 64
+    assert reach >= 64
 
 
 def test_small_halo_is_detected_not_silent(V):
-    """A halo smaller than the orbit's reprojection distance drops temporal merges: the counter must say so."""
-    # (vertical reprojection grows with the distance from the image centre row: split where it is large)
-    bad, ooh, _ = run_bands(V, "smoke_1080p_temporal", 3, 4, halo=8, check_counter=False, edges=[0, 300, 800, 1080])
+    """A band thinner than the orbit's reprojection distance: some previous-frame pixels lie two bands away, where nobody
+    can supply them; those merges are dropped and the counter must say so."""
+    bad, ooh, _ = run_bands(V, "smoke_1080p_temporal", 3, 4, halo=8, check_counter=False, edges=[0, 700, 708, 1080])
     assert ooh > 0, (ooh, bad)
 
 

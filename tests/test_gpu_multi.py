@@ -106,7 +106,8 @@ def bench_worker(rank, world, port, name, frames, out_dir, mode):
     full, ctr, diag = make(None, rank, 32) if rank == 0 else (None, None, None)
     probe, ctr, diag = make((0, 64), rank, 0)
     gi = probe.gridInfo()
-    halo = bench.temporal_halo_rows(V, wl, list(gi.world_bbox_min), list(gi.world_bbox_max), ctr, diag, frames=frames + 1)
+    reach = bench.temporal_halo_rows(V, wl, list(gi.world_bbox_min), list(gi.world_bbox_max), ctr, diag, frames=frames + 1)
+    halo = reach if mode == "nccl" else 32          # peer memory reads reprojected pixels in place from the adjacent band
     probe.destroy()
     edges = [0, int(H * 0.46), H] if world == 2 else [round(i * H / world) for i in range(world + 1)]     # uneven, like the cost-balanced split
     band = (edges[rank], edges[rank + 1])

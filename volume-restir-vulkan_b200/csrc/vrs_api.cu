@@ -25,11 +25,14 @@ using namespace vrs;
 // Frames in flight (the reference keeps 2-3 swapchain images in flight, nvvk/appbase_vk.cpp:412-418): the front half of
 // frame n+1 (coverage, classification, primary event, RIS, shadow rays: nothing in it reads the previous frame) runs on its
 // own stream while the back half of frame n (temporal merge, spatial reuse, shade, halo exchanges) is still executing.
-// Buffers are sized for that: 3 G-buffers (frame n writes n % 3 and reads (n - 1) % 3 as "previous"), 3 pairs of reservoir
-// buffers (frame n ping-pongs inside pair n % 3 and reads the final one of frame n - 1), 2 sets of work queues and 2 device
+// Buffers are sized for that: 4 G-buffers (frame n writes n % 4 and reads (n - 1) % 4 as "previous"), 4 pairs of reservoir
+// buffers (frame n ping-pongs inside pair n % 4 and reads the final one of frame n - 1), 2 sets of work queues and 2 device
 // parameter blocks (n % 2).  front(n) waits for back(n - 2), back(n) for front(n) and, by stream order, back(n - 1).
-#define VRS_NG 3
-#define VRS_NR 6
+// (Three of each would do for one GPU.  The fourth covers several GPUs: a neighbour reads this context's frame n - 1 planes in
+// place during ITS temporal pass of frame n, and this context's front(n + 3) — the first writer of those planes with four
+// buffers — cannot start before its back(n + 1), whose first phase waits for the flag that neighbour publishes after that pass.)
+#define VRS_NG 4
+#define VRS_NR 8
 #define VRS_NQ 2
 struct GraphEntry { cudaGraphExec_t exec = nullptr; uint32_t launches = 0; };
 struct FrameIdx { int g = 0, gprev = 0, ra = 0, rb = 0, q = 0; };
@@ -54,8 +57,6 @@ struct vrs_ctx {
   int src_r = 0;                         // most recently written reservoir buffer inside the frame
   int last_q = 0;                        // queue set of the last frame (vrs_get_counters)
   cudaStream_t front_stream = nullptr;   // front halves run here (frames in flight)
-  cudaStream_t aux_stream = nullptr;     // the end-of-frame halo push runs here, next to the shade pass (created on first use)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_front_done[VRS_NQ] = {nullptr}, ev_back_done[VRS_NQ] = {nullptr};
   bool back_recorded[VRS_NQ] = {false, false};
   bool halo_pending = false;             // a halo push has been enqueued whose consumer-side wait has not
@@ -258,7 +259,6 @@ void vrs_destroy(vrs_ctx* ctx) {
   if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
   if (ctx->ev_halo_src) cudaEventDestroy(ctx->ev_halo_src);
   if (ctx->ev_halo_done) cudaEventDestroy(ctx->ev_halo_done);
-  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); }
   if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -572,7 +572,7 @@ static vrs_status upload_params(vrs_ctx* ctx, const FrameParams& F, int q, cudaS
 static FrameIdx frame_idx(uint64_t n) {
   FrameIdx f;
   f.g = (int)(n % VRS_NG); f.gprev = (int)((n + VRS_NG - 1) % VRS_NG);
-  f.ra = 2 * (int)(n % 3); f.rb = f.ra + 1;
+  f.ra = 2 * (int)(n % (VRS_NR / 2)); f.rb = f.ra + 1;
   f.q = (int)(n % VRS_NQ);
   return f;
 }
@@ -583,6 +583,7 @@ static FrameIdx frame_idx(uint64_t n) {
 // halo row the neighbour stores.
 static vrs_status halo_push(vrs_ctx* ctx, cudaStream_t st, bool gbuf, int g_index, int r_index, int max_rows) {
   if (ctx->peer_mode) {
+    // (gbuf = false and r_index < 0: no payload, the kernel only publishes the serial — "my planes of this frame are final")
     // one kernel stores the boundary rows into both neighbours' halo rows (NVLink P2P / same-device stores) and publishes the serial
     HaloPush H; memset(&H, 0, sizeof(H));
     auto add = [&](float4* mine, float4* up, float4* down) { H.src[H.nplanes] = mine; H.up_dst[H.nplanes] = up; H.down_dst[H.nplanes] = down; H.nplanes++; };
@@ -687,8 +688,22 @@ static vrs_status enqueue_back_phase(vrs_ctx* ctx, const FrameParams& F, const F
     const bool needs_finish = (F.flags & (VRS_RESTIR_VISIBILITY_REUSE_FLAG | VRS_RESTIR_TEMPORAL_REUSE_FLAG)) != 0;
     // the previous frame's G-buffer + final reservoir halo rows (pushed at the end of that frame) are read by the temporal merge
     if ((s = halo_wait(ctx, st))) return s;
+    PrevAccess PA; memset(&PA, 0, sizeof(PA));
+    if (ctx->peer_mode) {
+      // peer memory: a reprojection that leaves this band reads the neighbour's planes of the previous frame in place
+      PA.own_y0 = ctx->band_y0; PA.own_y1 = ctx->band_y1;
+      auto peer_planes = [&](const vrs_ctx::Peer& P, Planes& pl, ResPlanes& rp) {
+        pl.worldPos = P.g[fi.gprev][0]; pl.albedo = P.g[fi.gprev][1]; pl.normal = P.g[fi.gprev][2]; pl.mat = P.g[fi.gprev][3];
+        rp.info = P.r[ctx->final_r][0]; rp.weight = P.r[ctx->final_r][1];
+      };
+      if (ctx->peer_up.present) { peer_planes(ctx->peer_up, PA.up, PA.upR); PA.up_y0 = ctx->peer_up.band_y0; PA.up_row0 = ctx->peer_up.store_y0; }
+      if (ctx->peer_down.present) { peer_planes(ctx->peer_down, PA.down, PA.downR); PA.down_y1 = ctx->peer_down.band_y1; PA.down_row0 = ctx->peer_down.store_y0; }
+    } else {
+      // one GPU: every row; NCCL: the halo rows were shipped at the end of the previous frame
+      PA.own_y0 = ctx->store_y0; PA.own_y1 = ctx->store_y1;
+    }
     launch_initial_finish(st, ctx->lights, F, ctx->d_params + fi.q, planes_of(ctx, fi.g), planes_of(ctx, fi.gprev), res_of(ctx, ctx->final_r), res_of(ctx, fi.ra),
-                          ctx->queues[fi.q], ctx->trace, ctx->store_y0, ctx->store_y1, ctx->xflags + 5, &ctx->kt);   // main.cpp:405-409
+                          ctx->queues[fi.q], ctx->trace, ctx->store_y0, PA, ctx->xflags + 5, &ctx->kt);   // main.cpp:405-409
     CK(cudaGetLastError());
     if (needs_finish) ctx->timings.launches += 1;
     CK(mark(ctx, 1, st));
@@ -700,26 +715,18 @@ static vrs_status enqueue_back_phase(vrs_ctx* ctx, const FrameParams& F, const F
     if (multi && phase < iters && (s = halo_push(ctx, st, false, 0, ctx->src_r, sp_rows))) return s;
   } else {
     CK(mark(ctx, 3, st));
-    // What the NEXT frame's temporal reprojection may read of this frame: G-buffer + final reservoirs over every halo row
-    // (tens of MB at 4K).  Both are final here, so the push runs on a side stream next to the shade pass (fork / join, also
-    // under graph capture); its consumer-side wait is phase 0 of the next frame, i.e. it overlaps that frame's front half.
+    // What the NEXT frame's temporal pass reads of this frame.  Peer memory: neighbours read this band's planes in place, so only
+    // a flag travels ("this frame's G-buffer and final reservoirs are complete; my own temporal pass no longer reads yours of
+    // the frame before") — it is published before the shade pass, which touches neither.  NCCL: the G-buffer + final reservoirs
+    // of every halo row are shipped.  Either way the consumer-side wait is phase 0 of the next frame.
     const bool push_t = multi && want_temporal_push;
-    const bool side = push_t && ctx->peer_mode && !ctx->kt.on;
-    if (side) {
-      if (!ctx->aux_stream) {
-        CK(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-      }
-      CK(cudaEventRecord(ctx->ev_fork, st)); CK(cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
-      if ((s = halo_push(ctx, ctx->aux_stream, true, fi.g, ctx->src_r, 1 << 30))) return s;
-    }
+    if (push_t && ctx->peer_mode && (s = halo_push(ctx, st, false, 0, -1, 0))) return s;
     launch_shade(st, ctx->grid, ctx->lights, F, ctx->d_params + fi.q, planes_of(ctx, fi.g), res_of(ctx, ctx->src_r), ctx->accum, ctx->band_y0,
                  ctx->band_y1, ctx->store_y0, &ctx->kt);                                             // main.cpp:416-433
     CK(cudaGetLastError());
     ctx->timings.launches += 1;
     CK(mark(ctx, 4, st));
-    if (side) { CK(cudaEventRecord(ctx->ev_join, ctx->aux_stream)); CK(cudaStreamWaitEvent(st, ctx->ev_join, 0)); }
-    else if (push_t && (s = halo_push(ctx, st, true, fi.g, ctx->src_r, 1 << 30))) return s;
+    if (push_t && !ctx->peer_mode && (s = halo_push(ctx, st, true, fi.g, ctx->src_r, 1 << 30))) return s;
   }
   return VRS_OK;
 }
@@ -732,10 +739,10 @@ static void finish_frame_state(vrs_ctx* ctx, const FrameIdx& fi) {
   ctx->history_valid = true;
 }
 
-// Graph cache: the launch sequence of a frame half depends only on the buffer rotation (frame_no % 6), on where the previous
+// Graph cache: the launch sequence of a frame half depends only on the buffer rotation (frame_no % 4), on where the previous
 // frame left its final reservoirs, on the structural flags and on whether a halo push is pending.
 static uint64_t graph_key(vrs_ctx* ctx, const FrameParams& F, int half, bool want_temporal_push) {
-  uint64_t k = (uint64_t)(ctx->frame_no % 6) | ((uint64_t)(F.flags & 0x3f) << 6) | ((uint64_t)ctx->cfg.spatial_iterations << 12) |
+  uint64_t k = (uint64_t)(ctx->frame_no % 4) | ((uint64_t)(F.flags & 0x3f) << 6) | ((uint64_t)ctx->cfg.spatial_iterations << 12) |
                ((uint64_t)(F.cull ? 1 : 0) << 16) | ((uint64_t)(ctx->pass_timing ? 1 : 0) << 17) | ((uint64_t)half << 19);
   if (half == 1) k |= ((uint64_t)ctx->final_r << 3) | ((uint64_t)(ctx->peer_mode ? 1 : 0) << 15) | ((uint64_t)(ctx->halo_pending ? 1 : 0) << 18) |
                       ((uint64_t)(want_temporal_push ? 1 : 0) << 20);
@@ -1018,7 +1025,7 @@ vrs_status vrs_write_image(vrs_ctx* ctx, const char* path) {
 }
 
 // ------------------------------------------------------------------------------------------ multi-GPU
-// ---- peer-memory exchange set-up: blob = { band_y0, band_y1, store_y0, store_y1 (int32) | 25 x cudaIpcMemHandle_t }
+// ---- peer-memory exchange set-up: blob = { band_y0, band_y1, store_y0, store_y1 (int32) | 33 x cudaIpcMemHandle_t }
 vrs_status vrs_peer_export(vrs_ctx* ctx, uint8_t blob[VRS_PEER_BLOB_BYTES]) {
   if (!ctx || !blob) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);

@@ -59,6 +59,16 @@ struct Planes {                   // band-local RGBA32F planes (reference layout
 };
 struct ResPlanes { float4* info; float4* weight; };
 
+// Where the temporal pass finds the previous frame's pixel of image row fy: rows [own_y0, own_y1) in this context's own
+// planes; with peer memory, rows [up_y0, own_y0) in the up neighbour's planes (its first stored row is up_row0) and rows
+// [own_y1, down_y1) in the down neighbour's.  Null plane pointers = no neighbour on that side.
+struct PrevAccess {
+  int own_y0, own_y1;
+  Planes up, down;
+  ResPlanes upR, downR;
+  int up_y0, up_row0, down_y1, down_row0;
+};
+
 // Per-frame work lists (all indices are band-local pixel indices or hit slots).  Only pixels whose primary ray has a
 // real collision ("hits", listed in pixel order) carry G-buffer / reservoir data; for every other pixel the only word
 // anybody reads is worldPos.w = 0, which is what keeps the frame's HBM traffic proportional to the

@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(128, 8) k_primary_simple(const GridDev G, cons
 }
 
 __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, Planes prev, ResPlanes prevR,
-                                                ResPlanes outR, Queues Q, uint32_t* __restrict__ trace, int store_y0, int store_y1,
+                                                ResPlanes outR, Queues Q, uint32_t* __restrict__ trace, int store_y0, const PrevAccess PA,
                                                 unsigned* __restrict__ out_of_halo) {
   const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
@@ -561,9 +561,18 @@ __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FramePa
       q[1] = (q[1] + 1.0f) * 0.5f * float(F.H);
       if (q[0] > 0.0f && q[1] > 0.0f && q[0] < float(F.W) && q[1] < float(F.H)) {
         int fx = int(q[0]), fy = int(q[1]);
-        if (fy < store_y0 || fy >= store_y1) atomicAdd(out_of_halo, 1u);                               // halo_rows too small for this camera motion (vrs_get_counters)
-        else {                                                                                         // rows held by this context
-          size_t pidx = (size_t)(fy - store_y0) * F.W + (size_t)fx;
+        // Where the previous frame's pixel lives: in this context's own rows, or (several GPUs, peer memory) in the band of the
+        // neighbour above / below, read in place over NVLink — only the few pixels whose reprojection crosses a band edge pay
+        // that latency, and no halo rows have to be shipped for the temporal pass.
+        const Planes* pp = &prev; const ResPlanes* prp = &prevR;
+        int row0 = store_y0;
+        bool have = fy >= PA.own_y0 && fy < PA.own_y1;
+        if (!have && fy < PA.own_y0 && PA.up.worldPos && fy >= PA.up_y0) { pp = &PA.up; prp = &PA.upR; row0 = PA.up_row0; have = true; }
+        if (!have && fy >= PA.own_y1 && PA.down.worldPos && fy < PA.down_y1) { pp = &PA.down; prp = &PA.downR; row0 = PA.down_row0; have = true; }
+        if (!have) atomicAdd(out_of_halo, 1u);                                                         // beyond the rows anybody can supply (vrs_get_counters)
+        else {
+          const Planes& prev = *pp; const ResPlanes& prevR = *prp;
+          size_t pidx = (size_t)(fy - row0) * F.W + (size_t)fx;
           if (!(prev.worldPos[pidx].w < 0.5f)) {                 // a previous miss holds no data (its zero normal fails :274 anyway)
             GInfo pg = ginfo_from_planes(prev, pidx, F.camPos);                                        // prevGInfo.camPos = gInfo.camPos (:259)
             V3 pd = sub(gi.worldPos, pg.worldPos);
@@ -1027,10 +1036,10 @@ void launch_initial_front(cudaStream_t st, const GridDev& G, const LightsDev& L,
 // Back half of the initial pass: apply the shadow transmittance, temporal merge with the previous frame's G-buffer /
 // final reservoirs (restir.rgen:229-284), final pack.  No-op when neither visibility nor temporal reuse is on.
 void launch_initial_finish(cudaStream_t st, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, Planes prev, ResPlanes prevR,
-                           ResPlanes outR, const Queues& Q, uint32_t* trace, int store_y0, int store_y1, unsigned* out_of_halo, KTimer* kt) {
+                           ResPlanes outR, const Queues& Q, uint32_t* trace, int store_y0, const PrevAccess& PA, unsigned* out_of_halo, KTimer* kt) {
   if ((F.flags & (FLAG_VISIBILITY | FLAG_TEMPORAL)) == 0) return;
   static const int g_finish = resident_grid(k_finish, 128, 8);
-  k_finish<<<g_finish, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, store_y1, out_of_halo);
+  k_finish<<<g_finish, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, PA, out_of_halo);
   ktick(kt, st, "k_finish");
 }
 int initial_front_launches(int flags, bool culling, const LightsDev& L) {

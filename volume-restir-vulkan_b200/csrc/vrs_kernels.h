@@ -11,6 +11,7 @@ struct Planes;
 struct ResPlanes;
 struct Queues;
 struct HaloPush;
+struct PrevAccess;
 
 // Optional per-kernel timing of an eagerly launched frame: one event after every kernel on the launching stream.
 struct KTimer {
@@ -29,7 +30,7 @@ inline void ktick(KTimer* kt, cudaStream_t s, const char* name) {
 void launch_initial_front(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur,
                           ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1, int persistent_blocks, KTimer* kt);
 void launch_initial_finish(cudaStream_t st, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, Planes prev, ResPlanes prevR,
-                           ResPlanes outR, const Queues& Q, uint32_t* trace, int store_y0, int store_y1, unsigned* out_of_halo, KTimer* kt);
+                           ResPlanes outR, const Queues& Q, uint32_t* trace, int store_y0, const PrevAccess& PA, unsigned* out_of_halo, KTimer* kt);
 int initial_front_launches(int flags, bool culling, const LightsDev& L);
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt);
