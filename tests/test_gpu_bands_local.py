@@ -92,7 +92,7 @@ def test_two_bands_equal_one_frame_bunny_4k(V):
 def test_small_halo_is_detected_not_silent(V):
     """A band thinner than the orbit's reprojection distance: some previous-frame pixels lie two bands away, where nobody
     can supply them; those merges are dropped and the counter must say so."""
-    bad, ooh, _ = run_bands(V, "smoke_1080p_temporal", 3, 4, halo=8, check_counter=False, edges=[0, 700, 708, 1080])
+    bad, ooh, _ = run_bands(V, "smoke_1080p_temporal", 3, 4, halo=8, check_counter=False, edges=[0, 300, 308, 1080])
     assert ooh > 0, (ooh, bad)
 
 

@@ -150,10 +150,10 @@ def test_cpp_host_driver_matches_python_host(V, O, tmp_path):
     R.destroy()
 
 
-@pytest.mark.parametrize("env", [{"VRS_RIS": "t"}, {"VRS_RIS": "c"}, {"VRS_SPATIAL": "c"}, {"VRS_RIS_SMALL": "1"},
+@pytest.mark.parametrize("env", [{"VRS_RIS": "t"}, {"VRS_RIS": "c"}, {"VRS_RIS_SMALL": "1"}, {"VRS_PIPELINE": "0"}, {"VRS_MARCH": "s"},
                                  {"VRS_NO_GRAPH": "1", "VRS_NO_CULL": "1"}])
 def test_every_kernel_form_matches_the_oracle(env):
-    """The RIS stage has two forms (serial per thread, warp-cooperative) and spatial reuse two; the
+    """The RIS stage has two forms (serial per thread, warp-cooperative), the raymarch kernels two (scheduled, plain); the
     launcher picks one from the light-table size and the hit count.  Each form, forced through its environment switch
     in a fresh process, must reproduce the oracle bit for bit (__graft_entry__.smoke compares frame and traces)."""
     import os

@@ -552,6 +552,7 @@ static vrs_status make_params(vrs_ctx* ctx, const vrs_global_uniforms* gu, const
   F.W = ctx->W; F.H = ctx->H; F.M = ru->initialLightSampleCount; F.temporalMult = ru->temporalSampleCountMultiplier;
   F.spatialNeighbors = ru->spatialNeighbors; F.spatialRadius = ru->spatialRadius; F.fireflyClamp = ru->fireflyClampThreshold;
   F.flags = ru->flags; F.clock = clock;
+  F.roughness = ctx->grid.roughness; F.metallic = ctx->grid.metallic;
   if (!ctx->history_valid) F.flags &= ~VRS_RESTIR_TEMPORAL_REUSE_FLAG;   // first frame / new lights / new grid / resize: nothing valid to merge
   if (pc) { F.clear[0] = pc->clearColorRed; F.clear[1] = pc->clearColorGreen; F.clear[2] = pc->clearColorBlue; F.frame = pc->frame; F.initialize = pc->initialize; }
   return VRS_OK;
@@ -583,30 +584,38 @@ static FrameIdx frame_idx(uint64_t n) {
 // halo row the neighbour stores.
 static vrs_status halo_push(vrs_ctx* ctx, cudaStream_t st, bool gbuf, int g_index, int r_index, int max_rows) {
   if (ctx->peer_mode) {
-    // (gbuf = false and r_index < 0: no payload, the kernel only publishes the serial — "my planes of this frame are final")
+    // (g_index always names the frame's G-buffer: its worldPos.w is the hit test.  gbuf = false and r_index < 0: no payload, the kernel only publishes the serial — "my planes of this frame are final")
     // one kernel stores the boundary rows into both neighbours' halo rows (NVLink P2P / same-device stores) and publishes the serial
     HaloPush H; memset(&H, 0, sizeof(H));
+    const vrs_ctx::Peer& U = ctx->peer_up; const vrs_ctx::Peer& D = ctx->peer_down;
     auto add = [&](float4* mine, float4* up, float4* down) { H.src[H.nplanes] = mine; H.up_dst[H.nplanes] = up; H.down_dst[H.nplanes] = down; H.nplanes++; };
-    if (gbuf) for (int p = 0; p < 4; ++p) add(ctx->g_planes[g_index][p], ctx->peer_up.present ? ctx->peer_up.g[g_index][p] : nullptr, ctx->peer_down.present ? ctx->peer_down.g[g_index][p] : nullptr);
-    if (r_index >= 0) for (int p = 0; p < 2; ++p) add(ctx->r_planes[r_index][p], ctx->peer_up.present ? ctx->peer_up.r[r_index][p] : nullptr, ctx->peer_down.present ? ctx->peer_down.r[r_index][p] : nullptr);
+    // worldPos (hit marker) whole, albedo + normal + the reservoir pair only for hit pixels; matProps is a per-grid constant
+    // nobody reads from the plane (ginfo_from_planes)
+    H.wp_src = ctx->g_planes[g_index][0]; H.wp_up = U.present ? U.g[g_index][0] : nullptr; H.wp_down = D.present ? D.g[g_index][0] : nullptr;
+    H.copy_wp = gbuf ? 1 : 0;
+    if (gbuf) for (int p = 1; p < 3; ++p) add(ctx->g_planes[g_index][p], U.present ? U.g[g_index][p] : nullptr, D.present ? D.g[g_index][p] : nullptr);
+    if (r_index >= 0) for (int p = 0; p < 2; ++p) add(ctx->r_planes[r_index][p], U.present ? U.r[r_index][p] : nullptr, D.present ? D.r[r_index][p] : nullptr);
+    const bool payload = gbuf || r_index >= 0;
     const int band_h = ctx->band_y1 - ctx->band_y0;
     if (ctx->peer_up.present) {          // my first rows -> the rows just below the up neighbour's band
       int rows = ctx->peer_up.store_y1 - ctx->peer_up.band_y1; if (rows > band_h) rows = band_h;
       if (rows > max_rows) rows = max_rows;
+      if (!payload) rows = 0;
       H.up_count = (size_t)rows * ctx->W; H.up_src_off = (size_t)(ctx->band_y0 - ctx->store_y0) * ctx->W;
       H.up_dst_off = (size_t)(ctx->band_y0 - ctx->peer_up.store_y0) * ctx->W; H.up_flag = ctx->peer_up.flags + 1;     // "written by the down neighbour"
     }
     if (ctx->peer_down.present) {        // my last rows -> the rows just above the down neighbour's band
       int rows = ctx->peer_down.band_y0 - ctx->peer_down.store_y0; if (rows > band_h) rows = band_h;
       if (rows > max_rows) rows = max_rows;
+      if (!payload) rows = 0;
       H.down_count = (size_t)rows * ctx->W; H.down_src_off = (size_t)(ctx->band_y1 - rows - ctx->store_y0) * ctx->W;
       H.down_dst_off = (size_t)(ctx->band_y1 - rows - ctx->peer_down.store_y0) * ctx->W; H.down_flag = ctx->peer_down.flags + 0;   // "written by the up neighbour"
     }
     H.serial = ctx->xflags + 2; H.block_counter = ctx->xflags + 3;
-    // enough blocks to keep NVLink busy: one per 2048 float4 of payload, between 64 and 4 per SM
-    size_t blocks = (H.up_count + H.down_count) * (size_t)H.nplanes / 2048;
+    // one pixel per thread, a few pixels per thread for large pushes; a flag-only push is one block
+    size_t blocks = (H.up_count + H.down_count + 1023) / 1024;
     const size_t max_blocks = (size_t)(ctx->persistent_blocks / 3);
-    if (blocks < 64) blocks = 64;
+    if (blocks < 1) blocks = 1;
     if (blocks > max_blocks) blocks = max_blocks;
     launch_halo_push(st, H, (int)blocks, &ctx->kt);
     CK(cudaGetLastError());
@@ -712,7 +721,7 @@ static vrs_status enqueue_back_phase(vrs_ctx* ctx, const FrameParams& F, const F
   } else if (phase <= iters) {                                                                       // main.cpp:410-413
     if ((s = halo_wait(ctx, st))) return s;
     if ((s = enqueue_spatial(ctx, fi, (uint32_t)(phase - 1), st))) return s;
-    if (multi && phase < iters && (s = halo_push(ctx, st, false, 0, ctx->src_r, sp_rows))) return s;
+    if (multi && phase < iters && (s = halo_push(ctx, st, false, fi.g, ctx->src_r, sp_rows))) return s;
   } else {
     CK(mark(ctx, 3, st));
     // What the NEXT frame's temporal pass reads of this frame.  Peer memory: neighbours read this band's planes in place, so only
@@ -720,7 +729,7 @@ static vrs_status enqueue_back_phase(vrs_ctx* ctx, const FrameParams& F, const F
     // the frame before") — it is published before the shade pass, which touches neither.  NCCL: the G-buffer + final reservoirs
     // of every halo row are shipped.  Either way the consumer-side wait is phase 0 of the next frame.
     const bool push_t = multi && want_temporal_push;
-    if (push_t && ctx->peer_mode && (s = halo_push(ctx, st, false, 0, -1, 0))) return s;
+    if (push_t && ctx->peer_mode && (s = halo_push(ctx, st, false, fi.g, -1, 0))) return s;
     launch_shade(st, ctx->grid, ctx->lights, F, ctx->d_params + fi.q, planes_of(ctx, fi.g), res_of(ctx, ctx->src_r), ctx->accum, ctx->band_y0,
                  ctx->band_y1, ctx->store_y0, &ctx->kt);                                             // main.cpp:416-433
     CK(cudaGetLastError());

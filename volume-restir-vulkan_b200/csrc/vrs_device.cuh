@@ -52,6 +52,7 @@ struct FrameParams {
   int frame, initialize;
   float cullVP[16];               // world -> clip of the primary rays (inverse of viewInverse / projInverse), for k_cover
   int cull;                       // 1 = cullVP is valid, screen-space coverage culling may be used
+  float roughness, metallic;      // the volume's material constants (what restir.rgen:197 stores in the matProps image of every hit)
 };
 
 struct Planes {                   // band-local RGBA32F planes (reference layouts)
@@ -87,13 +88,17 @@ struct Queues {
   float4* shadow_ray;     // 2 x float4 per shadow-queue entry
 };
 
-// One peer-memory halo exchange: rows of `src` planes -> the up / down neighbour's planes (peer pointers, null = no neighbour)
+// One peer-memory halo exchange: boundary rows -> the up / down neighbour's halo rows (peer pointers, null = no neighbour).
+// The worldPos plane travels whole (its w is the hit marker every consumer tests first); the other planes only where the
+// pixel is a hit — a miss pixel's remaining planes are never read, and NVLink stores are what this costs.
 struct HaloPush {
-  const float4* src[6];
-  float4* up_dst[6];
-  float4* down_dst[6];
+  const float4* wp_src; float4* wp_up; float4* wp_down;   // worldPos plane of the frame; copied when copy_wp, always the hit test
+  int copy_wp;
+  const float4* src[4];
+  float4* up_dst[4];
+  float4* down_dst[4];
   int nplanes;
-  size_t up_src_off, up_dst_off, up_count;         // in float4 elements
+  size_t up_src_off, up_dst_off, up_count;         // in float4 elements (= pixels)
   size_t down_src_off, down_dst_off, down_count;
   unsigned* up_flag;                               // "from below" flag in the up neighbour's memory
   unsigned* down_flag;                             // "from above" flag in the down neighbour's memory
@@ -663,8 +668,13 @@ __device__ __forceinline__ void mat_vec(const float* m, float x, float y, float 
   for (int r = 0; r < 4; ++r) o[r] = m[0 + r] * x + m[4 + r] * y + m[8 + r] * z + m[12 + r] * w;
 }
 
-__device__ __forceinline__ GInfo ginfo_from_planes(const Planes& gb, size_t idx, const float* camPos) {
-  float4 p = gb.worldPos[idx], a = gb.albedo[idx], n = gb.normal[idx], m = gb.mat[idx];
+// GeometryInfo of a hit pixel from the G-buffer planes (spatialReuse.comp:65-74 / restir_post.frag:60-67).  The matProps plane of
+// a volume hit always holds {roughness, metallic, 1, 1} of the grid, so the two constants come from the frame parameters
+// instead of a fourth 16-byte gather per pixel (the plane itself is still written for readback).
+__device__ __forceinline__ GInfo ginfo_from_planes(const Planes& gb, size_t idx, const FrameParams& F) {
+  const float* camPos = F.camPos;
+  float4 p = gb.worldPos[idx], a = gb.albedo[idx], n = gb.normal[idx];
+  const float2 m = make_float2(F.roughness, F.metallic);
   GInfo g;
   g.albedo[0] = a.x; g.albedo[1] = a.y; g.albedo[2] = a.z; g.albedo[3] = a.w;
   g.normal = v3(n.x, n.y, n.z);

@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FramePa
     const uint32_t idx = Q.hit_pix[s];
     uint32_t seed = Q.hit_seed[s];
     Res res = unpackReservoir(outR.info[idx], outR.weight[idx]);
-    GInfo gi = ginfo_from_planes(cur, idx, F.camPos);
+    GInfo gi = ginfo_from_planes(cur, idx, F);
     if ((F.flags & FLAG_VISIBILITY) != 0 && res.w > 0.0f) {                                            // :229-235 -> transmittance
       const float T = Q.hit_T[s];
       res.w = res.w * T;
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FramePa
           const Planes& prev = *pp; const ResPlanes& prevR = *prp;
           size_t pidx = (size_t)(fy - row0) * F.W + (size_t)fx;
           if (!(prev.worldPos[pidx].w < 0.5f)) {                 // a previous miss holds no data (its zero normal fails :274 anyway)
-            GInfo pg = ginfo_from_planes(prev, pidx, F.camPos);                                        // prevGInfo.camPos = gInfo.camPos (:259)
+            GInfo pg = ginfo_from_planes(prev, pidx, F);                                        // prevGInfo.camPos = gInfo.camPos (:259)
             V3 pd = sub(gi.worldPos, pg.worldPos);
             if (dot(pd, pd) < 0.01f) {
               V3 ad = v3(gi.albedo[0] - pg.albedo[0], gi.albedo[1] - pg.albedo[1], gi.albedo[2] - pg.albedo[2]);
@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(128, MINB) k_spatial_thread(const LightsDev L,
     if (part != 0 && ((y >= ylo && y < yhi) != (part == 1))) continue;
     uint32_t seed = pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_SPATIAL0 + iteration);   // :58-59
     Res res = unpackReservoir(inR.info[idx], inR.weight[idx]);
-    GInfo gi = ginfo_from_planes(cur, idx, F.camPos);
+    GInfo gi = ginfo_from_planes(cur, idx, F);
     uint32_t Z = res.M;
     const float radius = F.spatialRadius;
     uint32_t k = F.spatialNeighbors; if (k > (uint32_t)MAX_NEIGHBORS) k = MAX_NEIGHBORS;
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(128, MINB) k_spatial_thread(const LightsDev L,
     }
     if (nacc > 0) {
       for (int j = 0; j < nacc; ++j) {                                           // reservoir.glsl:70-73
-        GInfo ng = ginfo_from_planes(cur, nb_idx[j], F.camPos);
+        GInfo ng = ginfo_from_planes(cur, nb_idx[j], F);
         float pHat = evaluatePHat(L, res.lightIndex, ng);
         if (pHat > 0.0f) Z += nb_M[j];
       }
@@ -660,181 +660,6 @@ __global__ void __launch_bounds__(128, MINB) k_spatial_thread(const LightsDev L,
   }
 }
 
-
-// ---- Spatial reuse, cooperative form.  Which neighbours a pixel merges, and what each contributes, is independent per
-// (pixel, neighbour) pair once the offset draws come first; only the running sum of updateReservoir is serial.  A warp
-// takes a group of hit pixels and works on PAIRS, so that rejected neighbours (outside the disk, missed, dissimilar)
-// cost no lane time in the expensive parts:
-//   step 1  lane = pixel  own reservoir + G-buffer, per-pixel shading terms -> shared memory
-//   phase A lane = pair   offset, bounds, neighbour gathers, similarity tests; accepted pairs -> work list
-//   phase B lane = accepted pair   pHat of the neighbour's light at this pixel (reservoir.glsl:62-63)
-//   step 3  lane = pixel  M and sumWeights accumulation, selection draws, in neighbour order (reservoir.glsl:61-68)
-//   phase C lane = accepted pair   pHat of the finally selected light at the neighbour's geometry (reservoir.glsl:70-73)
-//   final   lane = pixel  Z, w (reservoir.glsl:74-75), store
-static constexpr int SP_PAIRS = 288;       // >= group size * (k | 1)
-struct SpSmem {
-  float P[3][32], n[3][32], alb[3][32], albedoLum[32], rough[32], metal[32], wo[3][32], fresnelOut[32], smithOut[32], a[32];
-  uint32_t seed0[32], finalLight[32];
-  int px[32], py[32];
-  uint32_t nidx[SP_PAIRS], nM[SP_PAIRS], nLight[SP_PAIRS];   // per pair: neighbour pixel (~0 = rejected), its M, its light
-  float nW[SP_PAIRS], nPHat[SP_PAIRS];                       // its w (phase B turns it into the merge weight), pHat at this pixel
-  uint16_t list[SP_PAIRS];                                   // accepted pairs: pair | pixel << 9
-};
-
-__global__ void __launch_bounds__(128, 6) k_spatial_coop(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes inR, ResPlanes outR,
-                                                         Queues Q, uint32_t iteration, int store_y0, int store_y1, int target_warps) {
-  __shared__ SpSmem sm_all[4];
-  __shared__ uint32_t jmpA[32], jmpC[32];                    // LCG advanced by 2 * i draws
-  SpSmem& sm = sm_all[threadIdx.x >> 5];
-  const FrameParams& F = *Fp;
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  if (threadIdx.x < 32) {
-    uint32_t A = 1u, C = 0u;
-    for (uint32_t i = 0; i < 2u * threadIdx.x; ++i) { A = A * 1664525u; C = C * 1664525u + 1013904223u; }
-    jmpA[threadIdx.x] = A; jmpC[threadIdx.x] = C;
-  }
-  __syncthreads();
-  const uint32_t nhit = Q.counters[Q_HIT];
-  const uint32_t nwarps = gridDim.x * 4u, warp = blockIdx.x * 4u + (threadIdx.x >> 5);
-  uint32_t k = F.spatialNeighbors; if (k > (uint32_t)MAX_NEIGHBORS) k = MAX_NEIGHBORS;
-  const uint32_t kp = k | 1u;                                // odd pair stride: lane = pixel reads are bank-conflict free
-  const uint32_t gmax = (uint32_t)SP_PAIRS / kp < 32u ? (uint32_t)SP_PAIRS / kp : 32u;
-  const uint32_t gsz = group_size_for(nhit, nwarps, (uint32_t)target_warps, gmax);
-  const float radius = F.spatialRadius;
-
-  for (uint32_t g0 = warp * gsz; g0 < nhit; g0 += nwarps * gsz) {
-    const uint32_t npix = nhit - g0 < gsz ? nhit - g0 : gsz;
-    const bool pix = (uint32_t)lane < npix;
-    // ---------------- step 1: lane = pixel
-    uint32_t idx = 0, seed = 0;
-    Res res = newReservoir();
-    if (pix) {
-      idx = Q.hit_pix[g0 + (uint32_t)lane];
-      const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
-      seed = pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_SPATIAL0 + iteration);             // :58-59
-      res = unpackReservoir(inR.info[idx], inR.weight[idx]);
-      const GInfo gi = ginfo_from_planes(cur, idx, F.camPos);
-      const ShadePre pre = shade_pre(gi);
-      sm.P[0][lane] = gi.worldPos.x; sm.P[1][lane] = gi.worldPos.y; sm.P[2][lane] = gi.worldPos.z;
-      sm.n[0][lane] = gi.normal.x; sm.n[1][lane] = gi.normal.y; sm.n[2][lane] = gi.normal.z;
-      sm.alb[0][lane] = gi.albedo[0]; sm.alb[1][lane] = gi.albedo[1]; sm.alb[2][lane] = gi.albedo[2];
-      sm.albedoLum[lane] = gi.albedoLum; sm.rough[lane] = gi.roughness; sm.metal[lane] = gi.metallic;
-      sm.wo[0][lane] = pre.wo.x; sm.wo[1][lane] = pre.wo.y; sm.wo[2][lane] = pre.wo.z;
-      sm.fresnelOut[lane] = pre.fresnelOut; sm.smithOut[lane] = pre.smithOut; sm.a[lane] = pre.a;
-      sm.seed0[lane] = seed; sm.px[lane] = x; sm.py[lane] = y;
-    }
-    __syncwarp();
-    // ---------------- phase A: lane = (pixel, neighbour) pair
-    const uint32_t npairs = npix * k;
-    uint32_t nlist = 0u;
-    for (uint32_t q0 = 0; q0 < npairs; q0 += 32u) {
-      const uint32_t q = q0 + (uint32_t)lane;
-      bool acc = false;
-      uint32_t pair = 0u, p = 0u;
-      if (q < npairs) {
-        p = q / k;
-        const uint32_t i = q - p * k;
-        pair = p * kp + i;
-        uint32_t so = jmpA[i] * sm.seed0[p] + jmpC[i];
-        const float r1 = rnd(so), r2 = rnd(so);
-        const float dx = (r1 * 2.0f - 1.0f) * radius, dy = (r2 * 2.0f - 1.0f) * radius;
-        // Every plane the tests and the merge may need is requested at once, from this pixel's own (cached) slot when the
-        // offset is rejected outright: one L2 round trip per pair instead of three dependent ones.
-        const int ox = int(dx), oy = int(dy);
-        const int nx = sm.px[p] + ox, ny = sm.py[p] + oy;
-        const bool inside = !(dx * dx + dy * dy > radius * radius) && !(ox == 0 && oy == 0) && nx >= 0 && ny >= 0 && nx < (int)F.W && ny < (int)F.H &&
-                            ny >= store_y0 && ny < store_y1;
-        const size_t ni = inside ? (size_t)(ny - store_y0) * F.W + (size_t)nx : (size_t)(sm.py[p] - store_y0) * F.W + (size_t)sm.px[p];
-        const float4 nwp = cur.worldPos[ni], na = cur.albedo[ni], nn = cur.normal[ni], ri = inR.info[ni], rw = inR.weight[ni];
-        uint32_t nidx = 0xFFFFFFFFu;
-        if (inside && !(nwp.w < 0.5f)) {
-          const V3 pd = sub(v3(sm.P[0][p], sm.P[1][p], sm.P[2][p]), v3(nwp.x, nwp.y, nwp.z));
-          const V3 ad = v3(sm.alb[0][p] - na.x, sm.alb[1][p] - na.y, sm.alb[2][p] - na.z);
-          if (dot(pd, pd) < 0.01f && dot(ad, ad) < 0.01f && dot(v3(sm.n[0][p], sm.n[1][p], sm.n[2][p]), v3(nn.x, nn.y, nn.z)) > 0.5f) {
-            const Res nr = unpackReservoir(ri, rw);
-            nidx = (uint32_t)ni;
-            sm.nM[pair] = nr.M; sm.nLight[pair] = nr.lightIndex; sm.nW[pair] = nr.w;
-            acc = true;
-          }
-        }
-        sm.nidx[pair] = nidx;
-      }
-      const unsigned m = __ballot_sync(full, acc);
-      if (acc) sm.list[nlist + (uint32_t)__popc(m & lt_mask)] = (uint16_t)(pair | (p << 9));
-      nlist += (uint32_t)__popc(m);
-    }
-    __syncwarp();
-    // ---------------- phase B: lane = accepted pair, pHat of the neighbour's sample at this pixel
-    for (uint32_t e0 = 0; e0 < nlist; e0 += 32u) {
-      const uint32_t e = e0 + (uint32_t)lane;
-      if (e < nlist) {
-        const uint32_t pr = sm.list[e], pair = pr & 0x1FFu, p = pr >> 9;
-        GInfo g;
-        g.worldPos = v3(sm.P[0][p], sm.P[1][p], sm.P[2][p]); g.normal = v3(sm.n[0][p], sm.n[1][p], sm.n[2][p]);
-        g.albedoLum = sm.albedoLum[p]; g.roughness = sm.rough[p]; g.metallic = sm.metal[p];
-        ShadePre pre;
-        pre.wo = v3(sm.wo[0][p], sm.wo[1][p], sm.wo[2][p]); pre.fresnelOut = sm.fresnelOut[p]; pre.smithOut = sm.smithOut[p];
-        pre.a = sm.a[p]; pre.cosOut = 0.0f;
-        const float pHat = evaluatePHat(L, sm.nLight[pair], g, pre);
-        sm.nPHat[pair] = pHat;
-        sm.nW[pair] = pHat * sm.nW[pair] * float(sm.nM[pair]);                                         // reservoir.glsl:63
-      }
-    }
-    __syncwarp();
-    // ---------------- step 3: lane = pixel, reservoir.glsl:61-68 in neighbour order
-    uint32_t Z = res.M;
-    int nacc = 0;
-    uint32_t selPair = 0xFFFFFFFFu;
-    if (pix) {
-      for (uint32_t i = 0; i < 2u * k; ++i) lcg(seed);                                                 // behind the offset draws
-      for (uint32_t i = 0; i < k; ++i) {
-        const uint32_t pair = (uint32_t)lane * kp + i;
-        if (sm.nidx[pair] == 0xFFFFFFFFu) continue;
-        ++nacc;
-        res.M += sm.nM[pair];
-        const float weight = sm.nW[pair];
-        if (weight > 0.0f) {
-          res.sumWeights += weight;
-          const float replacePossibility = weight / res.sumWeights;
-          if (rnd(seed) < replacePossibility) selPair = pair;
-        }
-      }
-      if (selPair != 0xFFFFFFFFu) {
-        const uint32_t ni = sm.nidx[selPair];
-        const Res nr = unpackReservoir(inR.info[ni], inR.weight[ni]);
-        res.lightIndex = nr.lightIndex; res.lightKind = nr.lightKind; res.pHat = sm.nPHat[selPair]; res.w = nr.w; res.sampleSeed = nr.sampleSeed;
-      }
-      sm.finalLight[lane] = res.lightIndex;
-    }
-    __syncwarp();
-    // ---------------- phase C: lane = accepted pair, the selected light seen from the neighbour (reservoir.glsl:70-73)
-    for (uint32_t e0 = 0; e0 < nlist; e0 += 32u) {
-      const uint32_t e = e0 + (uint32_t)lane;
-      if (e < nlist) {
-        const uint32_t pr = sm.list[e], pair = pr & 0x1FFu, p = pr >> 9;
-        const GInfo ng = ginfo_from_planes(cur, sm.nidx[pair], F.camPos);
-        const float pHat = evaluatePHat(L, sm.finalLight[p], ng);
-        if (!(pHat > 0.0f)) sm.nM[pair] = 0u;
-      }
-    }
-    __syncwarp();
-    // ---------------- final: lane = pixel
-    if (pix) {
-      if (nacc > 0) {
-        for (uint32_t i = 0; i < k; ++i) {
-          const uint32_t pair = (uint32_t)lane * kp + i;
-          if (sm.nidx[pair] != 0xFFFFFFFFu) Z += sm.nM[pair];
-        }
-        if (res.w > 0.0f) res.w = res.sumWeights / (float(Z) * res.pHat);                              // :74-75
-      }
-      float4 a, b; packReservoir(res, a, b);
-      outR.info[idx] = a; outR.weight[idx] = b;
-    }
-    __syncwarp();
-  }
-}
 
 // -------------------------------------------------------------------------------------------------
 // Final shade — restir_post.frag main (:57-105): shade, emissive override, firefly clamp, running mean.
@@ -852,7 +677,7 @@ __global__ void __launch_bounds__(256) k_shade(const GridDev G, const LightsDev 
   if (wp.w < 0.5f) {
     c = v3(F.clear[0], F.clear[1], F.clear[2]);
   } else {
-    GInfo gi = ginfo_from_planes(cur, idx, F.camPos);
+    GInfo gi = ginfo_from_planes(cur, idx, F);
     Res res = unpackReservoir(rs.info[idx], rs.weight[idx]);
     gi.sampleSeed = res.sampleSeed;
     V3 pHat = evaluatePHatFull(L, res.lightIndex, gi);
@@ -886,9 +711,18 @@ __global__ void __launch_bounds__(256) k_shade(const GridDev G, const LightsDev 
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_halo_push(HaloPush H) {
   const size_t stride = (size_t)gridDim.x * blockDim.x, tid0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  for (int p = 0; p < H.nplanes; ++p) {
-    if (H.up_dst[p]) for (size_t i = tid0; i < H.up_count; i += stride) H.up_dst[p][H.up_dst_off + i] = H.src[p][H.up_src_off + i];
-    if (H.down_dst[p]) for (size_t i = tid0; i < H.down_count; i += stride) H.down_dst[p][H.down_dst_off + i] = H.src[p][H.down_src_off + i];
+  const size_t total = H.up_count + H.down_count;
+  for (size_t i = tid0; i < total; i += stride) {           // one pixel per thread: consecutive lanes, consecutive 16-byte stores
+    const bool up = i < H.up_count;
+    const size_t k = up ? i : i - H.up_count;
+    const size_t so = (up ? H.up_src_off : H.down_src_off) + k, dof = (up ? H.up_dst_off : H.down_dst_off) + k;
+    const float4 wp = H.wp_src[so];
+    if (H.copy_wp) (up ? H.wp_up : H.wp_down)[dof] = wp;
+    if (!(wp.w < 0.5f)) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (p < H.nplanes) (up ? H.up_dst[p] : H.down_dst[p])[dof] = H.src[p][so];
+    }
   }
   __threadfence_system();
   __syncthreads();
@@ -1052,17 +886,10 @@ int initial_front_launches(int flags, bool culling, const LightsDev& L) {
 }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt) {
-  static const bool thread_form = !(getenv("VRS_SPATIAL") && getenv("VRS_SPATIAL")[0] == 'c');
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   static const int target_warps = sms * (getenv("VRS_MIN_WARPS_PER_SM") ? atoi(getenv("VRS_MIN_WARPS_PER_SM")) : MIN_WARPS_PER_SM);
-  static const int coop_blocks = [] {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_spatial_coop, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-    return sms * per_sm;
-  }();
   static const int g8 = resident_grid(k_spatial_thread<8>, 128, 8);
-  if (thread_form) k_spatial_thread<8><<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
-  else if (part != 2) k_spatial_coop<<<coop_blocks, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, target_warps);   // (no row split: part 1 does all)
+  k_spatial_thread<8><<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
   ktick(kt, s, "k_spatial");
 }
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, ResPlanes rs,
