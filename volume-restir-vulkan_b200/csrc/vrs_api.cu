@@ -678,10 +678,10 @@ static int back_phases(vrs_ctx* ctx, const FrameParams& F) {
   const bool spatial = (F.flags & VRS_RESTIR_SPATIAL_REUSE_FLAG) != 0 && ctx->cfg.spatial_iterations > 0;
   return 2 + (spatial ? (int)ctx->cfg.spatial_iterations : 0);
 }
-static vrs_status enqueue_spatial(vrs_ctx* ctx, const FrameIdx& fi, uint32_t iteration, cudaStream_t st) {
+static vrs_status enqueue_spatial(vrs_ctx* ctx, const FrameParams& F, const FrameIdx& fi, uint32_t iteration, cudaStream_t st) {
   const int dst = ctx->src_r == fi.ra ? fi.rb : fi.ra;
   launch_spatial(st, ctx->lights, ctx->d_params + fi.q, planes_of(ctx, fi.g), res_of(ctx, ctx->src_r), res_of(ctx, dst), ctx->queues[fi.q],
-                 iteration, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks, 0, 0, 0, &ctx->kt);
+                 iteration, F.spatialNeighbors, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks, 0, 0, 0, &ctx->kt);
   CK(cudaGetLastError());
   ctx->src_r = dst;
   ctx->timings.launches += 1;
@@ -720,7 +720,7 @@ static vrs_status enqueue_back_phase(vrs_ctx* ctx, const FrameParams& F, const F
     CK(mark(ctx, 2, st));
   } else if (phase <= iters) {                                                                       // main.cpp:410-413
     if ((s = halo_wait(ctx, st))) return s;
-    if ((s = enqueue_spatial(ctx, fi, (uint32_t)(phase - 1), st))) return s;
+    if ((s = enqueue_spatial(ctx, F, fi, (uint32_t)(phase - 1), st))) return s;
     if (multi && phase < iters && (s = halo_push(ctx, st, false, fi.g, ctx->src_r, sp_rows))) return s;
   } else {
     CK(mark(ctx, 3, st));
@@ -803,7 +803,7 @@ vrs_status vrs_pass_spatial(vrs_ctx* ctx, const vrs_restir_uniforms* ru, uint32_
   cudaSetDevice(ctx->device);
   FrameParams F; vrs_status s = make_params(ctx, nullptr, ru, nullptr, clock, F); if (s) return s;
   if ((s = upload_params(ctx, F, ctx->cur.q, ctx->stream))) return s;
-  return enqueue_spatial(ctx, ctx->cur, iteration, ctx->stream);
+  return enqueue_spatial(ctx, F, ctx->cur, iteration, ctx->stream);
 }
 vrs_status vrs_pass_shade(vrs_ctx* ctx, const vrs_restir_uniforms* ru, const vrs_push_constant_restir* pc, uint32_t clock) {
   if (!ctx || !ru || !pc) return VRS_ERR_INVALID;

@@ -33,7 +33,7 @@ void launch_initial_finish(cudaStream_t st, const LightsDev& L, const FrameParam
                            ResPlanes outR, const Queues& Q, uint32_t* trace, int store_y0, const PrevAccess& PA, unsigned* out_of_halo, KTimer* kt);
 int initial_front_launches(int flags, bool culling, const LightsDev& L);
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
-                    uint32_t iteration, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt);
+                    uint32_t iteration, uint32_t spatial_neighbors, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt);
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, ResPlanes rs,
                   float4* accum, int y0, int y1, int store_y0, KTimer* kt);
 void launch_halo_push(cudaStream_t s, const HaloPush& H, int blocks, KTimer* kt);
