@@ -114,7 +114,7 @@ int        vrs_abi_version(void);
  * dense brick atlas, stage it into HBM.  `.vrsg` files (this library's own flattened snapshot) load the same way. */
 vrs_status vrs_load_vdb(vrs_ctx* ctx, const char* path, const char* grid_name);
 vrs_status vrs_load_vrsg(vrs_ctx* ctx, const char* path);
-/* Host-only conversion `.vdb` -> `.vrsg` (no device needed; ctx may be NULL). */
+/* Host-only conversion `.vdb` -> `.vrsg` (no device needed); a `.vrsg` input is validated and re-written. */
 vrs_status vrs_convert_vdb(const char* vdb_path, const char* grid_name, const char* vrsg_path);
 /* Deterministic procedural stand-ins for the assets missing from the reference checkout
  * (.MISSING_LARGE_BLOBS:1-4): kind 0 = "bunny_cloud", 1 = "explosion", 2 = "fire", 3 = "torus_knot_helix",

@@ -277,3 +277,45 @@ def test_emissive_voxel_lights_from_temperature_grid(V, tmp_path):
     assert np.allclose(lights[:, 7], 0.2126 * 0.6 + 0.7152 * 0.2 + 0.0722 * 0.1)
     assert len(V.vdb_emissive_lights(path, "temperature", max_lights=5)) == 5
     assert len(V.vdb_emissive_lights(path, "density")) == 0               # log(1) + 273.15 < 275
+
+
+def test_malformed_vrsg_snapshots_are_rejected(V, tmp_path):
+    """the .vrsg reader must not trust indices or sizes from the file (they index host tables in finalize() and device
+    tables in the kernels).  vrs_convert_vdb validates a snapshot host-side: corrupt child indices, absurd sizes and
+    truncated payloads are VRS_ERR_FORMAT, never a crash."""
+    import struct
+    import zlib
+    src = open(common.asset("cube"), "rb").read()
+    assert src[:8] == b"VRSG0001"
+    raw_size, zipped = struct.unpack_from("<QQ", src, 8)
+    payload = bytearray(zlib.decompress(src[24:24 + zipped]))
+    assert len(payload) == raw_size
+    out = str(tmp_path / "out.vrsg")
+
+    def write(name, body, claim=None):
+        z = zlib.compress(bytes(body), 1)
+        p = str(tmp_path / name)
+        open(p, "wb").write(b"VRSG0001" + struct.pack("<QQ", len(body) if claim is None else claim, len(z)) + z)
+        return p
+
+    V.convert_vdb(write("good.vrsg", payload), out)                       # the untouched payload round-trips
+    nroot, n5, n4, nleaf, ntile = struct.unpack_from("<5I", payload, 40)
+    assert nroot >= 1 and n5 >= 1 and nleaf > 100
+    bad = bytearray(payload)
+    struct.pack_into("<i", bad, 60 + 12, n5 + 7)                           # root child -> a node that does not exist
+    cases = {"root_child.vrsg": (bad, None)}
+    bad = bytearray(payload)
+    off = 60 + 16 * nroot                                                  # first sparse i5 table: count, then (slot, value) records
+    (count,) = struct.unpack_from("<I", bad, off)
+    assert count >= 1
+    struct.pack_into("<i", bad, off + 4 + 4, n4 + 1000)                    # i5 child -> a node that does not exist
+    cases["i5_child.vrsg"] = (bad, None)
+    bad = bytearray(payload)
+    struct.pack_into("<I", bad, 40 + 16, 0x7FFFFFFF)                       # ntile absurd
+    cases["ntile.vrsg"] = (bad, None)
+    cases["truncated.vrsg"] = (payload[:len(payload) // 2], None)
+    cases["raw_size.vrsg"] = (payload, 1 << 40)                            # header claims a terabyte
+    for name, (body, claim) in cases.items():
+        with pytest.raises(V.VrsError) as e:
+            V.convert_vdb(write(name, body, claim), out)
+        assert e.value.status == 4, (name, e.value)                       # VRS_ERR_FORMAT

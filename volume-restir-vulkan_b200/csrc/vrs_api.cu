@@ -10,6 +10,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -357,28 +358,39 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
   return VRS_OK;
 }
 
+// No exception crosses the C ABI: a hostile file can still make a reader ask for an absurd allocation.
+#define VRS_GUARD(ctx_, body)                                                                                     \
+  try { body }                                                                                                    \
+  catch (const std::bad_alloc&) { return fail(ctx_, VRS_ERR_FORMAT, "file asks for more memory than can be allocated (corrupt?)"); } \
+  catch (const std::exception& e) { return fail(ctx_, VRS_ERR_FORMAT, std::string("reader failed: ") + e.what()); }
+
 vrs_status vrs_load_vdb(vrs_ctx* ctx, const char* path, const char* grid_name) {
   if (!ctx || !path) return VRS_ERR_INVALID;
   std::string p(path), err;
   if (p.size() > 5 && p.compare(p.size() - 5, 5, ".vrsg") == 0) return vrs_load_vrsg(ctx, path);
-  if (!read_vdb(p, grid_name, ctx->host_grid, err)) {
-    bool io = err.rfind("cannot open", 0) == 0 || err.rfind("short read", 0) == 0;
-    return fail(ctx, io ? VRS_ERR_IO : VRS_ERR_FORMAT, err);
-  }
-  return upload_grid(ctx);
+  VRS_GUARD(ctx,
+    if (!read_vdb(p, grid_name, ctx->host_grid, err)) {
+      bool io = err.rfind("cannot open", 0) == 0 || err.rfind("short read", 0) == 0;
+      return fail(ctx, io ? VRS_ERR_IO : VRS_ERR_FORMAT, err);
+    }
+    return upload_grid(ctx);)
 }
 vrs_status vrs_load_vrsg(vrs_ctx* ctx, const char* path) {
   if (!ctx || !path) return VRS_ERR_INVALID;
   std::string err;
-  if (!read_vrsg(path, ctx->host_grid, err)) return fail(ctx, err.rfind("cannot open", 0) == 0 ? VRS_ERR_IO : VRS_ERR_FORMAT, err);
-  return upload_grid(ctx);
+  VRS_GUARD(ctx,
+    if (!read_vrsg(path, ctx->host_grid, err)) return fail(ctx, err.rfind("cannot open", 0) == 0 ? VRS_ERR_IO : VRS_ERR_FORMAT, err);
+    return upload_grid(ctx);)
 }
 vrs_status vrs_convert_vdb(const char* vdb_path, const char* grid_name, const char* vrsg_path) {
   if (!vdb_path || !vrsg_path) return VRS_ERR_INVALID;
   HostGrid g; std::string err;
-  if (!read_vdb(vdb_path, grid_name, g, err)) return fail(nullptr, err.rfind("cannot open", 0) == 0 ? VRS_ERR_IO : VRS_ERR_FORMAT, err);
-  if (!write_vrsg(vrsg_path, g, err)) return fail(nullptr, VRS_ERR_IO, err);
-  return VRS_OK;
+  const std::string in(vdb_path);
+  const bool is_vrsg = in.size() > 5 && in.compare(in.size() - 5, 5, ".vrsg") == 0;      // a snapshot is validated and re-written
+  VRS_GUARD(nullptr,
+    if (!(is_vrsg ? read_vrsg(in, g, err) : read_vdb(in, grid_name, g, err))) return fail(nullptr, err.rfind("cannot open", 0) == 0 ? VRS_ERR_IO : VRS_ERR_FORMAT, err);
+    if (!write_vrsg(vrsg_path, g, err)) return fail(nullptr, VRS_ERR_IO, err);
+    return VRS_OK;)
 }
 vrs_status vrs_make_procedural_grid(vrs_ctx* ctx, int kind, uint32_t resolution) {
   if (!ctx) return VRS_ERR_INVALID;

@@ -115,7 +115,7 @@ namespace {
 
 struct Reader {
   const uint8_t* d; size_t n, p = 0; bool ok = true;
-  void need(size_t k) { if (p + k > n) ok = false; }
+  void need(size_t k) { if (p > n || k > n - p) ok = false; }     // (p + k could wrap for a hostile offset)
   void raw(void* out, size_t k) { need(k); if (!ok) { memset(out, 0, k); return; } memcpy(out, d + p, k); p += k; }
   template <class T> T get() { T v; raw(&v, sizeof(T)); return v; }
   std::string str() { uint32_t l = get<uint32_t>(); need(l); if (!ok) return ""; std::string s((const char*)d + p, l); p += l; return s; }
@@ -236,7 +236,7 @@ bool read_block(Ctx& c, size_t count, size_t item, std::vector<uint8_t>& out) {
     c.r.need((size_t)zipped);
     if (!c.r.ok) return false;
     uLongf dst = (uLongf)out.size();
-    if (uncompress(out.data(), &dst, c.r.d + c.r.p, (uLong)zipped) != Z_OK) { c.err = "zlib block corrupt"; return false; }
+    if (uncompress(out.data(), &dst, c.r.d + c.r.p, (uLong)zipped) != Z_OK || dst != (uLongf)out.size()) { c.err = "zlib block corrupt"; return false; }
     c.r.p += (size_t)zipped;
     return true;
   }
@@ -490,6 +490,7 @@ bool read_vrsg(const std::string& path, HostGrid& g, std::string& err) {
   if (ok) { z.resize(zipped); ok = fread(z.data(), 1, zipped, f) == zipped; }
   fclose(f);
   if (!ok) { err = "not a .vrsg file: " + path; return false; }
+  if (raw_size > ((uint64_t)1 << 36) || raw_size > zipped * 1100 + (1 << 20)) { err = "corrupt .vrsg header (payload size)"; return false; }   // zlib cannot expand more than ~1032x
   std::vector<uint8_t> b(raw_size);
   uLongf dst = (uLongf)raw_size;
   if (uncompress(b.data(), &dst, z.data(), (uLong)zipped) != Z_OK || dst != raw_size) { err = "corrupt .vrsg payload"; return false; }
@@ -499,7 +500,8 @@ bool read_vrsg(const std::string& path, HostGrid& g, std::string& err) {
   g.level_set = flags & 1; g.half = flags & 2;
   g.background = r.get<float>(); g.voxel_size = r.get<double>(); r.raw(g.translation, 24);
   uint32_t nroot = r.get<uint32_t>(), n5 = r.get<uint32_t>(), n4 = r.get<uint32_t>(), nleaf = r.get<uint32_t>(), ntile = r.get<uint32_t>();
-  if (!r.ok || (uint64_t)nleaf * 1024 > raw_size + 1024 || (uint64_t)n5 * 4 > raw_size || (uint64_t)n4 * 4 > raw_size) { err = "corrupt .vrsg header"; return false; }
+  if (!r.ok || (uint64_t)nleaf * 1024 > raw_size + 1024 || (uint64_t)n5 * 4 > raw_size || (uint64_t)n4 * 4 > raw_size ||
+      (uint64_t)nroot * 16 > raw_size || (uint64_t)ntile * 5 > raw_size) { err = "corrupt .vrsg header"; return false; }
   g.root.resize(4 * (size_t)nroot); r.raw(g.root.data(), g.root.size() * 4);
   g.i5.assign((size_t)n5 * 32768, ~0); g.i4.assign((size_t)n4 * 4096, ~0);
   auto sparse = [&r](int32_t* slots, size_t n) {
@@ -518,6 +520,13 @@ bool read_vrsg(const std::string& path, HostGrid& g, std::string& err) {
     if (r.ok) { for (size_t i = 0; i < g.leaf_value.size(); ++i) { uint16_t h; memcpy(&h, r.d + r.p + 2 * i, 2); g.leaf_value[i] = half_to_float(h); } r.p += g.leaf_value.size() * 2; }
   } else r.raw(g.leaf_value.data(), g.leaf_value.size() * 4);
   if (!r.ok) { err = "truncated .vrsg payload"; return false; }
+  // every child / tile index must name an existing table entry: finalize(), the directory build and the device lookups trust them
+  auto child_ok = [](int32_t v, size_t nchild, size_t ntiles) { return v >= 0 ? (size_t)v < nchild : (size_t)(~v) < (ntiles ? ntiles : 1); };
+  bool idx_ok = true;
+  for (size_t k = 0; k < nroot && idx_ok; ++k) idx_ok = child_ok(g.root[4 * k + 3], n5, ntile);
+  for (size_t k = 0; k < g.i5.size() && idx_ok; ++k) idx_ok = child_ok(g.i5[k], n4, ntile);
+  for (size_t k = 0; k < g.i4.size() && idx_ok; ++k) idx_ok = child_ok(g.i4[k], nleaf, ntile);
+  if (!idx_ok) { err = "corrupt .vrsg tables (child index out of range)"; return false; }
   for (size_t k = 0; k < nroot; ++k) g.root_children += g.root[4 * k + 3] >= 0;
   g.name = "vrsg"; g.grid_type = g.half ? "Tree_float_5_4_3_HalfFloat" : "Tree_float_5_4_3";
   g.finalize();
