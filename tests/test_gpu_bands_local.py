@@ -23,7 +23,7 @@ def make(V, wl, path, band, halo, lights=None):
     return R
 
 
-def run_bands(V, name, nbands, frames, halo=None, W=None, H=None, M=None, edges=None, check_counter=True):
+def run_bands(V, name, nbands, frames, halo=None, W=None, H=None, M=None, edges=None, check_counter=True, orbit_deg=None):
     wl = dict(bench.WORKLOADS[name])
     if W:
         wl["W"], wl["H"] = W, H
@@ -47,7 +47,7 @@ def run_bands(V, name, nbands, frames, halo=None, W=None, H=None, M=None, edges=
         r_.createRestirUniformBuffer()
     bad = []
     for f in range(frames):
-        eye = bench.orbit_eye(ctr, radius, 0.0, bench.ORBIT_DEG * f)
+        eye = bench.orbit_eye(ctr, radius, 0.0, (bench.ORBIT_DEG if orbit_deg is None else orbit_deg) * f)
         for b in bands:
             b.CameraManip.setLookat(eye, ctr)
         V.render_frame_group(bands, f)               # one host thread: phases interleaved across the bands (vrs_render_frame_group)
@@ -92,7 +92,7 @@ def test_two_bands_equal_one_frame_bunny_4k(V):
 def test_small_halo_is_detected_not_silent(V):
     """A band thinner than the orbit's reprojection distance: some previous-frame pixels lie two bands away, where nobody
     can supply them; those merges are dropped and the counter must say so."""
-    bad, ooh, _ = run_bands(V, "smoke_1080p_temporal", 3, 4, halo=8, check_counter=False, edges=[0, 300, 308, 1080])
+    bad, ooh, _ = run_bands(V, "smoke_1080p_temporal", 3, 4, halo=8, check_counter=False, edges=[0, 300, 308, 1080], orbit_deg=25.0)
     assert ooh > 0, (ooh, bad)
 
 

@@ -661,157 +661,6 @@ __global__ void __launch_bounds__(128, MINB) k_spatial_thread(const LightsDev L,
 }
 
 
-// ---- Spatial reuse, warp form (default for k <= 8).  In the per-thread kernel above the two expensive parts — p-hat of a
-// neighbour's sample at this pixel (reservoir.glsl:62-63) and p-hat of the finally selected sample at every merged
-// neighbour (:70-73) — run once per loop trip with only the lanes whose neighbour passed the similarity tests: 12-14 of
-// 32 lanes (ncu).  Which neighbours a pixel merges, and each one's contribution, is independent per (pixel, neighbour) pair
-// once the offset draws come first; only the running sum of updateReservoir is serial.  So a warp takes 32 hit pixels and
-//   phase 1  lane = pixel   offsets, gathers, similarity tests; accepted neighbours -> per-lane slots in shared memory
-//   phase 2  lane = pair    the accepted pairs of the whole warp, densely packed: p-hat at the owner pixel, whose shading
-//                           terms arrive by shuffle from the owner lane
-//   phase 3  lane = pixel   M and sumWeights accumulation and the selection draws, in neighbour order
-//   phase 4  lane = pair    p-hat of the owner's selected light at the neighbour's geometry
-//   phase 5  lane = pixel   Z, w (reservoir.glsl:74-75), store
-// Same operations on the same values in the same order per pixel as k_spatial_thread, hence the same bits.
-static constexpr int SPW_K = 8;
-struct SpwSmem {
-  uint4 slot[SPW_K][32];          // per lane, per accepted neighbour: {stored pixel index, M, light index, w as bits}
-  float pHat[SPW_K][32];          // p-hat of that neighbour's light at the owner pixel
-  float weight[SPW_K][32];        // merge weight (phase 2), then 1 / 0 = counts towards Z (phase 4)
-  uint32_t prefix[32];            // exclusive prefix sum of the lanes' accepted counts
-};
-
-__global__ void __launch_bounds__(128, 6) k_spatial_warp(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes inR, ResPlanes outR,
-                                                         Queues Q, uint32_t iteration, int store_y0, int store_y1) {
-  __shared__ SpwSmem sm_all[4];
-  SpwSmem& sm = sm_all[threadIdx.x >> 5];
-  const FrameParams& F = *Fp;
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const uint32_t nhit = Q.counters[Q_HIT];
-  const uint32_t nwarps = gridDim.x * 4u, warp = blockIdx.x * 4u + (threadIdx.x >> 5);
-  const uint32_t k = F.spatialNeighbors;                      // <= SPW_K (launch_spatial)
-  const float radius = F.spatialRadius;
-  const float pre_a = gmax(0.001f, F.roughness * F.roughness);                                       // disneyBRDF.glsl:53
-
-  for (uint32_t g0 = warp * 32u; g0 < nhit; g0 += nwarps * 32u) {
-    const bool pix = g0 + (uint32_t)lane < nhit;
-    // ---------------- phase 1: lane = pixel
-    uint32_t idx = 0, seed = 0, nacc = 0;
-    Res res = newReservoir();
-    GInfo gi; ShadePre pre;
-    gi.worldPos = gi.normal = gi.camPos = v3(0.f, 0.f, 0.f); gi.albedoLum = 0.f; gi.roughness = F.roughness; gi.metallic = F.metallic;
-    gi.albedo[0] = gi.albedo[1] = gi.albedo[2] = gi.albedo[3] = 0.f; gi.sampleSeed = 0;
-    pre.wo = v3(0.f, 0.f, 0.f); pre.cosOut = pre.fresnelOut = pre.smithOut = 0.f; pre.a = pre_a;
-    if (pix) {
-      idx = Q.hit_pix[g0 + (uint32_t)lane];
-      const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
-      seed = pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_SPATIAL0 + iteration);             // :58-59
-      res = unpackReservoir(inR.info[idx], inR.weight[idx]);
-      gi = ginfo_from_planes(cur, idx, F);
-      pre = shade_pre(gi);
-      uint32_t sO = seed;                                                           // the 2k offset draws come first:
-      for (uint32_t i = 0; i < 2u * k; ++i) lcg(seed);                              // `seed` continues behind them with the selection draws
-      for (uint32_t i = 0; i < k; ++i) {
-        const float r1 = rnd(sO), r2 = rnd(sO);
-        const float dx = (r1 * 2.0f - 1.0f) * radius, dy = (r2 * 2.0f - 1.0f) * radius;
-        const int ox = int(dx), oy = int(dy);
-        const int nx = x + ox, ny = y + oy;
-        const bool inside = !(dx * dx + dy * dy > radius * radius) && !(ox == 0 && oy == 0) && nx >= 0 && ny >= 0 && nx < (int)F.W && ny < (int)F.H &&
-                            ny >= store_y0 && ny < store_y1;                          // (rows outside the ones held: halo too small)
-        // all planes of the neighbour are requested at once (from this pixel's own slot when the offset is rejected outright)
-        const size_t nidx = inside ? (size_t)(ny - store_y0) * F.W + (size_t)nx : (size_t)idx;
-        const float4 nwp = cur.worldPos[nidx], na = cur.albedo[nidx], nn = cur.normal[nidx], ri = inR.info[nidx], rw = inR.weight[nidx];
-        if (!inside) continue;
-        if (nwp.w < 0.5f) continue;
-        const V3 pd = sub(gi.worldPos, v3(nwp.x, nwp.y, nwp.z));
-        if (!(dot(pd, pd) < 0.01f)) continue;
-        const V3 ad = v3(gi.albedo[0] - na.x, gi.albedo[1] - na.y, gi.albedo[2] - na.z);
-        if (!(dot(ad, ad) < 0.01f)) continue;
-        if (!(dot(gi.normal, v3(nn.x, nn.y, nn.z)) > 0.5f)) continue;
-        sm.slot[nacc][lane] = make_uint4((uint32_t)nidx, __float_as_uint(ri.x), __float_as_uint(ri.y), __float_as_uint(rw.z));   // {pixel, M, lightIndex, w}
-        ++nacc;
-      }
-    }
-    // ---------------- pair bookkeeping: exclusive prefix of the accepted counts
-    uint32_t incl = nacc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(full, incl, o); if (lane >= o) incl += v; }
-    const uint32_t T = __shfl_sync(full, incl, 31);
-    sm.prefix[lane] = incl - nacc;
-    __syncwarp();
-    // ---------------- phase 2: lane = pair, p-hat of the neighbour's sample at the owner pixel (reservoir.glsl:62-63)
-    for (uint32_t q0 = 0; q0 < T; q0 += 32u) {
-      const uint32_t q = q0 + (uint32_t)lane;
-      const bool act = q < T;
-      uint32_t o = 0;
-#pragma unroll
-      for (uint32_t st = 16u; st > 0u; st >>= 1) if (sm.prefix[o + st] <= q) o += st;                 // last lane whose pairs start at or before q
-      if (!act) o = (uint32_t)lane;
-      GInfo g; ShadePre pp;
-      g.worldPos = v3(__shfl_sync(full, gi.worldPos.x, o), __shfl_sync(full, gi.worldPos.y, o), __shfl_sync(full, gi.worldPos.z, o));
-      g.normal = v3(__shfl_sync(full, gi.normal.x, o), __shfl_sync(full, gi.normal.y, o), __shfl_sync(full, gi.normal.z, o));
-      g.albedoLum = __shfl_sync(full, gi.albedoLum, o); g.roughness = F.roughness; g.metallic = F.metallic;
-      pp.wo = v3(__shfl_sync(full, pre.wo.x, o), __shfl_sync(full, pre.wo.y, o), __shfl_sync(full, pre.wo.z, o));
-      pp.fresnelOut = __shfl_sync(full, pre.fresnelOut, o); pp.smithOut = __shfl_sync(full, pre.smithOut, o); pp.a = pre_a; pp.cosOut = 0.0f;
-      if (act) {
-        const uint32_t j = q - sm.prefix[o];
-        const uint4 sl = sm.slot[j][o];
-        const float pHat = evaluatePHat(L, sl.z, g, pp);
-        sm.pHat[j][o] = pHat;
-        sm.weight[j][o] = pHat * __uint_as_float(sl.w) * float(sl.y);                                  // reservoir.glsl:63
-      }
-    }
-    __syncwarp();
-    // ---------------- phase 3: lane = pixel, reservoir.glsl:61-68 in neighbour order
-    uint32_t Z = res.M;
-    int selj = -1;
-    for (uint32_t j = 0; j < nacc; ++j) {
-      res.M += sm.slot[j][lane].y;
-      const float weight = sm.weight[j][lane];
-      if (weight > 0.0f) {
-        res.sumWeights += weight;
-        const float replacePossibility = weight / res.sumWeights;
-        if (rnd(seed) < replacePossibility) selj = (int)j;
-      }
-    }
-    if (selj >= 0) {
-      const uint4 sl = sm.slot[selj][lane];
-      const float4 ni = inR.info[sl.x];                                                                // lightKind, sampleSeed of the selected neighbour
-      res.lightIndex = sl.z; res.lightKind = __float_as_int(ni.z); res.pHat = sm.pHat[selj][lane]; res.w = __uint_as_float(sl.w); res.sampleSeed = __float_as_uint(ni.w);
-    }
-    const uint32_t finalLight = res.lightIndex;
-    __syncwarp();
-    // ---------------- phase 4: lane = pair, the selected light seen from the neighbour (reservoir.glsl:70-73)
-    for (uint32_t q0 = 0; q0 < T; q0 += 32u) {
-      const uint32_t q = q0 + (uint32_t)lane;
-      const bool act = q < T;
-      uint32_t o = 0;
-#pragma unroll
-      for (uint32_t st = 16u; st > 0u; st >>= 1) if (sm.prefix[o + st] <= q) o += st;
-      if (!act) o = (uint32_t)lane;
-      const uint32_t fl = __shfl_sync(full, finalLight, o);
-      if (act) {
-        const uint32_t j = q - sm.prefix[o];
-        const GInfo ng = ginfo_from_planes(cur, sm.slot[j][o].x, F);
-        const float pHat = evaluatePHat(L, fl, ng);
-        sm.weight[j][o] = pHat > 0.0f ? 1.0f : 0.0f;
-      }
-    }
-    __syncwarp();
-    // ---------------- phase 5: lane = pixel
-    if (pix) {
-      if (nacc > 0) {
-        for (uint32_t j = 0; j < nacc; ++j) if (sm.weight[j][lane] != 0.0f) Z += sm.slot[j][lane].y;
-        if (res.w > 0.0f) res.w = res.sumWeights / (float(Z) * res.pHat);                              // :74-75
-      }
-      float4 a, b; packReservoir(res, a, b);
-      outR.info[idx] = a; outR.weight[idx] = b;
-    }
-    __syncwarp();
-  }
-}
-
 // -------------------------------------------------------------------------------------------------
 // Final shade — restir_post.frag main (:57-105): shade, emissive override, firefly clamp, running mean.
 // Every pixel; a miss pixel costs its worldPos read (16 B) and the accumulation update only.
@@ -1039,10 +888,9 @@ void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, P
                     uint32_t iteration, uint32_t spatial_neighbors, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt) {
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   static const int target_warps = sms * (getenv("VRS_MIN_WARPS_PER_SM") ? atoi(getenv("VRS_MIN_WARPS_PER_SM")) : MIN_WARPS_PER_SM);
-  static const int g8 = resident_grid(k_spatial_thread<8>, 128, 8), gw = resident_grid(k_spatial_warp, 128, 6);
-  static const bool thread_form = getenv("VRS_SPATIAL") && getenv("VRS_SPATIAL")[0] == 't';
-  if (!thread_form && spatial_neighbors <= (uint32_t)SPW_K) k_spatial_warp<<<gw, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1);
-  else k_spatial_thread<8><<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
+  static const int g8 = resident_grid(k_spatial_thread<8>, 128, 8);
+  (void)spatial_neighbors;
+  k_spatial_thread<8><<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
   ktick(kt, s, "k_spatial");
 }
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, ResPlanes rs,
