@@ -150,6 +150,26 @@ def build_scene_inputs(V, wl, R):
                         lambda n: R.collectEmissiveLights(0.85 * gi.max_density, n))
 
 
+def measured_reach_rows(V, wl, path, device, frames=61, q=4):
+    """How far (rows) the temporal reprojection of actual hit points moves on this orbit, measured: the orbit rendered at 1/q
+    resolution with temporal reuse on, the library's temporal_reach_rows counter scaled back up, plus 15 % and 8 rows.  Tighter
+    than the bounding-box bound of temporal_halo_rows (hits sit inside the box), which lets cost-balanced bands get thinner."""
+    W, H = wl["W"], wl["H"]
+    P = V.Renderer(max(W // q, 16), max(H // q, 16), spatial_iterations=0, device=device)
+    P.loadVDB(path)
+    lights, ctr, diag = build_scene_inputs(V, wl, P)
+    P.createRestirLights(lights[:1])
+    P.m_restirUniforms.initialLightSampleCount, P.m_restirUniforms.flags = 1, 2
+    P.CameraManip.setLookat(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, 0.0), ctr)
+    P.createRestirUniformBuffer()
+    for f in range(frames):
+        P.CameraManip.setLookat(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, ORBIT_DEG * f), ctr)
+        P.renderFrame(clock=f)
+    rows = P.counters().temporal_reach_rows
+    P.destroy()
+    return int(math.ceil((rows + 1) * q * 1.15)) + 8
+
+
 def temporal_halo_rows(V, wl, lo, hi, ctr, diag, frames=60, minimum=32):
     """Rows a band must keep above / below itself so that the temporal reprojection of any point of the grid's bounding box
     stays inside them on this camera orbit: max |row(prevVP p) - row(curVP p)| over a lattice of the box, plus a margin.
@@ -172,10 +192,13 @@ def temporal_halo_rows(V, wl, lo, hi, ctr, diag, frames=60, minimum=32):
     return max(minimum, (need + 7) // 8 * 8)
 
 
-def balanced_bands(V, wl, path, world, device):
-    """Per-row cost model for screen-space bands of equal estimated cost instead of equal height: a quarter-resolution
-    probe frame (rendered by every rank on its own GPU, bit-identical everywhere) gives the per-row count of
-    volume-hitting pixels; cost(row) = hits + 2.5 % of the pixels."""
+PROBE_ANGLES = tuple(float(a) for a in range(0, 360, 30))       # orbit positions the band balancer looks at
+
+
+def row_costs(V, wl, path, device):
+    """Per-row cost model at several orbit positions: a quarter-resolution probe frame per position (rendered by every rank on
+    its own GPU, bit-identical everywhere) gives the per-row count of volume-hitting pixels; cost(row) = hits + 2.5 % of the
+    pixels.  Returns an array [angle][row] at full resolution."""
     W, H = wl["W"], wl["H"]
     q = 4
     w4, h4 = max(W // q, 16), max(H // q, 16)
@@ -184,23 +207,29 @@ def balanced_bands(V, wl, path, world, device):
     lights, ctr, diag = build_scene_inputs(V, wl, P)
     P.createRestirLights(lights[:1])
     P.m_restirUniforms.initialLightSampleCount, P.m_restirUniforms.flags = 1, 0
-    hits = np.zeros(h4, np.float64)
-    for ang in (0.0, 90.0, 180.0, 270.0):
+    out = []
+    for ang in PROBE_ANGLES:
         P.CameraManip.setLookat(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, ang), ctr)
         P.createRestirUniformBuffer()
         P.renderFrame(clock=int(ang))
-        hits += P.readGBuffer()["worldPos"][..., 3].sum(1)
+        hits = P.readGBuffer()["worldPos"][..., 3].sum(1).astype(np.float64)
+        cost = np.repeat(hits, q)[:H] * q + 0.025 * W         # per full-resolution row (ncu: ~1.6 ns per hit, ~0.04 ns per pixel)
+        if len(cost) < H:
+            cost = np.concatenate([cost, np.full(H - len(cost), cost[-1])])
+        out.append(cost)
     P.destroy()
-    cost = np.repeat(hits / 4.0, q)[:H] * q + 0.025 * W         # per full-resolution row (ncu: ~1.6 ns per hit, ~0.04 ns per pixel)
-    if len(cost) < H:
-        cost = np.concatenate([cost, np.full(H - len(cost), cost[-1])])
-    return cost
+    return np.stack(out)
 
 
 def split_rows(cost, world, min_rows=32):
-    """Band edges that give every rank the same share of the per-row cost (bands keep at least `min_rows` rows = the halo)."""
-    H = len(cost)
-    cum = np.concatenate([[0.0], np.cumsum(cost)])
+    """Band edges for `world` ranks, every band at least `min_rows` tall.  `cost` is [row] or [position][row]: the bands first
+    get equal shares of the summed cost, then (several positions) the interior edges move to minimise the sum over the
+    positions of the slowest band's cost — frames advance in lock step with the slowest band, so what counts is the maximum
+    per frame, not the average load."""
+    cost = np.atleast_2d(np.asarray(cost, np.float64))
+    H = cost.shape[1]
+    tot = cost.sum(0)
+    cum = np.concatenate([[0.0], np.cumsum(tot)])
     edges = [0]
     for r in range(1, world):
         y = int(np.searchsorted(cum, cum[-1] * r / world))
@@ -210,15 +239,36 @@ def split_rows(cost, world, min_rows=32):
         edges[r] = max(edges[r], edges[r - 1] + min_rows)
     for r in range(world - 1, 0, -1):
         edges[r] = min(edges[r], edges[r + 1] - min_rows)
+    if cost.shape[0] > 1 and world > 1:
+        cums = np.concatenate([np.zeros((cost.shape[0], 1)), np.cumsum(cost, 1)], 1)
+
+        def objective(e):
+            return float(np.max(cums[:, e[1:]] - cums[:, e[:-1]], axis=1).sum())
+
+        best = objective(np.array(edges))
+        step = max(H // (8 * world), 1)
+        while step >= 1:
+            improved = False
+            for r in range(1, world):
+                for d in (-step, step):
+                    e = list(edges)
+                    e[r] += d
+                    if e[r] - e[r - 1] < min_rows or e[r + 1] - e[r] < min_rows:
+                        continue
+                    v = objective(np.array(e))
+                    if v < best * (1.0 - 1e-9):
+                        best, edges, improved = v, e, True
+            if not improved:
+                step //= 2
     return [(edges[r], edges[r + 1]) for r in range(world)]
 
 
-def calibrated_bands(V, wl, path, world, rank, device, dist, halo, min_rows, rounds=3, frames=12):
+def calibrated_bands(V, wl, path, world, rank, device, dist, halo, min_rows, rounds=3):
     """Start from the hit-count model, then correct it with measurements: every rank renders its band (no exchange, timing
-    only) for a few frames, the per-band times are all-gathered and turned into a per-band correction of the row costs.
-    Which rows a rank renders never changes a pixel (tests/test_gpu_multi.py); only the load balance does."""
+    only) at the probe positions of the orbit, the per-band times are all-gathered and turned into a per-band correction of
+    the row costs.  Which rows a rank renders never changes a pixel (tests/test_gpu_multi.py); only the load balance does."""
     import torch
-    cost = balanced_bands(V, wl, path, world, device)
+    cost = row_costs(V, wl, path, device)
     bands = split_rows(cost, world, min_rows)
     for _ in range(rounds):
         band = bands[rank]
@@ -231,22 +281,23 @@ def calibrated_bands(V, wl, path, world, rank, device, dist, halo, min_rows, rou
         R.CameraManip.setLookat(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, 0.0), ctr)
         R.createRestirUniformBuffer()
         R.setPassTiming(True)
-        tot = 0.0
-        for f in range(frames):
-            R.CameraManip.setLookat(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, 30.0 * f), ctr)     # spread over the orbit
-            R.renderFrame(clock=f)
-            if f >= 2:
-                tot += R.timings().frame_ms
+        times = np.zeros(len(PROBE_ANGLES))
+        for rep in range(2):                                      # first sweep warms up (graphs, caches)
+            for i, ang in enumerate(PROBE_ANGLES):
+                R.CameraManip.setLookat(orbit_eye(ctr, ORBIT_RADIUS * diag, 0.0, ang), ctr)
+                R.renderFrame(clock=i)
+                if rep == 1:
+                    times[i] = R.timings().frame_ms
         R.destroy()
-        t = torch.tensor([tot / (frames - 2)], device="cuda", dtype=torch.float64)
+        t = torch.tensor(times, device="cuda", dtype=torch.float64)
         allt = [torch.zeros_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
-        times = np.array([float(x[0]) for x in allt])
-        model = np.array([cost[b[0]:b[1]].sum() for b in bands])
-        corr = times / np.maximum(model, 1e-30)
+        meas = np.stack([x.cpu().numpy() for x in allt])                                    # [rank][position]
+        model = np.stack([cost[:, b[0]:b[1]].sum(1) for b in bands])                        # [rank][position]
+        corr = meas.sum(1) / np.maximum(model.sum(1), 1e-30)
         corr = corr / corr.mean()
         for (y0, y1), c in zip(bands, corr):
-            cost[y0:y1] *= 0.5 * (1.0 + c)                                               # damped
+            cost[:, y0:y1] *= 0.5 * (1.0 + c)                                               # damped
         bands = split_rows(cost, world, min_rows)
     return bands
 
@@ -313,6 +364,8 @@ def run_ours(args):
         # band (which therefore must be at least that tall), halo rows only serve spatial reuse (radius 30).  NCCL: they must
         # be shipped, the halo is that tall.
         reach = temporal_halo_rows(V, wl, lo, hi, ctr0, diag0) if wl["flags"] & 2 else 32
+        if wl["flags"] & 2:
+            reach = max(32, min(reach, (measured_reach_rows(V, wl, path, local) + 7) // 8 * 8))     # same on every rank (deterministic render)
         halo = reach if args.exchange == "nccl" else 32
     bands = calibrated_bands(V, wl, path, world, rank, local, dist, halo, reach) if world > 1 else [(0, H)]
     band = bands[rank] if world > 1 else None
@@ -546,7 +599,7 @@ def run_ours(args):
             "metric": "ReSTIR frames/s", "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_desc(wl),
             "config": config_of(wl, args.workload),
-            "partition": ("cost-balanced bands (hit-count model corrected by 3 timed calibration rounds) x%d %s, halo %d rows, temporal reach %d rows (%s)"
+            "partition": ("bands minimising the slowest band's cost over 12 orbit positions (hit-count model corrected by 3 timed calibration rounds) x%d %s, halo %d rows, temporal reach %d rows (%s)"
                           % (world, [b[1] - b[0] for b in bands], halo, reach,
                              "shipped as halo rows" if args.exchange == "nccl" else "read in place from the adjacent band over NVLink")) if world > 1 else "single GPU",
             "repetitions_ms_per_step": [round(r_, 5) for r_ in reps], "timed_region_s": round(sum(reps) * args.steps / 1e3, 3),

@@ -217,8 +217,9 @@ void*      vrs_stream(vrs_ctx* ctx);                                            
 /* Work counters of the last frame (valid after vrs_synchronize) and the cumulative health counters of the halo exchange:
  * temporal_out_of_halo = hit pixels whose temporal reprojection fell on a row of the image this context does not store
  * (halo_rows too small for the camera motion: those merges were skipped, the frame differs from a single-GPU frame);
- * comm_timeouts = halo waits that gave up (a neighbour never published its rows). */
-typedef struct { uint32_t candidates, hits, shadow_rays, temporal_out_of_halo, comm_timeouts; } vrs_counters;
+ * comm_timeouts = halo waits that gave up (a neighbour never published its rows); temporal_reach_rows = the largest vertical
+ * distance (rows) any temporal reprojection has moved so far — what a launcher sizes band heights / halos from. */
+typedef struct { uint32_t candidates, hits, shadow_rays, temporal_out_of_halo, comm_timeouts, temporal_reach_rows; } vrs_counters;
 vrs_status vrs_get_counters(vrs_ctx* ctx, vrs_counters* out);
 /* Per-kernel CUDA-event times of the last frame.  While enabled, frames are launched kernel by kernel (no CUDA graph)
  * with an event after every kernel on the context stream; meant for a short probe next to the timed loops. */

@@ -94,6 +94,12 @@ def test_counters(V):
     c = R.counters()
     hit = int((R.readGBuffer()["worldPos"][..., 3] > 0.5).sum())
     assert c.hits == hit and c.candidates >= hit and c.shadow_rays <= hit and c.temporal_out_of_halo == 0 and c.comm_timeouts == 0
+    assert c.temporal_reach_rows == 0                                    # no temporal pass ran yet
+    R.m_restirUniforms.flags = 1 | 2
+    for f in range(1, 4):                                                # orbit: the reprojection moves rows, the counter records how far
+        R.CameraManip.setLookat(common.orbit_eye(ctr, 1.4 * diag, 0.0, 12.0 * f), ctr)
+        R.renderFrame(clock=f)
+    assert 0 < R.counters().temporal_reach_rows < 72
     R.setKernelTiming(True)
     R.renderFrame(clock=1)
     kt = R.kernelTimes()

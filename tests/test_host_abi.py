@@ -185,6 +185,14 @@ def test_bench_row_split_balances_cost_and_keeps_halo():
         assert shares.max() / shares.mean() < 1.15
     flat = bench.split_rows(np.zeros(H) + 1e-9, 8)                    # degenerate cost: still a valid partition
     assert flat[0][0] == 0 and flat[-1][1] == H and all(b[1] - b[0] >= 32 for b in flat)
+    # several camera positions: the bump moves; the split minimises the per-position maximum, never worse than the average split
+    costs = np.stack([1.0 + 50.0 * np.exp(-((y - c) / 120.0) ** 2) for c in (450.0, 600.0, 750.0)])
+    for world in (2, 4, 8):
+        avg = bench.split_rows(costs.sum(0), world, 48)
+        opt = bench.split_rows(costs, world, 48)
+        worst = lambda bands: sum(max(c[b[0]:b[1]].sum() for b in bands) for c in costs)
+        assert opt[0][0] == 0 and opt[-1][1] == H and all(b[1] == n[0] for b, n in zip(opt, opt[1:])) and all(b[1] - b[0] >= 48 for b in opt)
+        assert worst(opt) <= worst(avg) * (1.0 + 1e-9)
 
 
 def test_bench_issue_roofline_helper():

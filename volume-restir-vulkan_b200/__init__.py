@@ -95,7 +95,7 @@ class Timings(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("candidates", C.c_uint32), ("hits", C.c_uint32), ("shadow_rays", C.c_uint32),
-                ("temporal_out_of_halo", C.c_uint32), ("comm_timeouts", C.c_uint32)]
+                ("temporal_out_of_halo", C.c_uint32), ("comm_timeouts", C.c_uint32), ("temporal_reach_rows", C.c_uint32)]
 
 
 class KernelTime(C.Structure):

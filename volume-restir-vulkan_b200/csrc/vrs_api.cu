@@ -1162,6 +1162,7 @@ vrs_status vrs_get_counters(vrs_ctx* ctx, vrs_counters* out) {
   out->candidates = q[0]; out->hits = q[1]; out->shadow_rays = q[2];
   out->temporal_out_of_halo = x[5];
   out->comm_timeouts = ctx->comm_timeouts + x[4];
+  out->temporal_reach_rows = x[6];
   return VRS_OK;
 }
 

@@ -561,6 +561,12 @@ __global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FramePa
       q[1] = (q[1] + 1.0f) * 0.5f * float(F.H);
       if (q[0] > 0.0f && q[1] > 0.0f && q[0] < float(F.W) && q[1] < float(F.H)) {
         int fx = int(q[0]), fy = int(q[1]);
+        {   // how far the reprojection moved vertically (launchers size bands / halos from it: vrs_get_counters)
+          const int dyr = abs(fy - ((int)(idx / F.W) + store_y0));
+          const unsigned am = __activemask();
+          const int mx = __reduce_max_sync(am, dyr);
+          if ((threadIdx.x & 31) == __ffs(am) - 1) atomicMax(out_of_halo + 1, (unsigned)mx);
+        }
         // Where the previous frame's pixel lives: in this context's own rows, or (several GPUs, peer memory) in the band of the
         // neighbour above / below, read in place over NVLink — only the few pixels whose reprojection crosses a band edge pay
         // that latency, and no halo rows have to be shipped for the temporal pass.
