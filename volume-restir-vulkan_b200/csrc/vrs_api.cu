@@ -23,18 +23,19 @@
 using namespace vrs;
 
 #define VRS_PARAM_SLOTS 8
-// Frames in flight (the reference keeps 2-3 swapchain images in flight, nvvk/appbase_vk.cpp:412-418): the front half of
-// frame n+1 (coverage, classification, primary event, RIS, shadow rays: nothing in it reads the previous frame) runs on its
-// own stream while the back half of frame n (temporal merge, spatial reuse, shade, halo exchanges) is still executing.
-// Buffers are sized for that: 4 G-buffers (frame n writes n % 4 and reads (n - 1) % 4 as "previous"), 4 pairs of reservoir
-// buffers (frame n ping-pongs inside pair n % 4 and reads the final one of frame n - 1), 2 sets of work queues and 2 device
-// parameter blocks (n % 2).  front(n) waits for back(n - 2), back(n) for front(n) and, by stream order, back(n - 1).
-// (Three of each would do for one GPU.  The fourth covers several GPUs: a neighbour reads this context's frame n - 1 planes in
-// place during ITS temporal pass of frame n, and this context's front(n + 3) — the first writer of those planes with four
-// buffers — cannot start before its back(n + 1), whose first phase waits for the flag that neighbour publishes after that pass.)
-#define VRS_NG 4
-#define VRS_NR 8
-#define VRS_NQ 2
+// Frames in flight (the reference keeps 2-3 swapchain images in flight, nvvk/appbase_vk.cpp:412-418).  A frame is three
+// stages on three streams: A (coverage, classification, primary event, hit list), B (RIS candidates, shadow rays) — nothing in
+// A or B reads the previous frame — and the back half (temporal merge, spatial reuse, shade, halo exchanges).  A(n + 2), B(n + 1)
+// and back(n) may execute at the same time; each kernel's ramp and tail is filled by the other stages' kernels.
+// Buffers are sized for that: 5 G-buffers (frame n writes n % 5 and reads (n - 1) % 5 as "previous"), 5 pairs of reservoir
+// buffers (frame n ping-pongs inside pair n % 5 and reads the final one of frame n - 1), 3 sets of work queues and 3 device
+// parameter blocks (n % 3).  A(n) waits for back(n - 3), B(n) for A(n), back(n) for B(n) and, by stream order, back(n - 1).
+// (Four G-buffers / pairs would do for one GPU.  The fifth covers several GPUs: a neighbour reads this context's frame n - 1
+// planes in place during ITS temporal pass of frame n, and this context's A(n + 4) — the first writer of those planes — cannot
+// start before its back(n + 1), whose first phase waits for the flag that neighbour publishes after that pass.)
+#define VRS_NG 5
+#define VRS_NR 10
+#define VRS_NQ 3
 struct GraphEntry { cudaGraphExec_t exec = nullptr; uint32_t launches = 0; };
 struct FrameIdx { int g = 0, gprev = 0, ra = 0, rb = 0, q = 0; };
 
@@ -57,9 +58,11 @@ struct vrs_ctx {
   int final_r = 0;                       // final reservoirs of the last completed frame (temporal input of the next)
   int src_r = 0;                         // most recently written reservoir buffer inside the frame
   int last_q = 0;                        // queue set of the last frame (vrs_get_counters)
-  cudaStream_t front_stream = nullptr;   // front halves run here (frames in flight)
-  cudaEvent_t ev_front_done[VRS_NQ] = {nullptr}, ev_back_done[VRS_NQ] = {nullptr};
-  bool back_recorded[VRS_NQ] = {false, false};
+  cudaStream_t front_stream = nullptr;   // stage A runs here (frames in flight)
+  cudaStream_t mid_stream = nullptr;     // stage B
+  cudaEvent_t ev_front_done[VRS_NQ] = {nullptr}, ev_mid_done[VRS_NQ] = {nullptr}, ev_back_done[VRS_NQ] = {nullptr};
+  bool back_recorded[VRS_NQ] = {false, false, false};
+  int depth = 3;                         // stages that may overlap: 3 = A | B | back, 2 = A+B | back, 1 = none (VRS_PIPELINE)
   bool halo_pending = false;             // a halo push has been enqueued whose consumer-side wait has not
   bool pipeline = true;
   bool replaying = false;                 // a captured half is being replayed: bodies only advance host-side state
@@ -170,7 +173,7 @@ static vrs_status alloc_frame_buffers(vrs_ctx* ctx) {
   }
   for (int i = 0; i < 2; ++i) if (!alloc((void**)&ctx->display[i], ctx->npix * 4)) return VRS_ERR_CUDA;
   ctx->frame_no = 0; ctx->cur = FrameIdx(); ctx->last_g = ctx->final_r = ctx->src_r = ctx->last_q = 0;
-  ctx->back_recorded[0] = ctx->back_recorded[1] = false;
+  for (int i = 0; i < VRS_NQ; ++i) ctx->back_recorded[i] = false;
   ctx->halo_pending = false;
   ctx->present_count = 0;
   ctx->history_valid = false;
@@ -193,11 +196,14 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
     return cudaMemset(*p, 0, bytes) == cudaSuccess;
   };
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->front_stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
+      cudaStreamCreateWithFlags(&ctx->front_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->mid_stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
   for (int i = 0; i < VRS_NQ; ++i)
     if (cudaEventCreateWithFlags(&ctx->ev_front_done[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_mid_done[i], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_back_done[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
   ctx->pipeline = !(getenv("VRS_PIPELINE") && getenv("VRS_PIPELINE")[0] == '0');
+  ctx->depth = getenv("VRS_PIPELINE") && getenv("VRS_PIPELINE")[0] == '2' ? 2 : 3;
   if (vrs_status s = alloc_frame_buffers(ctx)) return bail(s);
   {
     cudaDeviceProp prop;
@@ -225,6 +231,7 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
 
 static void invalidate_graphs(vrs_ctx* ctx) {
   if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
+  if (ctx->mid_stream) cudaStreamSynchronize(ctx->mid_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   ctx->graphs.clear(); ctx->seen.clear();
@@ -239,9 +246,14 @@ void vrs_destroy(vrs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
+  if (ctx->mid_stream) cudaStreamSynchronize(ctx->mid_stream);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) comm_destroy(ctx->comm);
-  for (int i = 0; i < VRS_NQ; ++i) { if (ctx->ev_front_done[i]) cudaEventDestroy(ctx->ev_front_done[i]); if (ctx->ev_back_done[i]) cudaEventDestroy(ctx->ev_back_done[i]); }
+  for (int i = 0; i < VRS_NQ; ++i) {
+    if (ctx->ev_front_done[i]) cudaEventDestroy(ctx->ev_front_done[i]);
+    if (ctx->ev_mid_done[i]) cudaEventDestroy(ctx->ev_mid_done[i]);
+    if (ctx->ev_back_done[i]) cudaEventDestroy(ctx->ev_back_done[i]);
+  }
   for (vrs_ctx::Peer* p : {&ctx->peer_up, &ctx->peer_down}) for (void* q : p->opened) cudaIpcCloseMemHandle(q);
   cudaFree(ctx->xflags);
   free_grid(ctx);
@@ -261,6 +273,7 @@ void vrs_destroy(vrs_ctx* ctx) {
   if (ctx->ev_halo_src) cudaEventDestroy(ctx->ev_halo_src);
   if (ctx->ev_halo_done) cudaEventDestroy(ctx->ev_halo_done);
   if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
+  if (ctx->mid_stream) cudaStreamDestroy(ctx->mid_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -349,6 +362,7 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
       attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
       cudaStreamSetAttribute(ctx->front_stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaStreamSetAttribute(ctx->mid_stream, cudaStreamAttributeAccessPolicyWindow, &attr);
       cudaGetLastError();       // best effort: the window is an optimisation, never an error
     }
   }
@@ -677,14 +691,25 @@ static bool culling_on(vrs_ctx* ctx, const FrameParams& F) {
 //   iters + 1     shade; on several GPUs push what the next frame's temporal reprojection reads (all halo rows)
 // A phase never waits for a push of the same phase, so phases of several contexts may be interleaved by one host thread in
 // any order that keeps the phase number non-decreasing (vrs_render_frame_group).
-static vrs_status enqueue_front(vrs_ctx* ctx, const FrameParams& F, const FrameIdx& fi, cudaStream_t st) {
+static vrs_status enqueue_front_a(vrs_ctx* ctx, const FrameParams& F, const FrameIdx& fi, cudaStream_t st) {
   CK(mark(ctx, 0, st));
-  launch_initial_front(st, ctx->grid, ctx->lights, F, ctx->d_params + fi.q, planes_of(ctx, fi.g), res_of(ctx, fi.ra), ctx->queues[fi.q], ctx->trace,
-                       ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks, &ctx->kt);
+  launch_front_trace(st, ctx->grid, F, ctx->d_params + fi.q, planes_of(ctx, fi.g), ctx->queues[fi.q], ctx->trace,
+                     ctx->band_y0, ctx->band_y1, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks, &ctx->kt);
   CK(cudaGetLastError());
-  ctx->timings.launches += (uint32_t)initial_front_launches(F.flags, culling_on(ctx, F), ctx->lights);
+  ctx->timings.launches += (uint32_t)front_trace_launches(culling_on(ctx, F));
+  return VRS_OK;
+}
+static vrs_status enqueue_front_b(vrs_ctx* ctx, const FrameParams& F, const FrameIdx& fi, cudaStream_t st) {
+  launch_front_ris(st, ctx->grid, ctx->lights, F, ctx->d_params + fi.q, planes_of(ctx, fi.g), res_of(ctx, fi.ra), ctx->queues[fi.q], ctx->trace,
+                   ctx->store_y0, ctx->persistent_blocks, &ctx->kt);
+  CK(cudaGetLastError());
+  ctx->timings.launches += (uint32_t)front_ris_launches(F.flags, ctx->lights);
   ctx->src_r = fi.ra;
   return VRS_OK;
+}
+static vrs_status enqueue_front(vrs_ctx* ctx, const FrameParams& F, const FrameIdx& fi, cudaStream_t st) {
+  vrs_status s = enqueue_front_a(ctx, F, fi, st);
+  return s ? s : enqueue_front_b(ctx, F, fi, st);
 }
 static int back_phases(vrs_ctx* ctx, const FrameParams& F) {
   const bool spatial = (F.flags & VRS_RESTIR_SPATIAL_REUSE_FLAG) != 0 && ctx->cfg.spatial_iterations > 0;
@@ -760,11 +785,11 @@ static void finish_frame_state(vrs_ctx* ctx, const FrameIdx& fi) {
   ctx->history_valid = true;
 }
 
-// Graph cache: the launch sequence of a frame half depends only on the buffer rotation (frame_no % 4), on where the previous
+// Graph cache: the launch sequence of a stage depends only on the buffer rotation (frame_no % 15 = lcm of the ring lengths), on where the previous
 // frame left its final reservoirs, on the structural flags and on whether a halo push is pending.
 static uint64_t graph_key(vrs_ctx* ctx, const FrameParams& F, int half, bool want_temporal_push) {
-  uint64_t k = (uint64_t)(ctx->frame_no % 4) | ((uint64_t)(F.flags & 0x3f) << 6) | ((uint64_t)ctx->cfg.spatial_iterations << 12) |
-               ((uint64_t)(F.cull ? 1 : 0) << 16) | ((uint64_t)(ctx->pass_timing ? 1 : 0) << 17) | ((uint64_t)half << 19);
+  uint64_t k = (uint64_t)(ctx->frame_no % 15) | ((uint64_t)(F.flags & 0x3f) << 6) | ((uint64_t)ctx->cfg.spatial_iterations << 12) |
+               ((uint64_t)(F.cull ? 1 : 0) << 16) | ((uint64_t)(ctx->pass_timing ? 1 : 0) << 17) | ((uint64_t)half << 21);
   if (half == 1) k |= ((uint64_t)ctx->final_r << 3) | ((uint64_t)(ctx->peer_mode ? 1 : 0) << 15) | ((uint64_t)(ctx->halo_pending ? 1 : 0) << 18) |
                       ((uint64_t)(want_temporal_push ? 1 : 0) << 20);
   return k;
@@ -806,6 +831,7 @@ vrs_status vrs_pass_initial(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
   const FrameIdx fi = frame_idx(ctx->frame_no);
   ctx->cur = fi;
   CK(cudaStreamSynchronize(ctx->front_stream));          // the per-pass calls run on the main stream, strictly in order
+  CK(cudaStreamSynchronize(ctx->mid_stream));
   if ((s = upload_params(ctx, F, fi.q, ctx->stream))) return s;
   if ((s = enqueue_front(ctx, F, fi, ctx->stream))) return s;
   return enqueue_back_phase(ctx, F, fi, 0, false, ctx->stream);
@@ -839,22 +865,32 @@ vrs_status vrs_render_frame(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
   // NCCL send/recv under stream capture hangs here (NCCL 2.28.9): NCCL contexts launch eagerly.  Per-kernel timing and
   // per-pass timing want one stream with nothing overlapping the kernels they bracket.
   const bool eager = no_graph || ctx->comm || ctx->kt.on;
-  const bool overlap = ctx->pipeline && !ctx->kt.on && !ctx->pass_timing;
+  // (the diagnostic trace buffer is one per context, written by every stage: frames must not overlap while it is on)
+  const bool overlap = ctx->pipeline && !ctx->kt.on && !ctx->pass_timing && !ctx->trace;
   const FrameIdx fi = frame_idx(ctx->frame_no);
   ctx->cur = fi;
   const bool want_temporal_push = (ru->flags & VRS_RESTIR_TEMPORAL_REUSE_FLAG) != 0;
-  cudaStream_t fs = overlap ? ctx->front_stream : ctx->stream;
+  cudaStream_t sa = overlap ? ctx->front_stream : ctx->stream;
+  cudaStream_t sb = overlap ? (ctx->depth >= 3 ? ctx->mid_stream : ctx->front_stream) : ctx->stream;
   if (ctx->kt.on) { ctx->kt.n = 0; CK(cudaEventRecord(ctx->kt.ev[0], ctx->stream)); }
-  // ---- front half: needs the queue set / parameter block / G-buffer that frame n - 2 (n - 3) used
-  if (overlap && ctx->back_recorded[fi.q]) CK(cudaStreamWaitEvent(fs, ctx->ev_back_done[fi.q], 0));
-  if ((s = upload_params(ctx, F, fi.q, fs))) return s;
-  if (eager) s = enqueue_front(ctx, F, fi, fs);
-  else s = run_captured(ctx, graph_key(ctx, F, 0, false), fs, [&]() -> vrs_status {
-    if (ctx->replaying) { ctx->src_r = fi.ra; return VRS_OK; }
-    return enqueue_front(ctx, F, fi, fs);
+  // ---- stage A: needs the queue set / parameter block that frame n - 3 used, and a G-buffer slot nobody reads any more
+  if (overlap && ctx->back_recorded[fi.q]) CK(cudaStreamWaitEvent(sa, ctx->ev_back_done[fi.q], 0));
+  if ((s = upload_params(ctx, F, fi.q, sa))) return s;
+  if (eager) s = enqueue_front_a(ctx, F, fi, sa);
+  else s = run_captured(ctx, graph_key(ctx, F, 0, false), sa, [&]() -> vrs_status {
+    if (ctx->replaying) return VRS_OK;
+    return enqueue_front_a(ctx, F, fi, sa);
   });
   if (s) return s;
-  if (overlap) { CK(cudaEventRecord(ctx->ev_front_done[fi.q], fs)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_front_done[fi.q], 0)); }
+  // ---- stage B
+  if (overlap && sb != sa) { CK(cudaEventRecord(ctx->ev_front_done[fi.q], sa)); CK(cudaStreamWaitEvent(sb, ctx->ev_front_done[fi.q], 0)); }
+  if (eager) s = enqueue_front_b(ctx, F, fi, sb);
+  else s = run_captured(ctx, graph_key(ctx, F, 2, false), sb, [&]() -> vrs_status {
+    if (ctx->replaying) { ctx->src_r = fi.ra; return VRS_OK; }
+    return enqueue_front_b(ctx, F, fi, sb);
+  });
+  if (s) return s;
+  if (overlap) { CK(cudaEventRecord(ctx->ev_mid_done[fi.q], sb)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_mid_done[fi.q], 0)); }
   // ---- back half
   const int nph = back_phases(ctx, F);
   auto back = [&]() -> vrs_status {
@@ -892,6 +928,7 @@ vrs_status vrs_render_frame_group(vrs_ctx** ctxs, uint32_t n, const vrs_global_u
     ctx->timings.launches = 0;
     fi[i] = frame_idx(ctx->frame_no); ctx->cur = fi[i];
     CK(cudaStreamSynchronize(ctx->front_stream));
+    CK(cudaStreamSynchronize(ctx->mid_stream));
     if ((s = upload_params(ctx, F[i], fi[i].q, ctx->stream))) return s;
     if ((s = enqueue_front(ctx, F[i], fi[i], ctx->stream))) return s;
   }
@@ -911,6 +948,7 @@ vrs_status vrs_synchronize(vrs_ctx* ctx) {
   if (!ctx) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
   CK(cudaStreamSynchronize(ctx->front_stream));
+  CK(cudaStreamSynchronize(ctx->mid_stream));
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->comm_stream) CK(cudaStreamSynchronize(ctx->comm_stream));
   if (ctx->peer_mode) {          // did a halo wait give up?  (k_halo_wait sets xflags[4]; stale halo rows must not pass as VRS_OK)
@@ -1046,7 +1084,7 @@ vrs_status vrs_write_image(vrs_ctx* ctx, const char* path) {
 }
 
 // ------------------------------------------------------------------------------------------ multi-GPU
-// ---- peer-memory exchange set-up: blob = { band_y0, band_y1, store_y0, store_y1 (int32) | 33 x cudaIpcMemHandle_t }
+// ---- peer-memory exchange set-up: blob = { band_y0, band_y1, store_y0, store_y1 (int32) | 41 x cudaIpcMemHandle_t }
 vrs_status vrs_peer_export(vrs_ctx* ctx, uint8_t blob[VRS_PEER_BLOB_BYTES]) {
   if (!ctx || !blob) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);

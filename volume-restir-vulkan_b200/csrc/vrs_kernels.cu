@@ -808,29 +808,25 @@ static int resident_grid(K kernel, int block_threads, int fallback_per_sm) {
 // ------------------------------------------------------------------------------------------------- launchers
 // `F` is the host copy (launch geometry, which kernels run); `dF` is the same struct in device memory, read by the
 // kernels — so that a captured CUDA graph of the frame stays valid while the per-frame values change.
-// Front half of the initial pass (everything that does not depend on the previous frame): coverage mask, classification,
-// primary volume event, hit list, RIS candidates, shadow rays.  Writes cur G-buffer, the tmp reservoir outR and the work
-// queues Q; the host runtime may run it concurrently with the back half of the previous frame (frames in flight).
-void launch_initial_front(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur,
-                          ResPlanes outR, const Queues& Q, uint32_t* trace, int y0, int y1, int store_y0, int store_y1, int persistent_blocks, KTimer* kt) {
-  // tuning knobs of the persistent raymarch kernels: idle lanes that trigger a refill | cell visits per scheduling decision << 8
-  // | warps that a small launch is spread over (lanes_for) << 16
+// Front of the initial pass (everything that does not depend on the previous frame), in two stages the host runtime may run
+// on different streams and overlap with other frames (frames in flight):
+//   stage A launch_front_trace  coverage mask, classification, primary volume event, hit list   -> work queues Q, hit scratch in cur.worldPos
+//   stage B launch_front_ris    RIS candidates (G-buffer + tmp reservoir outR), shadow rays       -> cur, outR, Q.hit_T / hit_seed
+static int march_refill() {
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   static const int target_warps = sms * (getenv("VRS_MIN_WARPS_PER_SM") ? atoi(getenv("VRS_MIN_WARPS_PER_SM")) : MIN_WARPS_PER_SM);
-  static const int ris_blocks = [] {   // one resident wave of the cooperative RIS kernel
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ris_coop, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-    if (getenv("VRS_RIS_BLOCKS_PER_SM")) per_sm = atoi(getenv("VRS_RIS_BLOCKS_PER_SM"));
-    return sms * per_sm;
-  }();
+  // tuning knobs of the persistent raymarch kernels: idle lanes that trigger a refill | cell visits per scheduling decision << 8
+  // | warps that a small launch is spread over (lanes_for) << 16
   static const int refill = (getenv("VRS_REFILL") ? atoi(getenv("VRS_REFILL")) : REFILL_MIN_IDLE) |
                             ((getenv("VRS_CELLS") ? atoi(getenv("VRS_CELLS")) : CELLS_PER_DECISION) << 8) | (target_warps << 16);
-  // RIS stage: t(hread) | c(oop) | a(uto).  Measured on B200 (profiles/r01_summary.md): with light tables that stay
-  // L1-resident the plain per-thread loop is fastest; once they spill to L2 (thousands of lights) the cooperative kernel,
-  // which keeps the dependent table fetches of several pixels in flight, wins.
-  static const char ris_env = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'a';
-  static const uint32_t small_launch = getenv("VRS_RIS_SMALL") ? (uint32_t)atoi(getenv("VRS_RIS_SMALL")) : RIS_SMALL_LAUNCH;
-  const bool big_tables = (size_t)L.nlights * 32 + (size_t)L.ntable * 16 > (size_t)64 * 1024;
+  return refill;
+}
+static bool simple_march() { static const bool v = getenv("VRS_MARCH") && getenv("VRS_MARCH")[0] == 's'; return v; }
+static int march_waves() { static const int v = getenv("VRS_MARCH_WAVES") ? atoi(getenv("VRS_MARCH_WAVES")) : 1; return v; }
+
+void launch_front_trace(cudaStream_t st, const GridDev& G, const FrameParams& F, const FrameParams* dF, Planes cur, const Queues& Q, uint32_t* trace,
+                        int y0, int y1, int store_y0, int store_y1, int persistent_blocks, KTimer* kt) {
+  const int refill = march_refill();
   cudaMemsetAsync(Q.counters, 0, 8 * sizeof(uint32_t), st);
   // screen-space coverage culling (k_cover); the RNG / cell trace of a culled ray would differ, so tracing turns it off
   static const bool no_cull = getenv("VRS_NO_CULL") != nullptr;
@@ -838,18 +834,17 @@ void launch_initial_front(cudaStream_t st, const GridDev& G, const LightsDev& L,
   const long long ncell = (long long)G.cdim[0] * G.cdim[1] * G.cdim[2];
   if (F.cull && !trace && !no_cull && Q.cover && ncell <= (1ll << 27)) {          // (8 threads per cell in a 32-bit grid index)
     tiles_x = ((int)F.W + COVER_TILE - 1) / COVER_TILE;
-    const int tiles_y = ((int)F.H + COVER_TILE - 1) / COVER_TILE;
     const int band_ty0 = y0 / COVER_TILE, band_ty1 = (y1 - 1) / COVER_TILE;
     cudaMemsetAsync(Q.cover + (size_t)band_ty0 * tiles_x, 0, (size_t)tiles_x * (band_ty1 - band_ty0 + 1), st);
+    const int tiles_y = ((int)F.H + COVER_TILE - 1) / COVER_TILE;
     k_cover<<<(unsigned)((ncell * 8 + 127) / 128), 128, 0, st>>>(G, dF, Q, tiles_x, tiles_y, band_ty0, band_ty1);
     ktick(kt, st, "k_cover");
   }
   dim3 block(32, 8), grid((F.W + 31) / 32, (y1 - y0 + 7) / 8);
   k_classify<<<grid, block, 0, st>>>(G, dF, cur, Q, trace, y0, y1, store_y0, tiles_x);
   ktick(kt, st, "k_classify");
-  static const bool simple_march = getenv("VRS_MARCH") && getenv("VRS_MARCH")[0] == 's';
-  static const int g_ps = resident_grid(k_primary_simple, 128, 8) * (getenv("VRS_MARCH_WAVES") ? atoi(getenv("VRS_MARCH_WAVES")) : 1), g_ss = resident_grid(k_shadow_simple, 128, 8) * (getenv("VRS_MARCH_WAVES") ? atoi(getenv("VRS_MARCH_WAVES")) : 1);
-  if (simple_march) k_primary_simple<<<g_ps, 128, 0, st>>>(G, dF, cur, Q, trace, store_y0);
+  static const int g_ps = resident_grid(k_primary_simple, 128, 8) * march_waves();
+  if (simple_march()) k_primary_simple<<<g_ps, 128, 0, st>>>(G, dF, cur, Q, trace, store_y0);
   else k_primary<<<persistent_blocks, 128, 0, st>>>(G, dF, cur, Q, trace, store_y0, refill);
   ktick(kt, st, "k_primary");
   // compaction runs over every stored row (8-byte aligned flag loads); flags outside the band rows stay 0
@@ -857,6 +852,25 @@ void launch_initial_front(cudaStream_t st, const GridDev& G, const LightsDev& L,
   const uint32_t nblocks = (uint32_t)((npix + COMPACT_BLOCK - 1) / COMPACT_BLOCK);
   k_hit_compact<<<nblocks, 256, 0, st>>>(Q.flag, npix, Q.counters, Q.hit_pix);
   ktick(kt, st, "k_hit_compact");
+}
+
+void launch_front_ris(cudaStream_t st, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur,
+                      ResPlanes outR, const Queues& Q, uint32_t* trace, int store_y0, int persistent_blocks, KTimer* kt) {
+  const int refill = march_refill();
+  const int target_warps = refill >> 16;
+  static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+  static const int ris_blocks = [] {   // one resident wave of the cooperative RIS kernel
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ris_coop, 128, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    if (getenv("VRS_RIS_BLOCKS_PER_SM")) per_sm = atoi(getenv("VRS_RIS_BLOCKS_PER_SM"));
+    return sms * per_sm;
+  }();
+  // RIS stage: t(hread) | c(oop) | a(uto).  Measured on B200 (profiles/r01_summary.md): with light tables that stay
+  // L1-resident the plain per-thread loop is fastest; once they spill to L2 (thousands of lights) the cooperative kernel,
+  // which keeps the dependent table fetches of several pixels in flight, wins.
+  static const char ris_env = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'a';
+  static const uint32_t small_launch = getenv("VRS_RIS_SMALL") ? (uint32_t)atoi(getenv("VRS_RIS_SMALL")) : RIS_SMALL_LAUNCH;
+  const bool big_tables = (size_t)L.nlights * 32 + (size_t)L.ntable * 16 > (size_t)64 * 1024;
   const bool vis = (F.flags & FLAG_VISIBILITY) != 0, temporal = (F.flags & FLAG_TEMPORAL) != 0;
   const int needs_finish = (vis || temporal) ? 1 : 0;
   static const int g_thread = resident_grid(k_ris_thread<8>, 128, 8);
@@ -868,7 +882,8 @@ void launch_initial_front(cudaStream_t st, const GridDev& G, const LightsDev& L,
   }
   ktick(kt, st, "k_ris");
   if (vis) {
-    if (simple_march) k_shadow_simple<<<g_ss, 128, 0, st>>>(G, Q);
+    static const int g_ss = resident_grid(k_shadow_simple, 128, 8) * march_waves();
+    if (simple_march()) k_shadow_simple<<<g_ss, 128, 0, st>>>(G, Q);
     else k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill);
     ktick(kt, st, "k_shadow");
   }
@@ -882,13 +897,14 @@ void launch_initial_finish(cudaStream_t st, const LightsDev& L, const FrameParam
   k_finish<<<g_finish, 128, 0, st>>>(L, dF, cur, prev, prevR, outR, Q, trace, store_y0, PA, out_of_halo);
   ktick(kt, st, "k_finish");
 }
-int initial_front_launches(int flags, bool culling, const LightsDev& L) {
+int front_trace_launches(bool culling) { return 3 /* classify, primary, compact */ + (culling ? 1 : 0); }
+int front_ris_launches(int flags, const LightsDev& L) {
   const bool vis = (flags & FLAG_VISIBILITY) != 0;
   // auto mode with small light tables launches both RIS forms (the device-side hit count decides which one works)
   const char ris_env = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'a';
   const bool big_tables = (size_t)L.nlights * 32 + (size_t)L.ntable * 16 > (size_t)64 * 1024;
   const int ris = (ris_env == 'a' && !big_tables) ? 2 : 1;
-  return 3 /* classify, primary, compact */ + ris + (culling ? 1 : 0) + (vis ? 1 : 0);
+  return ris + (vis ? 1 : 0);
 }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, uint32_t spatial_neighbors, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt) {
