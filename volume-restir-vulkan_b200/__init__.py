@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "libvrs.so")
 VISIBILITY_REUSE_FLAG, TEMPORAL_REUSE_FLAG, SPATIAL_REUSE_FLAG, USE_ENVIRONMENT_FLAG = 1, 2, 4, 8
 FINAL_VISIBILITY_FLAG, FINALIZE_W_FLAG = 16, 32
 
-PEER_BLOB_BYTES = 2688
+PEER_BLOB_BYTES = 3200
 
 STATUS = {0: "VRS_OK", 1: "VRS_ERR_INVALID", 2: "VRS_ERR_CUDA", 3: "VRS_ERR_IO", 4: "VRS_ERR_FORMAT",
           5: "VRS_ERR_UNSUPPORTED", 6: "VRS_ERR_COMM", 7: "VRS_ERR_NO_DEVICE"}

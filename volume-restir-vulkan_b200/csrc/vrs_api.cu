@@ -23,19 +23,20 @@
 using namespace vrs;
 
 #define VRS_PARAM_SLOTS 8
-// Frames in flight (the reference keeps 2-3 swapchain images in flight, nvvk/appbase_vk.cpp:412-418).  A frame is three
-// stages on three streams: A (coverage, classification, primary event, hit list), B (RIS candidates, shadow rays) — nothing in
-// A or B reads the previous frame — and the back half (temporal merge, spatial reuse, shade, halo exchanges).  A(n + 2), B(n + 1)
-// and back(n) may execute at the same time; each kernel's ramp and tail is filled by the other stages' kernels.
-// Buffers are sized for that: 5 G-buffers (frame n writes n % 5 and reads (n - 1) % 5 as "previous"), 5 pairs of reservoir
-// buffers (frame n ping-pongs inside pair n % 5 and reads the final one of frame n - 1), 3 sets of work queues and 3 device
-// parameter blocks (n % 3).  A(n) waits for back(n - 3), B(n) for A(n), back(n) for B(n) and, by stream order, back(n - 1).
-// (Four G-buffers / pairs would do for one GPU.  The fifth covers several GPUs: a neighbour reads this context's frame n - 1
-// planes in place during ITS temporal pass of frame n, and this context's A(n + 4) — the first writer of those planes — cannot
-// start before its back(n + 1), whose first phase waits for the flag that neighbour publishes after that pass.)
-#define VRS_NG 5
-#define VRS_NR 10
-#define VRS_NQ 3
+// Frames in flight (the reference keeps 2-3 swapchain images in flight, nvvk/appbase_vk.cpp:412-418).  A frame is four
+// stages on four streams: A (coverage, classification, primary event, hit list), B (RIS candidates), C (shadow rays) — nothing
+// in A, B or C reads the previous frame — and the back half (temporal merge, spatial reuse, shade, halo exchanges).  A(n + 3),
+// B(n + 2), C(n + 1) and back(n) may execute at the same time; each kernel's ramp and tail is filled by the other stages' kernels.
+// Buffers are sized for that: 6 G-buffers (frame n writes n % 6 and reads (n - 1) % 6 as "previous"), 6 pairs of reservoir
+// buffers (frame n ping-pongs inside pair n % 6 and reads the final one of frame n - 1), 4 sets of work queues and 4 device
+// parameter blocks (n % 4).  A(n) waits for back(n - 4), B(n) for A(n), C(n) for B(n), back(n) for C(n) and, by stream order,
+// back(n - 1).  (Five G-buffers / pairs would do for one GPU.  The sixth covers several GPUs: a neighbour reads this context's
+// frame n - 1 planes in place during ITS temporal pass of frame n, and this context's A(n + 5) — the first writer of those
+// planes — cannot start before its back(n + 1), whose first phase waits for the flag that neighbour publishes after that pass.)
+#define VRS_NG 6
+#define VRS_NR 12
+#define VRS_NQ 4
+#define VRS_NFRONT 3
 struct GraphEntry { cudaGraphExec_t exec = nullptr; uint32_t launches = 0; };
 struct FrameIdx { int g = 0, gprev = 0, ra = 0, rb = 0, q = 0; };
 
@@ -58,11 +59,10 @@ struct vrs_ctx {
   int final_r = 0;                       // final reservoirs of the last completed frame (temporal input of the next)
   int src_r = 0;                         // most recently written reservoir buffer inside the frame
   int last_q = 0;                        // queue set of the last frame (vrs_get_counters)
-  cudaStream_t front_stream = nullptr;   // stage A runs here (frames in flight)
-  cudaStream_t mid_stream = nullptr;     // stage B
-  cudaEvent_t ev_front_done[VRS_NQ] = {nullptr}, ev_mid_done[VRS_NQ] = {nullptr}, ev_back_done[VRS_NQ] = {nullptr};
-  bool back_recorded[VRS_NQ] = {false, false, false};
-  int depth = 3;                         // stages that may overlap: 3 = A | B | back, 2 = A+B | back, 1 = none (VRS_PIPELINE)
+  cudaStream_t fstream[VRS_NFRONT] = {nullptr};          // streams of the front stages A, B, C (frames in flight)
+  cudaEvent_t ev_stage_done[VRS_NFRONT][VRS_NQ] = {{nullptr}}, ev_back_done[VRS_NQ] = {nullptr};
+  bool back_recorded[VRS_NQ] = {false, false, false, false};
+  int depth = 4;                         // stages that may overlap: 4 = A | B | C | back, 3 = A | B+C | back, 2 = A+B+C | back (VRS_PIPELINE)
   bool halo_pending = false;             // a halo push has been enqueued whose consumer-side wait has not
   bool pipeline = true;
   bool replaying = false;                 // a captured half is being replayed: bodies only advance host-side state
@@ -196,14 +196,16 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
     return cudaMemset(*p, 0, bytes) == cudaSuccess;
   };
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->front_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->mid_stream, cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
+      cudaStreamCreateWithFlags(&ctx->fstream[0], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->fstream[1], cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->fstream[2], cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
   for (int i = 0; i < VRS_NQ; ++i)
-    if (cudaEventCreateWithFlags(&ctx->ev_front_done[i], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_mid_done[i], cudaEventDisableTiming) != cudaSuccess ||
+    if (cudaEventCreateWithFlags(&ctx->ev_stage_done[0][i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_stage_done[1][i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_stage_done[2][i], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_back_done[i], cudaEventDisableTiming) != cudaSuccess) { ctx->err = "event create failed"; return bail(VRS_ERR_CUDA); }
   ctx->pipeline = !(getenv("VRS_PIPELINE") && getenv("VRS_PIPELINE")[0] == '0');
-  ctx->depth = getenv("VRS_PIPELINE") && getenv("VRS_PIPELINE")[0] == '2' ? 2 : 3;
+  ctx->depth = getenv("VRS_PIPELINE") && getenv("VRS_PIPELINE")[0] >= '2' && getenv("VRS_PIPELINE")[0] <= '4' ? getenv("VRS_PIPELINE")[0] - '0' : 4;
   if (vrs_status s = alloc_frame_buffers(ctx)) return bail(s);
   {
     cudaDeviceProp prop;
@@ -229,9 +231,9 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
   return VRS_OK;
 }
 
+static void sync_front_streams(vrs_ctx* ctx) { for (int i = 0; i < VRS_NFRONT; ++i) if (ctx->fstream[i]) cudaStreamSynchronize(ctx->fstream[i]); }
 static void invalidate_graphs(vrs_ctx* ctx) {
-  if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
-  if (ctx->mid_stream) cudaStreamSynchronize(ctx->mid_stream);
+  sync_front_streams(ctx);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   ctx->graphs.clear(); ctx->seen.clear();
@@ -245,13 +247,11 @@ static void free_grid(vrs_ctx* ctx) {
 void vrs_destroy(vrs_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (ctx->front_stream) cudaStreamSynchronize(ctx->front_stream);
-  if (ctx->mid_stream) cudaStreamSynchronize(ctx->mid_stream);
+  sync_front_streams(ctx);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm) comm_destroy(ctx->comm);
   for (int i = 0; i < VRS_NQ; ++i) {
-    if (ctx->ev_front_done[i]) cudaEventDestroy(ctx->ev_front_done[i]);
-    if (ctx->ev_mid_done[i]) cudaEventDestroy(ctx->ev_mid_done[i]);
+    for (int k = 0; k < VRS_NFRONT; ++k) if (ctx->ev_stage_done[k][i]) cudaEventDestroy(ctx->ev_stage_done[k][i]);
     if (ctx->ev_back_done[i]) cudaEventDestroy(ctx->ev_back_done[i]);
   }
   for (vrs_ctx::Peer* p : {&ctx->peer_up, &ctx->peer_down}) for (void* q : p->opened) cudaIpcCloseMemHandle(q);
@@ -272,8 +272,7 @@ void vrs_destroy(vrs_ctx* ctx) {
   if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
   if (ctx->ev_halo_src) cudaEventDestroy(ctx->ev_halo_src);
   if (ctx->ev_halo_done) cudaEventDestroy(ctx->ev_halo_done);
-  if (ctx->front_stream) cudaStreamDestroy(ctx->front_stream);
-  if (ctx->mid_stream) cudaStreamDestroy(ctx->mid_stream);
+  for (int i = 0; i < VRS_NFRONT; ++i) if (ctx->fstream[i]) cudaStreamDestroy(ctx->fstream[i]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -361,8 +360,7 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
       attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
       attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
       cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-      cudaStreamSetAttribute(ctx->front_stream, cudaStreamAttributeAccessPolicyWindow, &attr);
-      cudaStreamSetAttribute(ctx->mid_stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      for (int i = 0; i < VRS_NFRONT; ++i) cudaStreamSetAttribute(ctx->fstream[i], cudaStreamAttributeAccessPolicyWindow, &attr);
       cudaGetLastError();       // best effort: the window is an optimisation, never an error
     }
   }
@@ -704,12 +702,21 @@ static vrs_status enqueue_front_b(vrs_ctx* ctx, const FrameParams& F, const Fram
                    ctx->store_y0, ctx->persistent_blocks, &ctx->kt);
   CK(cudaGetLastError());
   ctx->timings.launches += (uint32_t)front_ris_launches(F.flags, ctx->lights);
+  return VRS_OK;
+}
+static vrs_status enqueue_front_c(vrs_ctx* ctx, const FrameParams& F, const FrameIdx& fi, cudaStream_t st) {
+  launch_front_shadow(st, ctx->grid, F, ctx->queues[fi.q], ctx->persistent_blocks, &ctx->kt);
+  CK(cudaGetLastError());
+  ctx->timings.launches += (uint32_t)front_shadow_launches(F.flags);
   ctx->src_r = fi.ra;
   return VRS_OK;
 }
+static vrs_status enqueue_front_stage(vrs_ctx* ctx, int stage, const FrameParams& F, const FrameIdx& fi, cudaStream_t st) {
+  return stage == 0 ? enqueue_front_a(ctx, F, fi, st) : stage == 1 ? enqueue_front_b(ctx, F, fi, st) : enqueue_front_c(ctx, F, fi, st);
+}
 static vrs_status enqueue_front(vrs_ctx* ctx, const FrameParams& F, const FrameIdx& fi, cudaStream_t st) {
-  vrs_status s = enqueue_front_a(ctx, F, fi, st);
-  return s ? s : enqueue_front_b(ctx, F, fi, st);
+  for (int k = 0; k < VRS_NFRONT; ++k) { vrs_status s = enqueue_front_stage(ctx, k, F, fi, st); if (s) return s; }
+  return VRS_OK;
 }
 static int back_phases(vrs_ctx* ctx, const FrameParams& F) {
   const bool spatial = (F.flags & VRS_RESTIR_SPATIAL_REUSE_FLAG) != 0 && ctx->cfg.spatial_iterations > 0;
@@ -785,13 +792,14 @@ static void finish_frame_state(vrs_ctx* ctx, const FrameIdx& fi) {
   ctx->history_valid = true;
 }
 
-// Graph cache: the launch sequence of a stage depends only on the buffer rotation (frame_no % 15 = lcm of the ring lengths), on where the previous
+// Graph cache: the launch sequence of a stage depends only on the buffer rotation (frame_no % 12 = lcm of the ring lengths), on where the previous
 // frame left its final reservoirs, on the structural flags and on whether a halo push is pending.
 static uint64_t graph_key(vrs_ctx* ctx, const FrameParams& F, int half, bool want_temporal_push) {
-  uint64_t k = (uint64_t)(ctx->frame_no % 15) | ((uint64_t)(F.flags & 0x3f) << 6) | ((uint64_t)ctx->cfg.spatial_iterations << 12) |
-               ((uint64_t)(F.cull ? 1 : 0) << 16) | ((uint64_t)(ctx->pass_timing ? 1 : 0) << 17) | ((uint64_t)half << 21);
-  if (half == 1) k |= ((uint64_t)ctx->final_r << 3) | ((uint64_t)(ctx->peer_mode ? 1 : 0) << 15) | ((uint64_t)(ctx->halo_pending ? 1 : 0) << 18) |
-                      ((uint64_t)(want_temporal_push ? 1 : 0) << 20);
+  // half: 1 = back, 2 + k = front stage k
+  uint64_t k = (uint64_t)(ctx->frame_no % 12) | ((uint64_t)(F.flags & 0x3f) << 8) | ((uint64_t)(ctx->cfg.spatial_iterations & 7) << 14) |
+               ((uint64_t)(F.cull ? 1 : 0) << 17) | ((uint64_t)(ctx->pass_timing ? 1 : 0) << 18) | ((uint64_t)half << 24);
+  if (half == 1) k |= ((uint64_t)(ctx->final_r & 15) << 4) | ((uint64_t)(ctx->peer_mode ? 1 : 0) << 19) | ((uint64_t)(ctx->halo_pending ? 1 : 0) << 20) |
+                      ((uint64_t)(want_temporal_push ? 1 : 0) << 21);
   return k;
 }
 static vrs_status run_captured(vrs_ctx* ctx, uint64_t key, cudaStream_t st, const std::function<vrs_status()>& body) {
@@ -830,8 +838,7 @@ vrs_status vrs_pass_initial(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
   FrameParams F; vrs_status s = make_params(ctx, gu, ru, nullptr, clock, F); if (s) return s;
   const FrameIdx fi = frame_idx(ctx->frame_no);
   ctx->cur = fi;
-  CK(cudaStreamSynchronize(ctx->front_stream));          // the per-pass calls run on the main stream, strictly in order
-  CK(cudaStreamSynchronize(ctx->mid_stream));
+  sync_front_streams(ctx);                               // the per-pass calls run on the main stream, strictly in order
   if ((s = upload_params(ctx, F, fi.q, ctx->stream))) return s;
   if ((s = enqueue_front(ctx, F, fi, ctx->stream))) return s;
   return enqueue_back_phase(ctx, F, fi, 0, false, ctx->stream);
@@ -870,27 +877,23 @@ vrs_status vrs_render_frame(vrs_ctx* ctx, const vrs_global_uniforms* gu, const v
   const FrameIdx fi = frame_idx(ctx->frame_no);
   ctx->cur = fi;
   const bool want_temporal_push = (ru->flags & VRS_RESTIR_TEMPORAL_REUSE_FLAG) != 0;
-  cudaStream_t sa = overlap ? ctx->front_stream : ctx->stream;
-  cudaStream_t sb = overlap ? (ctx->depth >= 3 ? ctx->mid_stream : ctx->front_stream) : ctx->stream;
+  // stream of front stage k: depth 4 = one stream each, 3 = B and C share one, 2 = all three share one
+  cudaStream_t sst[VRS_NFRONT];
+  for (int k = 0; k < VRS_NFRONT; ++k) sst[k] = !overlap ? ctx->stream : ctx->fstream[ctx->depth >= 4 ? k : (ctx->depth == 3 ? (k ? 1 : 0) : 0)];
   if (ctx->kt.on) { ctx->kt.n = 0; CK(cudaEventRecord(ctx->kt.ev[0], ctx->stream)); }
-  // ---- stage A: needs the queue set / parameter block that frame n - 3 used, and a G-buffer slot nobody reads any more
-  if (overlap && ctx->back_recorded[fi.q]) CK(cudaStreamWaitEvent(sa, ctx->ev_back_done[fi.q], 0));
-  if ((s = upload_params(ctx, F, fi.q, sa))) return s;
-  if (eager) s = enqueue_front_a(ctx, F, fi, sa);
-  else s = run_captured(ctx, graph_key(ctx, F, 0, false), sa, [&]() -> vrs_status {
-    if (ctx->replaying) return VRS_OK;
-    return enqueue_front_a(ctx, F, fi, sa);
-  });
-  if (s) return s;
-  // ---- stage B
-  if (overlap && sb != sa) { CK(cudaEventRecord(ctx->ev_front_done[fi.q], sa)); CK(cudaStreamWaitEvent(sb, ctx->ev_front_done[fi.q], 0)); }
-  if (eager) s = enqueue_front_b(ctx, F, fi, sb);
-  else s = run_captured(ctx, graph_key(ctx, F, 2, false), sb, [&]() -> vrs_status {
-    if (ctx->replaying) { ctx->src_r = fi.ra; return VRS_OK; }
-    return enqueue_front_b(ctx, F, fi, sb);
-  });
-  if (s) return s;
-  if (overlap) { CK(cudaEventRecord(ctx->ev_mid_done[fi.q], sb)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_mid_done[fi.q], 0)); }
+  // stage A needs the queue set / parameter block that frame n - 4 used, and a G-buffer slot nobody reads any more
+  if (overlap && ctx->back_recorded[fi.q]) CK(cudaStreamWaitEvent(sst[0], ctx->ev_back_done[fi.q], 0));
+  if ((s = upload_params(ctx, F, fi.q, sst[0]))) return s;
+  for (int k = 0; k < VRS_NFRONT; ++k) {
+    if (overlap && k > 0 && sst[k] != sst[k - 1]) { CK(cudaEventRecord(ctx->ev_stage_done[k - 1][fi.q], sst[k - 1])); CK(cudaStreamWaitEvent(sst[k], ctx->ev_stage_done[k - 1][fi.q], 0)); }
+    if (eager) s = enqueue_front_stage(ctx, k, F, fi, sst[k]);
+    else s = run_captured(ctx, graph_key(ctx, F, 2 + k, false), sst[k], [&]() -> vrs_status {
+      if (ctx->replaying) { if (k == VRS_NFRONT - 1) ctx->src_r = fi.ra; return VRS_OK; }
+      return enqueue_front_stage(ctx, k, F, fi, sst[k]);
+    });
+    if (s) return s;
+  }
+  if (overlap) { CK(cudaEventRecord(ctx->ev_stage_done[VRS_NFRONT - 1][fi.q], sst[VRS_NFRONT - 1])); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_done[VRS_NFRONT - 1][fi.q], 0)); }
   // ---- back half
   const int nph = back_phases(ctx, F);
   auto back = [&]() -> vrs_status {
@@ -927,8 +930,7 @@ vrs_status vrs_render_frame_group(vrs_ctx** ctxs, uint32_t n, const vrs_global_u
     vrs_status s = make_params(ctx, gu, ru, pc, clock, F[i]); if (s) return s;
     ctx->timings.launches = 0;
     fi[i] = frame_idx(ctx->frame_no); ctx->cur = fi[i];
-    CK(cudaStreamSynchronize(ctx->front_stream));
-    CK(cudaStreamSynchronize(ctx->mid_stream));
+    sync_front_streams(ctx);
     if ((s = upload_params(ctx, F[i], fi[i].q, ctx->stream))) return s;
     if ((s = enqueue_front(ctx, F[i], fi[i], ctx->stream))) return s;
   }
@@ -947,8 +949,7 @@ vrs_status vrs_render_frame_group(vrs_ctx** ctxs, uint32_t n, const vrs_global_u
 vrs_status vrs_synchronize(vrs_ctx* ctx) {
   if (!ctx) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  CK(cudaStreamSynchronize(ctx->front_stream));
-  CK(cudaStreamSynchronize(ctx->mid_stream));
+  for (int i = 0; i < VRS_NFRONT; ++i) CK(cudaStreamSynchronize(ctx->fstream[i]));
   CK(cudaStreamSynchronize(ctx->stream));
   if (ctx->comm_stream) CK(cudaStreamSynchronize(ctx->comm_stream));
   if (ctx->peer_mode) {          // did a halo wait give up?  (k_halo_wait sets xflags[4]; stale halo rows must not pass as VRS_OK)
@@ -1084,7 +1085,7 @@ vrs_status vrs_write_image(vrs_ctx* ctx, const char* path) {
 }
 
 // ------------------------------------------------------------------------------------------ multi-GPU
-// ---- peer-memory exchange set-up: blob = { band_y0, band_y1, store_y0, store_y1 (int32) | 41 x cudaIpcMemHandle_t }
+// ---- peer-memory exchange set-up: blob = { band_y0, band_y1, store_y0, store_y1 (int32) | 49 x cudaIpcMemHandle_t }
 vrs_status vrs_peer_export(vrs_ctx* ctx, uint8_t blob[VRS_PEER_BLOB_BYTES]) {
   if (!ctx || !blob) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);

@@ -802,7 +802,10 @@ static int resident_grid(K kernel, int block_threads, int fallback_per_sm) {
   cudaGetDevice(&d); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block_threads, 0) != cudaSuccess || per_sm < 1) per_sm = fallback_per_sm;
   const int scale = getenv("VRS_WAVE_SCALE") ? atoi(getenv("VRS_WAVE_SCALE")) : 1;
-  return sms * per_sm * (scale > 0 ? scale : 1);
+  const int pct = getenv("VRS_GRID_PCT") ? atoi(getenv("VRS_GRID_PCT")) : 100;      // (measurements: leave room for the kernels of other stages)
+  int g = sms * per_sm * (scale > 0 ? scale : 1);
+  if (pct > 0 && pct < 100) g = g * pct / 100 < sms ? sms : g * pct / 100;
+  return g;
 }
 
 // ------------------------------------------------------------------------------------------------- launchers
@@ -811,7 +814,7 @@ static int resident_grid(K kernel, int block_threads, int fallback_per_sm) {
 // Front of the initial pass (everything that does not depend on the previous frame), in two stages the host runtime may run
 // on different streams and overlap with other frames (frames in flight):
 //   stage A launch_front_trace  coverage mask, classification, primary volume event, hit list   -> work queues Q, hit scratch in cur.worldPos
-//   stage B launch_front_ris    RIS candidates (G-buffer + tmp reservoir outR), shadow rays       -> cur, outR, Q.hit_T / hit_seed
+//   stage B launch_front_ris    RIS candidates (G-buffer + tmp reservoir outR), shadow-ray queue -> cur, outR, Q.shadow
 static int march_refill() {
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   static const int target_warps = sms * (getenv("VRS_MIN_WARPS_PER_SM") ? atoi(getenv("VRS_MIN_WARPS_PER_SM")) : MIN_WARPS_PER_SM);
@@ -881,12 +884,14 @@ void launch_front_ris(cudaStream_t st, const GridDev& G, const LightsDev& L, con
     k_ris_thread<8><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
   }
   ktick(kt, st, "k_ris");
-  if (vis) {
-    static const int g_ss = resident_grid(k_shadow_simple, 128, 8) * march_waves();
-    if (simple_march()) k_shadow_simple<<<g_ss, 128, 0, st>>>(G, Q);
-    else k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, refill);
-    ktick(kt, st, "k_shadow");
-  }
+}
+//   stage C launch_front_shadow  ratio-tracking transmittance toward the selected light          -> Q.hit_T / hit_seed
+void launch_front_shadow(cudaStream_t st, const GridDev& G, const FrameParams& F, const Queues& Q, int persistent_blocks, KTimer* kt) {
+  if ((F.flags & FLAG_VISIBILITY) == 0) return;
+  static const int g_ss = resident_grid(k_shadow_simple, 128, 8) * march_waves();
+  if (simple_march()) k_shadow_simple<<<g_ss, 128, 0, st>>>(G, Q);
+  else k_shadow<<<persistent_blocks, 128, 0, st>>>(G, Q, march_refill());
+  ktick(kt, st, "k_shadow");
 }
 // Back half of the initial pass: apply the shadow transmittance, temporal merge with the previous frame's G-buffer /
 // final reservoirs (restir.rgen:229-284), final pack.  No-op when neither visibility nor temporal reuse is on.
@@ -904,8 +909,10 @@ int front_ris_launches(int flags, const LightsDev& L) {
   const char ris_env = getenv("VRS_RIS") ? getenv("VRS_RIS")[0] : 'a';
   const bool big_tables = (size_t)L.nlights * 32 + (size_t)L.ntable * 16 > (size_t)64 * 1024;
   const int ris = (ris_env == 'a' && !big_tables) ? 2 : 1;
-  return ris + (vis ? 1 : 0);
+  (void)vis;
+  return ris;
 }
+int front_shadow_launches(int flags) { return (flags & FLAG_VISIBILITY) != 0 ? 1 : 0; }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
                     uint32_t iteration, uint32_t spatial_neighbors, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt) {
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
