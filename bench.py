@@ -263,7 +263,7 @@ def split_rows(cost, world, min_rows=32):
     return [(edges[r], edges[r + 1]) for r in range(world)]
 
 
-def calibrated_bands(V, wl, path, world, rank, device, dist, halo, min_rows, rounds=3):
+def calibrated_bands(V, wl, path, world, rank, device, dist, halo, min_rows, rounds=5):
     """Start from the hit-count model, then correct it with measurements: every rank renders its band (no exchange, timing
     only) at the probe positions of the orbit, the per-band times are all-gathered and turned into a per-band correction of
     the row costs.  Which rows a rank renders never changes a pixel (tests/test_gpu_multi.py); only the load balance does."""
@@ -297,7 +297,7 @@ def calibrated_bands(V, wl, path, world, rank, device, dist, halo, min_rows, rou
         corr = meas.sum(1) / np.maximum(model.sum(1), 1e-30)
         corr = corr / corr.mean()
         for (y0, y1), c in zip(bands, corr):
-            cost[:, y0:y1] *= 0.5 * (1.0 + c)                                               # damped
+            cost[:, y0:y1] *= c ** 0.75                                                     # damped
         bands = split_rows(cost, world, min_rows)
     return bands
 
@@ -602,7 +602,7 @@ def run_ours(args):
             "metric": "ReSTIR frames/s", "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_step, 5), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": data_desc(wl),
             "config": config_of(wl, args.workload),
-            "partition": ("bands minimising the slowest band's cost over 12 orbit positions (hit-count model corrected by 3 timed calibration rounds) x%d %s, halo %d rows, temporal reach %d rows (%s)"
+            "partition": ("bands minimising the slowest band's cost over 12 orbit positions (hit-count model corrected by 5 timed calibration rounds) x%d %s, halo %d rows, temporal reach %d rows (%s)"
                           % (world, [b[1] - b[0] for b in bands], halo, reach,
                              "shipped as halo rows" if args.exchange == "nccl" else "read in place from the adjacent band over NVLink")) if world > 1 else "single GPU",
             "repetitions_ms_per_step": [round(r_, 5) for r_ in reps], "timed_region_s": round(sum(reps) * args.steps / 1e3, 3),
