@@ -66,7 +66,7 @@ def test_alias_table_and_lights_match_reference(V, O):
         got = V.generate_point_lights(g["min"], g["max"], bool(g["white"]), g["n"])
         assert got.ravel().view(np.uint32).tolist() == g["out"]
     rng = np.random.default_rng(5)
-    for n in (1, 2, 17, 1000, 10000):
+    for n in (1, 2, 17, 1000, 10000, 100000):           # 100 000 = configs[4]
         pdf = rng.uniform(0, 3, n).astype(np.float32)
         a, b = V.create_alias_table(pdf), O.create_alias_table(pdf)
         assert a.tobytes() == b.tobytes()
@@ -75,6 +75,28 @@ def test_alias_table_and_lights_match_reference(V, O):
         mass = a["prob"].astype(np.float64).copy()
         np.add.at(mass, a["alias"], 1.0 - a["prob"].astype(np.float64))
         assert np.allclose(mass / n, pdf / pdf.sum(), atol=2e-6)
+
+
+def test_configs4_light_set_and_alias_table_match_the_reference_sources(V, O):
+    """BASELINE configs[4]: 100 000 lights.  The light set bench.py builds for it and its alias table, product vs oracle bit for
+    bit, and — when the reference's own restir_utils.cpp is compiled here (oracle/_ref) — against that too."""
+    import ctypes as C
+    lo, hi = [-3.2, 0.4, -1.9], [2.7, 6.1, 2.2]
+    n = 100000
+    a, b = V.generate_point_lights(lo, hi, False, n), O.generate_point_lights(lo, hi, False, n)
+    assert a.shape == (n, 8) and a.tobytes() == b.tobytes()
+    ta, tb = V.create_alias_table(a[:, 7]), O.create_alias_table(a[:, 7])
+    assert ta.tobytes() == tb.tobytes()
+    R = O.ref()
+    if R is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    names = [s for s in ("ref_createAliasTable", "ref_create_alias_table") if hasattr(R, s)]
+    if not names:
+        pytest.skip("reference alias-table entry point not exported by this _ref build")
+    out = np.zeros(n, dtype=ta.dtype)
+    pdf = np.ascontiguousarray(a[:, 7])
+    getattr(R, names[0])(pdf.ctypes.data_as(C.c_void_p), C.c_int(n), out.ctypes.data_as(C.c_void_p))
+    assert out.tobytes() == ta.tobytes()
 
 
 def test_camera_matches_reference(V):

@@ -14,7 +14,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvrs.so")
+# VRS_LIB picks another build of the same sources (libvrs_relaxed.so: measurements only, not bit-exact)
+LIB_PATH = os.path.join(HERE, os.environ.get("VRS_LIB", "libvrs.so"))
 
 VISIBILITY_REUSE_FLAG, TEMPORAL_REUSE_FLAG, SPATIAL_REUSE_FLAG, USE_ENVIRONMENT_FLAG = 1, 2, 4, 8
 FINAL_VISIBILITY_FLAG, FINALIZE_W_FLAG = 16, 32

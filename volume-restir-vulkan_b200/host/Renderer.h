@@ -68,6 +68,13 @@ class Renderer {
     m_restirPass.setup(this); m_spatialReusePass.setup(this);
   }
   void destroy() { if (ctx_) vrs_destroy(ctx_); ctx_ = nullptr; }
+  // Renderer::onResize (Renderer.cpp:1022-1026) + the passes' createRenderPass(VkExtent2D) (restirPass.cpp:79-81, spatialReusePass.cpp:41-43)
+  void onResize(int w, int h) {
+    check(vrs_resize(ctx_, (uint32_t)w, (uint32_t)h), ctx_, "vrs_resize");
+    width_ = (uint32_t)w; height_ = (uint32_t)h;
+    m_restirUniforms.screenSize[0] = width_; m_restirUniforms.screenSize[1] = height_;
+    have_ref_ = false;
+  }
   ~Renderer() { destroy(); }
 
   // Renderer::createVDBBuffer (Renderer.cpp:1408-1582): flatten + stage the grid instead of building spheres
