@@ -55,7 +55,7 @@ def timed(label, n):
 
 
 n = 60 * orbits
-timed("graphs, frames in flight (VRS_PIPELINE=%s)" % os.environ.get("VRS_PIPELINE", "3"), n)
+timed("graphs, frames in flight (VRS_PIPELINE=%s)" % os.environ.get("VRS_PIPELINE", "4"), n)
 R.setPassTiming(True); timed("graphs, per-pass events (no overlap)", n); R.setPassTiming(False)
 R.setKernelTiming(True); timed("eager + per-kernel events", n)
 acc = {}

@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(128, 8) k_primary_simple(const GridDev G, cons
   }
 }
 
-__global__ void __launch_bounds__(128) k_finish(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, Planes prev, ResPlanes prevR,
+__global__ void __launch_bounds__(128, 8) k_finish(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, Planes prev, ResPlanes prevR,
                                                 ResPlanes outR, Queues Q, uint32_t* __restrict__ trace, int store_y0, const PrevAccess PA,
                                                 unsigned* __restrict__ out_of_halo) {
   const FrameParams& F = *Fp;
@@ -671,7 +671,7 @@ __global__ void __launch_bounds__(128, MINB) k_spatial_thread(const LightsDev L,
 // Final shade — restir_post.frag main (:57-105): shade, emissive override, firefly clamp, running mean.
 // Every pixel; a miss pixel costs its worldPos read (16 B) and the accumulation update only.
 // -------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_shade(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes rs,
+__global__ void __launch_bounds__(256, 5) k_shade(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes rs,
                                                float4* __restrict__ accum, int y0, int y1, int store_y0) {
   const FrameParams& F = *Fp;
   const int x = blockIdx.x * 32 + threadIdx.x;
