@@ -63,9 +63,9 @@ struct vrs_ctx {
   cudaEvent_t ev_stage_done[VRS_NFRONT][VRS_NQ] = {{nullptr}}, ev_back_done[VRS_NQ] = {nullptr};
   bool back_recorded[VRS_NQ] = {false, false, false, false};
   int depth = 4;                         // stages that may overlap: 4 = A | B | C | back, 3 = A | B+C | back, 2 = A+B+C | back (VRS_PIPELINE)
-  bool halo_pending = false;             // a halo push has been enqueued whose consumer-side wait has not
-  bool pipeline = true;
-  bool replaying = false;                 // a captured half is being replayed: bodies only advance host-side state
+  bool halo_pending = false;             // a halo push has been enqueued whose consumer-side wait has not been yet
+  bool pipeline = true;                  // VRS_PIPELINE=0 switches the overlap of frames off
+  bool replaying = false;                // a captured stage is being replayed: bodies only advance host-side state
 
   HostGrid host_grid;
   bool has_grid = false;
@@ -82,12 +82,11 @@ struct vrs_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t display_ready[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
   uint32_t present_count = 0;
-  FrameParams* d_params = nullptr;           // VRS_NQ device-resident copies (frame n reads copy n % 2)
+  FrameParams* d_params = nullptr;           // VRS_NQ device-resident copies (frame n reads copy n % VRS_NQ)
   FrameParams* h_params = nullptr;           // pinned ring feeding it
   cudaEvent_t param_ev[VRS_PARAM_SLOTS] = {nullptr};
   uint64_t param_serial = 0;
-  std::map<uint64_t, GraphEntry> graphs;     // captured frames, keyed by ping-pong phase + structural flags
-  std::map<uint64_t, int> seen;
+  std::map<uint64_t, GraphEntry> graphs;     // captured stages, keyed by buffer-rotation phase + structural flags (graph_key)
   bool capturing = false;
   Queues queues[VRS_NQ]{};
   int persistent_blocks = 148 * 12;
@@ -101,7 +100,8 @@ struct vrs_ctx {
   struct Peer { bool present = false; float4* g[VRS_NG][4] = {{nullptr}}; float4* r[VRS_NR][2] = {{nullptr}}; unsigned* flags = nullptr; int store_y0 = 0, store_y1 = 0, band_y0 = 0, band_y1 = 0; std::vector<void*> opened; };
   Peer peer_up, peer_down;
   bool peer_mode = false;
-  unsigned* xflags = nullptr;                // [0] flag written by the up neighbour, [1] by the down neighbour, [2] serial, [3] block counter, [4] error
+  unsigned* xflags = nullptr;                // [0] flag written by the up neighbour, [1] by the down neighbour, [2] serial, [3] block counter, [4] wait timed out,
+                                             // [5] temporal reprojections nobody could supply, [6] largest vertical reprojection distance (rows)
   cudaStream_t comm_stream = nullptr;        // halo exchanges run here so that they can overlap the next kernels
   cudaEvent_t ev_halo_src = nullptr, ev_halo_done = nullptr;
   bool history_valid = false;                // false: the previous frame's buffers do not belong to this scene / size (first frame, new lights, new grid, resize)
@@ -236,7 +236,7 @@ static void invalidate_graphs(vrs_ctx* ctx) {
   sync_front_streams(ctx);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-  ctx->graphs.clear(); ctx->seen.clear();
+  ctx->graphs.clear();
 }
 
 static void free_grid(vrs_ctx* ctx) {
@@ -739,7 +739,7 @@ static vrs_status enqueue_back_phase(vrs_ctx* ctx, const FrameParams& F, const F
   int sp_rows = (int)ceilf(F.spatialRadius); if (sp_rows < 1) sp_rows = 1;      // |int(dy)| <= radius: the rows spatial reuse can reach
   if (phase == 0) {
     const bool needs_finish = (F.flags & (VRS_RESTIR_VISIBILITY_REUSE_FLAG | VRS_RESTIR_TEMPORAL_REUSE_FLAG)) != 0;
-    // the previous frame's G-buffer + final reservoir halo rows (pushed at the end of that frame) are read by the temporal merge
+    // joins the exchange that closed the previous frame (peer memory: the neighbours' "final" flag; NCCL: their halo rows)
     if ((s = halo_wait(ctx, st))) return s;
     PrevAccess PA; memset(&PA, 0, sizeof(PA));
     if (ctx->peer_mode) {
