@@ -328,38 +328,6 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
         dir[2 * ci] = c < 0 ? tile_density[~c] : leaf_max[c];
         memcpy(&dir[2 * ci + 1], &c, 4);
       }
-  // Empty-space skipping: an empty cell (majorant 0: no collision can happen in it, its leaf / tile index is never used) carries its
-  // chessboard distance to the nearest non-empty cell instead — exact two-pass chamfer transform with unit weights over the 26
-  // neighbours, capped at 255.  The raymarch walks that many cells without loading them (Ray::tail).
-  if (ncell <= ((size_t)1 << 27)) {
-    const int cx_ = G.cdim[0], cy_ = G.cdim[1], cz_ = G.cdim[2];
-    std::vector<uint8_t> dist(ncell);
-    for (size_t ci = 0; ci < ncell; ++ci) dist[ci] = dir[2 * ci] > 0.0f ? 0 : 255;
-    auto relax = [&](int x, int y, int z, int dx, int dy, int dz, uint8_t& d) {
-      const int nx = x + dx, ny = y + dy, nz = z + dz;
-      if (nx < 0 || ny < 0 || nz < 0 || nx >= cx_ || ny >= cy_ || nz >= cz_) return;
-      const uint8_t v = dist[((size_t)nz * cy_ + ny) * cx_ + nx];
-      if (v < 254 && (uint8_t)(v + 1) < d) d = (uint8_t)(v + 1);
-    };
-    for (int z = 0; z < cz_; ++z) for (int y = 0; y < cy_; ++y) for (int x = 0; x < cx_; ++x) {          // forward: the 13 neighbours already visited
-      uint8_t& d = dist[((size_t)z * cy_ + y) * cx_ + x];
-      if (d == 0) continue;
-      for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) relax(x, y, z, dx, dy, -1, d);
-      for (int dx = -1; dx <= 1; ++dx) relax(x, y, z, dx, -1, 0, d);
-      relax(x, y, z, -1, 0, 0, d);
-    }
-    for (int z = cz_ - 1; z >= 0; --z) for (int y = cy_ - 1; y >= 0; --y) for (int x = cx_ - 1; x >= 0; --x) {   // backward: the other 13
-      uint8_t& d = dist[((size_t)z * cy_ + y) * cx_ + x];
-      if (d == 0) continue;
-      for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx) relax(x, y, z, dx, dy, 1, d);
-      for (int dx = -1; dx <= 1; ++dx) relax(x, y, z, dx, 1, 0, d);
-      relax(x, y, z, 1, 0, 0, d);
-    }
-    for (size_t ci = 0; ci < ncell; ++ci)
-      if (!(dir[2 * ci] > 0.0f)) { const int32_t k = dist[ci] ? dist[ci] : 1; memcpy(&dir[2 * ci + 1], &k, 4); }
-  } else {
-    for (size_t ci = 0; ci < ncell; ++ci) if (!(dir[2 * ci] > 0.0f)) { const int32_t k = 1; memcpy(&dir[2 * ci + 1], &k, 4); }
-  }
   // One slab for every grid table, so that a single L2 access-policy window can pin the whole grid: the per-pixel
   // buffers stream through L2 every frame (hundreds of MB) and would otherwise evict the few MB every ray keeps re-reading.
   struct Part { const void* src; size_t bytes; const void** dst; };

@@ -27,9 +27,7 @@ struct GridDev {
   // Dense directory over the window's 8^3 cells (the top tree levels flattened once more): the raymarch reads one
   // L1/L2-resident entry per cell instead of walking root -> internal5 -> internal4.
   const float2* dir;              // [cdim z][cdim y][cdim x] {majorant density of the cell (0 = empty), leaf index (>= 0) or ~tile (< 0) as bits}:
-                                  // one 8-byte load per visited cell serves both the majorant test and the later brick lookup.
-                                  // An EMPTY cell carries, instead of the leaf, its chessboard distance D >= 1 (in cells) to the nearest
-                                  // non-empty cell: the next D - 1 cells of any ray are empty too and are walked without loading them
+                                  // one 8-byte load per visited cell serves both the majorant test and the later brick lookup
 };
 
 struct LightsDev {
@@ -498,41 +496,21 @@ struct Ray {
     mu = mu_d > 0.0f ? mu_d * G.density_scale : 0.0f;        // empty cell: seg = 0 below, tau is untouched (x - 0 = x)
   }
 
-  // leave the current cell along `axis`, branch-free: lanes of a warp leave along different axes, and a three-way branch would
-  // run its arms one after the other with a third of the lanes each (ncu: 1.7 - 5.7 lanes per instruction in those arms).
-  // true = the ray left the window
-  __device__ __forceinline__ bool step_cell(const GridDev& G) {
-    const int m0 = -(int)(axis == 0), m1 = -(int)(axis == 1), m2 = -(int)(axis == 2);
-    c[0] += sgn[0] & m0; c[1] += sgn[1] & m1; c[2] += sgn[2] & m2;
-    cell += (sgn[0] & m0) + ((sgn[1] * G.cdim[0]) & m1) + ((sgn[2] * (G.cdim[0] * G.cdim[1])) & m2);
-    const float n0 = tn[0] + dt[0], n1 = tn[1] + dt[1], n2 = tn[2] + dt[2];
-    tn[0] = axis == 0 ? n0 : tn[0]; tn[1] = axis == 1 ? n1 : tn[1]; tn[2] = axis == 2 ? n2 : tn[2];
-    return (unsigned)c[0] >= (unsigned)G.cdim[0] || (unsigned)c[1] >= (unsigned)G.cdim[1] || (unsigned)c[2] >= (unsigned)G.cdim[2];   // only the coordinate that moved can have left
-  }
-
   __device__ __forceinline__ int tail(const GridDev& G) {
     const float seg = (tcell - t) * mu;
     if (tau < seg) return RAY_COLLIDE;
     tau = tau - seg;
     t = tcell;
     if (last) return RAY_DONE;
-    if (step_cell(G)) return RAY_DONE;
-    // Empty-space skipping.  The cell just left was empty and D cells away (chessboard distance) from the nearest non-empty
-    // one: the next D - 1 cells along ANY ray are empty, so they are walked here — same exit times, same cell counter, tau
-    // untouched (an empty cell consumes (tcell - t) * 0 = 0 of it) — without their directory loads and without a scheduling
-    // round each.  Results are those of visiting them one by one.
-    if (!(mu_d > 0.0f)) {
-      for (int k = leaf; k > 1; --k) {
-        ncells += 1;
-        axis = 0; tcell = tn[0];
-        if (tn[1] < tcell) { tcell = tn[1]; axis = 1; }
-        if (tn[2] < tcell) { tcell = tn[2]; axis = 2; }
-        if (!(tcell < t1)) { t = t1; return RAY_DONE; }
-        t = tcell;
-        if (step_cell(G)) return RAY_DONE;
-      }
-    }
-    return RAY_SKIP;
+    // leave the cell along `axis`, branch-free: lanes of a warp leave along different axes, and a three-way branch would run
+    // its arms one after the other with a third of the lanes each (ncu: 1.7 - 5.7 lanes per instruction in those arms)
+    const int m0 = -(int)(axis == 0), m1 = -(int)(axis == 1), m2 = -(int)(axis == 2);
+    c[0] += sgn[0] & m0; c[1] += sgn[1] & m1; c[2] += sgn[2] & m2;
+    cell += (sgn[0] & m0) + ((sgn[1] * G.cdim[0]) & m1) + ((sgn[2] * (G.cdim[0] * G.cdim[1])) & m2);
+    const float n0 = tn[0] + dt[0], n1 = tn[1] + dt[1], n2 = tn[2] + dt[2];
+    tn[0] = axis == 0 ? n0 : tn[0]; tn[1] = axis == 1 ? n1 : tn[1]; tn[2] = axis == 2 ? n2 : tn[2];
+    const bool out = (unsigned)c[0] >= (unsigned)G.cdim[0] || (unsigned)c[1] >= (unsigned)G.cdim[1] || (unsigned)c[2] >= (unsigned)G.cdim[2];   // only the coordinate that moved can have left the window
+    return out ? RAY_DONE : RAY_SKIP;
   }
 
   // false = the ray ended at this collision (primary: real collision found; shadow: opaque)
