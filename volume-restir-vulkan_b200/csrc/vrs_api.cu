@@ -195,10 +195,16 @@ vrs_status vrs_create(const vrs_config* cfg, vrs_ctx** out) {
     if (cudaMalloc(p, bytes) != cudaSuccess) { ctx->err = "cudaMalloc failed (" + std::to_string(bytes) + " bytes)"; return false; }
     return cudaMemset(*p, 0, bytes) == cudaSuccess;
   };
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->fstream[0], cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->fstream[1], cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->fstream[2], cudaStreamNonBlocking) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
+  // The back half is the frame's critical chain (frame n + 1's temporal merge needs frame n's last spatial iteration, and on
+  // several GPUs the neighbours wait for its pushes): its stream outranks the front stages', so that its blocks are placed first
+  // whenever SM resources free up (VRS_NO_PRIORITY=1: all streams equal, for measurements).
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (getenv("VRS_NO_PRIORITY")) prio_hi = prio_lo;
+  if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ctx->fstream[0], cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ctx->fstream[1], cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&ctx->fstream[2], cudaStreamNonBlocking, prio_lo) != cudaSuccess) { ctx->err = "stream create failed"; return bail(VRS_ERR_CUDA); }
   for (int i = 0; i < VRS_NQ; ++i)
     if (cudaEventCreateWithFlags(&ctx->ev_stage_done[0][i], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_stage_done[1][i], cudaEventDisableTiming) != cudaSuccess ||
