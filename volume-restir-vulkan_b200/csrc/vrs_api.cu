@@ -731,7 +731,7 @@ static int back_phases(vrs_ctx* ctx, const FrameParams& F) {
 static vrs_status enqueue_spatial(vrs_ctx* ctx, const FrameParams& F, const FrameIdx& fi, uint32_t iteration, cudaStream_t st) {
   const int dst = ctx->src_r == fi.ra ? fi.rb : fi.ra;
   launch_spatial(st, ctx->lights, ctx->d_params + fi.q, planes_of(ctx, fi.g), res_of(ctx, ctx->src_r), res_of(ctx, dst), ctx->queues[fi.q],
-                 iteration, F.spatialNeighbors, ctx->store_y0, ctx->store_y1, ctx->persistent_blocks, 0, 0, 0, &ctx->kt);
+                 iteration, ctx->store_y0, ctx->store_y1, &ctx->kt);
   CK(cudaGetLastError());
   ctx->src_r = dst;
   ctx->timings.launches += 1;

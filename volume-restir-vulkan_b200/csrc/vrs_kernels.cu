@@ -16,15 +16,17 @@ static constexpr int MAX_NEIGHBORS = 16;
 // -------------------------------------------------------------------------------------------------
 // Initial pass — restir.rgen main (:136-290) on a volume, as a chain of kernels over device-side work lists.
 // The pass is instruction-issue bound (ncu, profiles/): what matters is how many of the 32 lanes do useful work and
-// how few bytes the empty part of the screen costs, so each stage runs on the smallest, densest set it can:
-//   A0 k_classify   every pixel: primary ray (:142-148) vs. the grid window; writes worldPos = 0 (the miss marker,
-//                   16 B/px) and queues the rays that enter the window.
-//   A1 k_primary    persistent warps: residual delta tracking of queued rays, unit steps batched per warp, lane
-//                   refill; a real collision leaves {t, voxel, RNG state, 1} in the pixel's worldPos slot.
-//   A2 k_hit_compact stream compaction of the hit flags -> hit list, pixel order inside 2048-pixel blocks (coalesced consumers).
-//   A3 k_ris        one thread per hit: G-buffer stores (:193-197), M-candidate RIS (:203-227), shadow-ray set-up.
-//   A4 k_shadow     persistent warps: ratio-tracking transmittance toward the selected light (:229-235).
-//   A5 k_finish     one thread per hit: apply the transmittance, temporal merge (:237-284), pack (:286-289).
+// how few bytes the empty part of the screen costs, so each stage runs on the smallest, densest set it can.  The host
+// runtime runs the chain as three stages on three streams plus the back half of the frame (vrs_api.cu, frames in flight):
+//   stage A  k_cover        non-empty cells of the grid -> screen tiles that can contain a collision
+//            k_classify     every pixel: writes worldPos = 0 (the miss marker, 16 B/px); in covered tiles the primary ray
+//                           (:142-148) vs. the grid window, queues the rays that enter it
+//            k_primary      persistent warps: residual delta tracking of queued rays, unit steps batched per warp, lane
+//                           refill; a real collision leaves {t, cell, RNG state, voxel in cell} in the pixel's worldPos slot
+//            k_hit_compact  stream compaction of the hit flags -> hit list, pixel order inside 2048-pixel blocks
+//   stage B  k_ris_*        per hit: G-buffer stores (:193-197), M-candidate RIS (:203-227), shadow-ray set-up
+//   stage C  k_shadow       persistent warps: ratio-tracking transmittance toward the selected light (:229-235)
+//   back     k_finish       per hit: apply the transmittance, temporal merge (:237-284), pack (:286-289)
 // -------------------------------------------------------------------------------------------------
 enum { Q_CAND = 0, Q_HIT = 1, Q_SHADOW = 2, Q_PRIMARY_HEAD = 3, Q_SHADOW_HEAD = 4, Q_COVER_ALL = 5 };
 static constexpr int COVER_TILE = 8;            // pixels per side of a coverage tile
@@ -267,10 +269,9 @@ __device__ __forceinline__ void ris_hit_store(const GridDev& G, const LightsDev&
   }
 }
 
-// Reference form of the RIS stage: one thread per hit pixel runs the M-candidate loop serially (kept selectable with
-// VRS_RIS=thread for A/B measurements; k_ris_coop below is the default and produces the same bits).
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_ris_thread(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
+// Thread form of the RIS stage: one thread per hit pixel runs the M-candidate loop serially.  The launcher uses it for light
+// tables that stay L1-resident (<= 64 KB) on large launches; k_ris_coop below takes the others and produces the same bits.
+__global__ void __launch_bounds__(128, 8) k_ris_thread(const GridDev G, const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes outR,
                                              Queues Q, uint32_t* __restrict__ trace, int store_y0, int needs_finish, uint32_t min_hits) {
   const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
@@ -608,17 +609,13 @@ __global__ void __launch_bounds__(128, 8) k_finish(const LightsDev L, const Fram
 // (reservoir.glsl:56-76), normalisation deferred to the finally selected sample.  One thread per hit pixel (the
 // `exist < 0.5` early-out of :76-79 is the hit list); neighbour G-buffer / reservoir reads are gathers through L2.
 // -------------------------------------------------------------------------------------------------
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_spatial_thread(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes inR, ResPlanes outR,
-                                                 Queues Q, uint32_t iteration, int store_y0, int store_y1, int part, int ylo, int yhi) {
+__global__ void __launch_bounds__(128, 8) k_spatial_thread(const LightsDev L, const FrameParams* __restrict__ Fp, Planes cur, ResPlanes inR, ResPlanes outR,
+                                                           Queues Q, uint32_t iteration, int store_y0, int store_y1) {
   const FrameParams& F = *Fp;
   const uint32_t nhit = Q.counters[Q_HIT];
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nhit; s += gridDim.x * blockDim.x) {
     const uint32_t idx = Q.hit_pix[s];
     const int x = (int)(idx % F.W), y = (int)(idx / F.W) + store_y0;
-    // multi-GPU: part 1 = only rows [ylo, yhi) whose neighbourhood lies inside the band (runs while the halo rows are
-    // still in flight), part 2 = only the rows outside it (after the halo wait); part 0 = every row
-    if (part != 0 && ((y >= ylo && y < yhi) != (part == 1))) continue;
     uint32_t seed = pixel_seed((uint32_t)x, (uint32_t)y, F.clock, PASS_SPATIAL0 + iteration);   // :58-59
     Res res = unpackReservoir(inR.info[idx], inR.weight[idx]);
     GInfo gi = ginfo_from_planes(cur, idx, F);
@@ -876,12 +873,12 @@ void launch_front_ris(cudaStream_t st, const GridDev& G, const LightsDev& L, con
   const bool big_tables = (size_t)L.nlights * 32 + (size_t)L.ntable * 16 > (size_t)64 * 1024;
   const bool vis = (F.flags & FLAG_VISIBILITY) != 0, temporal = (F.flags & FLAG_TEMPORAL) != 0;
   const int needs_finish = (vis || temporal) ? 1 : 0;
-  static const int g_thread = resident_grid(k_ris_thread<8>, 128, 8);
-  if (ris_env == 't') k_ris_thread<8><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, 0u);
+  static const int g_thread = resident_grid(k_ris_thread, 128, 8);
+  if (ris_env == 't') k_ris_thread<<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, 0u);
   else if (ris_env == 'c' || big_tables) k_ris_coop<<<ris_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, target_warps, 0xFFFFFFFFu);
   else {   // auto, small tables: the hit count (known only on the device) picks the form; the other launch returns at once
     k_ris_coop<<<ris_blocks, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, target_warps, small_launch);
-    k_ris_thread<8><<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
+    k_ris_thread<<<g_thread, 128, 0, st>>>(G, L, dF, cur, outR, Q, trace, store_y0, needs_finish, small_launch);
   }
   ktick(kt, st, "k_ris");
 }
@@ -914,12 +911,9 @@ int front_ris_launches(int flags, const LightsDev& L) {
 }
 int front_shadow_launches(int flags) { return (flags & FLAG_VISIBILITY) != 0 ? 1 : 0; }
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
-                    uint32_t iteration, uint32_t spatial_neighbors, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt) {
-  static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
-  static const int target_warps = sms * (getenv("VRS_MIN_WARPS_PER_SM") ? atoi(getenv("VRS_MIN_WARPS_PER_SM")) : MIN_WARPS_PER_SM);
-  static const int g8 = resident_grid(k_spatial_thread<8>, 128, 8);
-  (void)spatial_neighbors;
-  k_spatial_thread<8><<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1, part, ylo, yhi);
+                    uint32_t iteration, int store_y0, int store_y1, KTimer* kt) {
+  static const int g8 = resident_grid(k_spatial_thread, 128, 8);
+  k_spatial_thread<<<g8, 128, 0, s>>>(L, dF, cur, inR, outR, Q, iteration, store_y0, store_y1);
   ktick(kt, s, "k_spatial");
 }
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, ResPlanes rs,

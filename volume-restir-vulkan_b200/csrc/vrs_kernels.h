@@ -38,7 +38,7 @@ int front_ris_launches(int flags, const LightsDev& L);
 int front_shadow_launches(int flags);
 void launch_front_shadow(cudaStream_t st, const GridDev& G, const FrameParams& F, const Queues& Q, int persistent_blocks, KTimer* kt);
 void launch_spatial(cudaStream_t s, const LightsDev& L, const FrameParams* dF, Planes cur, ResPlanes inR, ResPlanes outR, const Queues& Q,
-                    uint32_t iteration, uint32_t spatial_neighbors, int store_y0, int store_y1, int persistent_blocks, int part, int ylo, int yhi, KTimer* kt);
+                    uint32_t iteration, int store_y0, int store_y1, KTimer* kt);
 void launch_shade(cudaStream_t s, const GridDev& G, const LightsDev& L, const FrameParams& F, const FrameParams* dF, Planes cur, ResPlanes rs,
                   float4* accum, int y0, int y1, int store_y0, KTimer* kt);
 void launch_halo_push(cudaStream_t s, const HaloPush& H, int blocks, KTimer* kt);
