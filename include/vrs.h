@@ -235,7 +235,8 @@ vrs_status vrs_comm_init(vrs_ctx* ctx, const uint8_t id128[128], int rank, int n
  * its per-pixel planes, the launcher all-gathers the blobs (any transport), every rank opens its two neighbours' planes
  * and from then on ONE kernel per exchange stores the boundary rows straight into the neighbours' halo rows over NVLink
  * and releases a system-scope flag; consumers acquire the flag in a one-thread wait kernel.  Being plain kernels, the
- * exchange is part of the captured CUDA graph of the frame. */
+ * exchange is part of the captured CUDA graph of the frame.  A context takes ONE transport, once: vrs_peer_connect or
+ * vrs_comm_init on a context that is already connected returns VRS_ERR_INVALID. */
 #define VRS_PEER_BLOB_BYTES 3200
 vrs_status vrs_peer_export(vrs_ctx* ctx, uint8_t blob[VRS_PEER_BLOB_BYTES]);
 vrs_status vrs_peer_connect(vrs_ctx* ctx, int rank, int nranks, const uint8_t* all_blobs /* nranks x VRS_PEER_BLOB_BYTES */);

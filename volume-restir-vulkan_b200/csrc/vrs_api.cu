@@ -286,6 +286,7 @@ void vrs_destroy(vrs_ctx* ctx) {
 // ------------------------------------------------------------------------------------------ grid staging
 static vrs_status upload_grid(vrs_ctx* ctx) {
   cudaSetDevice(ctx->device);
+  invalidate_graphs(ctx);   // frames in flight read the old tables, and captured stages point at them: drain, then drop
   free_grid(ctx);
   const HostGrid& h = ctx->host_grid;
   if (h.nleaf() == 0 && h.active_voxels == 0) return fail(ctx, VRS_ERR_FORMAT, "grid has no active voxels");
@@ -370,7 +371,6 @@ static vrs_status upload_grid(vrs_ctx* ctx) {
       cudaGetLastError();       // best effort: the window is an optimisation, never an error
     }
   }
-  invalidate_graphs(ctx);   // captured pointers are stale now
   ctx->has_grid = true;
   ctx->history_valid = false;   // the previous frame's G-buffer / reservoirs describe another volume
   return VRS_OK;
@@ -450,14 +450,16 @@ vrs_status vrs_grid_get_value(const vrs_ctx* ctx, int32_t i, int32_t j, int32_t 
 vrs_status vrs_grid_sample_device(vrs_ctx* ctx, const int32_t* ijk, uint32_t n, float* out) {
   if (!ctx || !ctx->has_grid || !ijk || !out) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
+  if (n == 0) return VRS_OK;
   int* d_ijk = nullptr; float* d_out = nullptr;
-  CK(cudaMalloc(&d_ijk, (size_t)n * 12)); CK(cudaMalloc(&d_out, (size_t)n * 4));
-  CK(cudaMemcpyAsync(d_ijk, ijk, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
-  launch_sample_density(ctx->stream, ctx->grid, d_ijk, n, d_out);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  cudaError_t e = cudaMalloc(&d_ijk, (size_t)n * 12);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * 4);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_ijk, ijk, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) { launch_sample_density(ctx->stream, ctx->grid, d_ijk, n, d_out); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(d_ijk); cudaFree(d_out);
+  if (e != cudaSuccess) { ctx->err = std::string("vrs_grid_sample_device: ") + cudaGetErrorString(e); return VRS_ERR_CUDA; }
   return VRS_OK;
 }
 
@@ -503,7 +505,8 @@ vrs_status vrs_vdb_emissive_lights(const char* vdb_path, const char* grid_name, 
                                    vrs_point_light* out, uint32_t* count) {
   if (!vdb_path || !cfg || !out || !count) return VRS_ERR_INVALID;
   HostGrid h; std::string err;
-  if (!read_vdb(vdb_path, grid_name, h, err)) return fail(nullptr, err.rfind("cannot open", 0) == 0 ? VRS_ERR_IO : VRS_ERR_FORMAT, err);
+  VRS_GUARD(nullptr,
+    if (!read_vdb(vdb_path, grid_name, h, err)) return fail(nullptr, err.rfind("cannot open", 0) == 0 ? VRS_ERR_IO : VRS_ERR_FORMAT, err);)
   const float A = (float)((double)cfg->world_scale * h.voxel_size);
   float B[3];
   for (int a = 0; a < 3; ++a) B[a] = (float)((double)cfg->world_scale * h.translation[a] + (double)cfg->world_translate[a]);
@@ -589,7 +592,7 @@ static vrs_status make_params(vrs_ctx* ctx, const vrs_global_uniforms* gu, const
 }
 
 // Per-frame values travel through device-resident FrameParams blocks (fed from a ring of pinned host slots), so the
-// kernels' launch arguments never change and the frame halves can be replayed as CUDA graphs.  Frame n uses block n % 2.
+// kernels' launch arguments never change and the frame's stages can be replayed as CUDA graphs.  Frame n uses block n % VRS_NQ.
 static vrs_status upload_params(vrs_ctx* ctx, const FrameParams& F, int q, cudaStream_t st) {
   const int slot = (int)(ctx->param_serial % VRS_PARAM_SLOTS);
   if (ctx->param_serial >= VRS_PARAM_SLOTS) CK(cudaEventSynchronize(ctx->param_ev[slot]));   // slot free again (normally long since)
@@ -1109,6 +1112,7 @@ vrs_status vrs_peer_export(vrs_ctx* ctx, uint8_t blob[VRS_PEER_BLOB_BYTES]) {
 vrs_status vrs_peer_connect(vrs_ctx* ctx, int rank, int nranks, const uint8_t* all_blobs) {
   if (!ctx || !all_blobs || rank < 0 || rank >= nranks) return VRS_ERR_INVALID;
   cudaSetDevice(ctx->device);
+  if (ctx->peer_mode || ctx->comm) return fail(ctx, VRS_ERR_INVALID, "context is already connected to its neighbours");
   if (nranks > 1 && ctx->band_y1 - ctx->band_y0 < (int)ctx->cfg.halo_rows)
     return fail(ctx, VRS_ERR_INVALID, "band shorter than halo_rows: halos are exchanged with adjacent ranks only");
   auto open_peer = [&](int r, vrs_ctx::Peer& P) -> vrs_status {
@@ -1142,6 +1146,7 @@ vrs_status vrs_comm_init(vrs_ctx* ctx, const uint8_t id128[128], int rank, int n
   cudaSetDevice(ctx->device);
   if (nranks > 1 && ctx->band_y1 - ctx->band_y0 < (int)ctx->cfg.halo_rows)
     return fail(ctx, VRS_ERR_INVALID, "band shorter than halo_rows: halos are exchanged with adjacent ranks only");
+  if (ctx->peer_mode || ctx->comm) return fail(ctx, VRS_ERR_INVALID, "context is already connected to its neighbours");
   std::string err;
   if (!ctx->comm_stream) CK(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
   ctx->comm = comm_create(id128, rank, nranks, err);
