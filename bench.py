@@ -468,7 +468,7 @@ def run_ours(args):
     pass_ms = {"initial": 0.0, "spatial": 0.0, "shade": 0.0, "exchange": 0.0}
     launches = 0
     R.setPassTiming(True)
-    probe = 20
+    probe = int(round(360.0 / ORBIT_DEG))          # one whole orbit: the average does not depend on where the timed blocks ended
     extend_inputs(probe + 2)
     barrier()
     for i in range(probe + 2):
@@ -486,13 +486,13 @@ def run_ours(args):
     # ---- per-kernel event times (frames launched kernel by kernel, one event after each kernel on the context stream)
     kernel_ms = {}
     R.setKernelTiming(True)
-    extend_inputs(14)
+    extend_inputs(probe + 2)
     barrier()
-    for i in range(14):
+    for i in range(probe + 2):                    # one whole orbit again
         step()
         if i >= 2:
             for name, ms in R.kernelTimes():
-                kernel_ms[name] = kernel_ms.get(name, 0.0) + ms / 12.0
+                kernel_ms[name] = kernel_ms.get(name, 0.0) + ms / float(probe)
     R.setKernelTiming(False)
     barrier()
     kernel_ms_ranks = None
